@@ -52,7 +52,7 @@ SIGNATURES = {
     "gymrl_sample_tanh_gaussian": (c_int, [_P, _P, c_int, _P, _P, _P, _P, c_int, c_int, c_float, c_float, c_float,
                                            c_u64, c_u64, c_u32, _P, c_int, _P]),
     "gymrl_add_gaussian_noise_clip": (c_int, [_P, _P, _P, c_int, c_int, c_float, c_float, c_float, c_u64, c_u64, c_u32, _P, _P]),
-    "gymrl_gae": (c_int, [_P] * 7 + [c_int, c_int, c_float, c_float, c_float, c_int, _P]),
+    "gymrl_gae": (c_int, [_P] * 7 + [c_int, c_int, c_double, c_double, c_double, c_int, _P]),
     "gymrl_sum_sumsq": (c_int, [_P, c_ll, _P, _P]),
     "gymrl_normalize_inplace": (c_int, [_P, c_ll, _P, c_double, c_int, c_float, _P]),
     "gymrl_ppo_loss": (c_int, [_P, c_int, _P, c_int, _P, _P, _P, _P, _P, _P, _P, _P, c_int, _P, c_int, _P, c_int, c_int, _P, _P]),
@@ -65,6 +65,7 @@ SIGNATURES = {
     "gymrl_polyak": (c_int, [_P, _P, c_ll, c_float, _P]),
     "gymrl_random_permutation": (c_int, [_P, c_int, c_u64, c_u32, _P, _P]),
     "gymrl_counter_add": (c_int, [_P, c_u32, _P]),
+    "gymrl_slice_i32": (c_int, [_P, _P, c_int, _P, _P]),
 }
 
 

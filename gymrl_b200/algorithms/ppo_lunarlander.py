@@ -1,0 +1,541 @@
+"""PPO for LunarLander-v3 on the B200 engine — same surface as the reference script
+``algorithms/ppo_lunarlander.py`` (Config, ActorCritic, RolloutBuffer, PPOTrainer with
+train()/eval()/test()/update()/collect_rollout()/compute_gae()), but every hot loop is a CUDA kernel
+behind the C ABI:
+
+    collect_rollout  (ref :198-231)  ->  T lockstep iterations over N env copies, captured as ONE CUDA graph:
+                                         5 dense-layer kernels -> categorical sample -> env step (auto-reset)
+    compute_gae      (ref :179-196)  ->  gymrl_gae (chunked fp64 scan over [T][N])
+    update           (ref :233-330)  ->  per minibatch (one captured graph, replayed epochs x minibatches times):
+                                         window of the device permutation -> forward (row gather fused) ->
+                                         fused loss/grad -> backward -> global-norm clip + Adam
+    LR anneal        (ref :337-341)  ->  host writes one float64 device scalar per update
+
+Vectorisation knobs are *extra* Config attributes whose defaults reproduce the reference at
+``num_envs = 1`` (T = update_freq = 2048 steps, 32 minibatches of 64, re-reset at every rollout):
+    num_envs, num_steps (= update_freq // num_envs), num_minibatches (= N*T // batch_size),
+    reset_each_rollout (= num_envs == 1), use_cuda_graph.
+Multi-GPU (one process per GPU): env shards by global env id, one NCCL sum-all-reduce of
+the flat gradient per optimizer step and a 3-scalar all-reduce for the advantage normalisation.
+"""
+from __future__ import annotations
+
+import signal
+import sys
+import time
+from collections import deque
+from typing import Optional, Tuple
+
+import numpy as np
+import torch
+import torch.nn as nn
+
+from .. import _ffi, ops
+from ..nn import FlatParams, FusedAdam, layer_init
+
+f32, i32, u8, f64 = torch.float32, torch.int32, torch.uint8, torch.float64
+
+
+class Config:
+    def __init__(self):
+        self.env_name = "LunarLander-v3"
+        self.seed = None
+
+        self.max_train_steps = 1_000_000
+        self.update_freq = 2048
+        self.num_epochs = 10
+        self.batch_size = 64
+
+        self.gamma = 0.99
+        self.gae_lambda = 0.95
+        self.clip_eps = 0.2
+        self.dual_clip = 3.0
+        self.entropy_coef = 0.01
+        self.value_coef = 0.5
+        self.max_grad_norm = 0.5
+
+        self.lr = 3e-4
+        self.anneal_lr = True
+
+        self.hidden_dim = 256
+
+        self.device = "cuda"  # there is no CPU path: the engine *is* the CUDA library
+
+        # ---- engine extras (defaults reproduce the reference at num_envs = 1) ----
+        self.num_envs = 1
+        self.num_steps = None
+        self.num_minibatches = None
+        self.reset_each_rollout = None
+        self.use_cuda_graph = True
+
+
+class ActorCritic(nn.Module):
+    """Same module tree / state_dict keys as the reference ActorCritic (ref :63-90)."""
+
+    def __init__(self, state_dim: int, action_dim: int, hidden_dim: int = 256):
+        super().__init__()
+        self.state_dim, self.action_dim, self.hidden_dim = state_dim, action_dim, hidden_dim
+        self.shared = nn.Sequential(
+            layer_init(nn.Linear(state_dim, hidden_dim)), nn.Tanh(),
+            layer_init(nn.Linear(hidden_dim, hidden_dim)), nn.Tanh())
+        self.actor = nn.Sequential(
+            layer_init(nn.Linear(hidden_dim, hidden_dim)), nn.Tanh(),
+            layer_init(nn.Linear(hidden_dim, action_dim), std=0.01))
+        self.critic = nn.Sequential(
+            layer_init(nn.Linear(hidden_dim, hidden_dim)), nn.Tanh(),
+            layer_init(nn.Linear(hidden_dim, 1), std=1.0))
+
+    # flat layout: the two head-trunk layers are adjacent so they run as one [2H, H] GEMM
+    PARAM_ORDER = ["shared.0.weight", "shared.0.bias", "shared.2.weight", "shared.2.bias",
+                   "actor.0.weight", "critic.0.weight", "actor.0.bias", "critic.0.bias",
+                   "actor.2.weight", "actor.2.bias", "critic.2.weight", "critic.2.bias"]
+
+    def to_engine(self, device) -> "ActorCriticEngine":
+        return ActorCriticEngine(self, device)
+
+
+class _Acts:
+    """Activation / gradient scratch for a fixed maximum batch M."""
+
+    def __init__(self, M: int, H: int, A: int, device, backward: bool):
+        self.M = M
+        self.h1 = torch.empty(M, H, device=device, dtype=f32)
+        self.h2 = torch.empty(M, H, device=device, dtype=f32)
+        self.ac = torch.empty(M, 2 * H, device=device, dtype=f32)
+        self.lv = torch.empty(M, 8, device=device, dtype=f32)  # [:, :A] logits, [:, A] value (A <= 7)
+        if backward:
+            self.dlv = torch.zeros(M, 8, device=device, dtype=f32)
+            self.dac = torch.empty(M, 2 * H, device=device, dtype=f32)
+            self.dh2 = torch.empty(M, H, device=device, dtype=f32)
+            self.dh1 = torch.empty(M, H, device=device, dtype=f32)
+
+
+class ActorCriticEngine:
+    """Forward / backward of ActorCritic through the C ABI dense-layer kernels."""
+
+    def __init__(self, model: ActorCritic, device):
+        self.model = model.to(device)
+        self.fp = FlatParams(self.model, ActorCritic.PARAM_ORDER, device)
+        self.H, self.A, self.D = model.hidden_dim, model.action_dim, model.state_dim
+        assert self.A <= 7
+        fp, H = self.fp, self.H
+        self.W1, self.b1 = fp.p("shared.0.weight"), fp.p("shared.0.bias")
+        self.W2, self.b2 = fp.p("shared.2.weight"), fp.p("shared.2.bias")
+        self.Wac = fp.span("actor.0.weight", "critic.0.weight", 2 * H, H)
+        self.bac = fp.span("actor.0.bias", "critic.0.bias", 1, 2 * H).view(2 * H)
+        self.Wa2, self.ba2 = fp.p("actor.2.weight"), fp.p("actor.2.bias")
+        self.Wc2, self.bc2 = fp.p("critic.2.weight"), fp.p("critic.2.bias")
+        self.gW1, self.gb1 = fp.g("shared.0.weight"), fp.g("shared.0.bias")
+        self.gW2, self.gb2 = fp.g("shared.2.weight"), fp.g("shared.2.bias")
+        self.gWac = fp.span("actor.0.weight", "critic.0.weight", 2 * H, H, grad=True)
+        self.gbac = fp.span("actor.0.bias", "critic.0.bias", 1, 2 * H, grad=True).view(2 * H)
+        self.gWa2, self.gba2 = fp.g("actor.2.weight"), fp.g("actor.2.bias")
+        self.gWc2, self.gbc2 = fp.g("critic.2.weight"), fp.g("critic.2.bias")
+        self.workspace = None
+
+    def alloc_workspace(self, M: int):
+        need = max(ops.backward_weight_workspace(M, 2 * self.H, self.H), ops.backward_weight_workspace(M, self.H, self.H),
+                   ops.backward_weight_workspace(M, self.H, self.D), ops.backward_weight_workspace(M, self.A, self.H))
+        self.workspace = torch.empty(need, device=self.fp.flat.device, dtype=torch.uint8)
+
+    def forward(self, x: torch.Tensor, acts: _Acts, M: int, row_index: Optional[torch.Tensor] = None):
+        """logits = acts.lv[:M, :A], value = acts.lv[:M, A]."""
+        T, H, A = _ffi.ACT_TANH, self.H, self.A
+        ops.linear_forward(x, self.W1, self.b1, T, row_index=row_index, out=acts.h1, M=M)
+        ops.linear_forward(acts.h1, self.W2, self.b2, T, out=acts.h2, M=M)
+        ops.linear_forward(acts.h2, self.Wac, self.bac, T, out=acts.ac, M=M)
+        ops.linear_forward(acts.ac[:, :H], self.Wa2, self.ba2, _ffi.ACT_NONE, out=acts.lv[:, :A], M=M)
+        ops.linear_forward(acts.ac[:, H:], self.Wc2, self.bc2, _ffi.ACT_NONE, out=acts.lv[:, A:A + 1], M=M)
+        return acts.lv
+
+    def backward(self, x: torch.Tensor, acts: _Acts, M: int, row_index: Optional[torch.Tensor] = None):
+        """Given acts.dlv[:M] = dL/d(logits, value), fill the flat gradient buffer."""
+        T, H, A, ws = _ffi.ACT_TANH, self.H, self.A, self.workspace
+        dl, dv = acts.dlv[:, :A], acts.dlv[:, A:A + 1]
+        ops.linear_backward_weight(dl, acts.ac[:, :H], self.gWa2, self.gba2, workspace=ws, M=M)
+        ops.linear_backward_weight(dv, acts.ac[:, H:], self.gWc2, self.gbc2, workspace=ws, M=M)
+        ops.linear_backward_input(dl[:M], self.Wa2, acts.ac[:, :H], T, out=acts.dac[:, :H])
+        ops.linear_backward_input(dv[:M], self.Wc2, acts.ac[:, H:], T, out=acts.dac[:, H:])
+        ops.linear_backward_weight(acts.dac, acts.h2, self.gWac, self.gbac, workspace=ws, M=M)
+        ops.linear_backward_input(acts.dac[:M], self.Wac, acts.h2, T, out=acts.dh2)
+        ops.linear_backward_weight(acts.dh2, acts.h1, self.gW2, self.gb2, workspace=ws, M=M)
+        ops.linear_backward_input(acts.dh2[:M], self.W2, acts.h1, T, out=acts.dh1)
+        ops.linear_backward_weight(acts.dh1, x, self.gW1, self.gb1, row_index=row_index, workspace=ws, M=M)
+
+
+class RolloutBuffer:
+    """Device-resident [T][N] SoA rollout store (ref RolloutBuffer :120-154 keeps Python lists).
+    obs rows are 32 B ([T+1][N][8]) so the env kernel writes coalesced lines and the minibatch gather
+    touches exactly one sector per sample."""
+
+    def __init__(self, T: int, N: int, D: int, device):
+        self.T, self.N, self.D = T, N, D
+        self.obs = torch.zeros(T + 1, N, D, device=device, dtype=f32)
+        self.action = torch.zeros(T, N, device=device, dtype=i32)
+        self.log_prob = torch.zeros(T, N, device=device, dtype=f32)
+        self.value = torch.zeros(T, N, device=device, dtype=f32)
+        self.reward = torch.zeros(T, N, device=device, dtype=f32)
+        self.done = torch.zeros(T, N, device=device, dtype=u8)
+        self.v_last = torch.zeros(N, device=device, dtype=f32)
+        self.adv = torch.zeros(T, N, device=device, dtype=f32)
+        self.ret = torch.zeros(T, N, device=device, dtype=f32)
+        self.filled = 0
+
+    # list-like views for code written against the reference buffer
+    @property
+    def states(self): return self.obs[:self.filled].reshape(-1, self.D)
+    @property
+    def actions(self): return self.action[:self.filled].reshape(-1)
+    @property
+    def log_probs(self): return self.log_prob[:self.filled].reshape(-1)
+    @property
+    def values(self): return self.value[:self.filled].reshape(-1)
+    @property
+    def rewards(self): return self.reward[:self.filled].reshape(-1)
+    @property
+    def dones(self): return self.done[:self.filled].reshape(-1)
+
+    def clear(self):
+        self.filled = 0
+
+    def __len__(self) -> int:
+        return self.filled * self.N
+
+
+def _dist_info():
+    import torch.distributed as dist
+    if dist.is_available() and dist.is_initialized():
+        return dist.get_rank(), dist.get_world_size()
+    return 0, 1
+
+
+class PPOTrainer:
+    def __init__(self, config: Config):
+        _ffi.require_cuda()
+        self.cfg = cfg = config
+        self.device = torch.device("cuda", torch.cuda.current_device())
+        self.rank, self.world = _dist_info()
+        N = int(cfg.num_envs)
+        T = int(cfg.num_steps) if cfg.num_steps else max(1, int(cfg.update_freq) // N)
+        self.N, self.T = N, T
+        self.n_mb = int(cfg.num_minibatches) if cfg.num_minibatches else max(1, (N * T) // int(cfg.batch_size))
+        assert (N * T) % self.n_mb == 0, "rollout size must be divisible by the number of minibatches"
+        self.mb = (N * T) // self.n_mb
+        self.reset_each_rollout = (N == 1) if cfg.reset_each_rollout is None else bool(cfg.reset_each_rollout)
+        self.seed = int(cfg.seed) if cfg.seed is not None else int(time.time_ns() & 0x7FFFFFFF)
+
+        self.env = ops.VecEnv(cfg.env_name, N, seed=self.seed, first_env_id=self.rank * N)
+        state_dim, action_dim = self.env.obs_dim, self.env.n_actions
+        self.model = ActorCritic(state_dim, action_dim, cfg.hidden_dim)
+        if self.world > 1:  # identical replicas: rank 0's initialisation everywhere
+            import torch.distributed as dist
+            for p in self.model.parameters():
+                t = p.data.to(self.device)
+                dist.broadcast(t, 0)
+                p.data = t
+        self.net = self.model.to_engine(self.device)
+        self.optimizer = FusedAdam(self.net.fp, lr=cfg.lr, eps=1e-5)
+        self.buffer = RolloutBuffer(T, N, state_dim, self.device)
+        self.acts_roll = _Acts(N, cfg.hidden_dim, action_dim, self.device, backward=False)
+        self.acts_mb = _Acts(self.mb, cfg.hidden_dim, action_dim, self.device, backward=True)
+        self.net.alloc_workspace(self.mb)
+        self.perm = torch.zeros(N * T, device=self.device, dtype=i32)
+        self.idx_mb = torch.zeros(self.mb, device=self.device, dtype=i32)
+        self.metrics = torch.zeros(8, device=self.device, dtype=f32)
+        self.adv_sums = torch.zeros(3, device=self.device, dtype=f64)  # sum, sumsq, count
+        self.ctr_action = torch.zeros(1, device=self.device, dtype=i32)   # draw counter: action sampling
+        self.ctr_perm = torch.zeros(1, device=self.device, dtype=i32)     # draw counter: permutations
+        self.ctr_mb = torch.zeros(1, device=self.device, dtype=i32)       # minibatch window within the epoch
+        self.term = torch.zeros(N, device=self.device, dtype=u8)
+        self.trunc = torch.zeros(N, device=self.device, dtype=u8)
+        self.loss_cfg = _ffi.PPOCfg(mode=_ffi.PPO_DUALCLIP, clip_eps_min=cfg.clip_eps, clip_eps_max=cfg.clip_eps,
+                                    dual_clip=cfg.dual_clip, value_coef=cfg.value_coef, entropy_coef=cfg.entropy_coef)
+        self.step_count = 0
+        self.episode_rewards = deque(maxlen=100)
+        self._episodes_seen = 0
+        self._g_roll = None
+        self._g_mb = None
+        self._g_mb_bwd = None
+        self._g_opt = None
+        self._started = False
+        self.graph_launches = 0   # kernels launched through graph replays (native launch_count() sees eager calls only)
+        if self.rank == 0:
+            print(f"Device: {self.device} ({torch.cuda.get_device_name(self.device)})")
+            print(f"State dim: {state_dim}, Action dim: {action_dim}")
+            print(f"Model parameters: {sum(p.numel() for p in self.model.parameters()):,}")
+            print(f"Envs: {N} x {self.world} GPU(s), rollout {T} steps, {self.n_mb} minibatches of {self.mb}")
+
+    # ---------------------------------------------------------------- rollout
+    def _rollout_body(self):
+        buf, env, net, acts = self.buffer, self.env, self.net, self.acts_roll
+        N, A = self.N, self.env.n_actions
+        for t in range(self.T):
+            net.forward(buf.obs[t], acts, N)
+            ops.sample_categorical(acts.lv[:, :A], seed=self.seed, first_id=self.rank * N, draw_base=self.ctr_action,
+                                   action=buf.action[t], logp=buf.log_prob[t], value_in=acts.lv[:, A:A + 1],
+                                   value_out=buf.value[t])
+            ops.counter_add(self.ctr_action, 1)
+            env.step(buf.action[t], obs=buf.obs[t + 1], reward=buf.reward[t], terminated=self.term, truncated=self.trunc,
+                     want_next_obs=False, done=buf.done[t])
+        net.forward(buf.obs[self.T], acts, N)
+        buf.v_last.copy_(acts.lv[:, A])
+
+    def collect_rollout(self):
+        """T lockstep steps of all N envs (ref collect_rollout :198-231). Returns the bootstrap values [N]."""
+        buf = self.buffer
+        buf.clear()
+        if self.cfg.use_cuda_graph and self._g_roll is None:
+            # graph capture needs one eager warm-up pass; it is a real rollout (env + RNG advance) whose
+            # transitions are dropped, exactly like the in-flight episode the reference drops at :200
+            if not self._started:
+                self.env.reset(out=buf.obs[0])
+                self._started = True
+            self._g_roll = self._capture(self._rollout_body)
+        if self.reset_each_rollout or not self._started:
+            self.env.reset(out=buf.obs[0])
+            self._started = True
+        else:
+            buf.obs[0].copy_(buf.obs[self.T])
+        if self.cfg.use_cuda_graph:
+            self._replay(self._g_roll)
+        else:
+            self._rollout_body()
+        buf.filled = self.T
+        self.step_count += self.N * self.T * self.world
+        return buf.v_last
+
+    # ---------------------------------------------------------------- GAE
+    def compute_gae(self, next_value=None) -> Tuple[torch.Tensor, torch.Tensor]:
+        """gymrl_gae over the [T][N] buffer (ref compute_gae :179-196).  Returns (advantages, returns) [T, N]."""
+        buf = self.buffer
+        if next_value is not None:
+            nv = torch.as_tensor(next_value, dtype=f32, device=self.device).reshape(-1)
+            buf.v_last.copy_(nv.expand(self.N) if nv.numel() == 1 else nv)
+        ops.gae(buf.reward, buf.value, buf.v_last, buf.done, self.cfg.gamma, self.cfg.gae_lambda, adv=buf.adv, ret=buf.ret)
+        return buf.adv, buf.ret
+
+    # ---------------------------------------------------------------- update
+    def _fwd_bwd_body(self):
+        buf, net, acts = self.buffer, self.net, self.acts_mb
+        A, M = self.env.n_actions, self.mb
+        obs_flat = buf.obs[:self.T].view(self.T * self.N, -1)
+        ops.slice_i32(self.idx_mb, self.perm, self.ctr_mb)
+        ops.counter_add(self.ctr_mb, 1)
+        net.forward(obs_flat, acts, M, row_index=self.idx_mb)
+        ops.ppo_loss(acts.lv[:, :A], acts.lv[:, A:A + 1], buf.action.view(-1), buf.log_prob.view(-1), buf.adv.view(-1),
+                     buf.ret.view(-1), self.loss_cfg, row_index=self.idx_mb, dlogits=acts.dlv[:, :A],
+                     dvalue=acts.dlv[:, A:A + 1], metrics=self.metrics)
+        net.backward(obs_flat, acts, M, row_index=self.idx_mb)
+
+    def _opt_body(self):
+        self.optimizer.launch(max_norm=self.cfg.max_grad_norm, grad_scale=1.0 / self.world)
+
+    def _minibatch_body(self):
+        self._fwd_bwd_body()
+        self._opt_body()
+
+    def _capture(self, fn):
+        torch.cuda.synchronize()
+        s = torch.cuda.Stream()
+        s.wait_stream(torch.cuda.current_stream())
+        with torch.cuda.stream(s):
+            fn()  # warm-up outside capture (first-launch module loads)
+        torch.cuda.current_stream().wait_stream(s)
+        torch.cuda.synchronize()
+        g = torch.cuda.CUDAGraph()
+        c0 = _ffi.launch_count()
+        with torch.cuda.graph(g):
+            fn()
+        g.n_kernels = _ffi.launch_count() - c0   # our kernels recorded in this graph (one launch call each)
+        return g
+
+    def _replay(self, g):
+        g.replay()
+        self.graph_launches += g.n_kernels
+
+    def _snapshot(self):
+        return {"flat": self.net.fp.flat.clone(), "m": self.optimizer.exp_avg.clone(), "v": self.optimizer.exp_avg_sq.clone(),
+                "step": self.optimizer.step_t.clone(), "ctr_mb": self.ctr_mb.clone(), "ctr_action": self.ctr_action.clone(),
+                "metrics": self.metrics.clone()}
+
+    def _restore(self, s):
+        self.net.fp.flat.copy_(s["flat"]); self.optimizer.exp_avg.copy_(s["m"]); self.optimizer.exp_avg_sq.copy_(s["v"])
+        self.optimizer.step_t.copy_(s["step"]); self.ctr_mb.copy_(s["ctr_mb"]); self.ctr_action.copy_(s["ctr_action"])
+        self.metrics.copy_(s["metrics"])
+
+    def _ensure_update_graphs(self):
+        if not self.cfg.use_cuda_graph or self._g_mb is not None or self._g_mb_bwd is not None:
+            return
+        snap = self._snapshot()  # capture warm-ups execute real steps: undo them
+        if self.world == 1:
+            self._g_mb = self._capture(self._minibatch_body)
+        else:
+            self._g_mb_bwd = self._capture(self._fwd_bwd_body)
+            self._g_opt = self._capture(self._opt_body)
+        self._restore(snap)
+
+    def total_launches(self) -> int:
+        return _ffi.launch_count() + self.graph_launches
+
+    def update(self, next_value=None, read_metrics: bool = True) -> dict:
+        cfg, buf = self.cfg, self.buffer
+        adv, _ = self.compute_gae(next_value)
+        # advantage normalisation, numpy semantics (ddof = 0, ref :236); global over all shards
+        self.adv_sums.zero_()
+        ops.sum_sumsq(adv, self.adv_sums[:2])
+        count = float(adv.numel())
+        if self.world > 1:
+            import torch.distributed as dist
+            self.adv_sums[2] = count
+            dist.all_reduce(self.adv_sums)
+            count = float(adv.numel() * self.world)
+        ops.normalize_inplace(adv, self.adv_sums, count, ddof=0, eps=1e-8)
+
+        self.optimizer.sync_lr()
+        self._ensure_update_graphs()
+        self.metrics.zero_()
+        for _ in range(cfg.num_epochs):
+            ops.random_permutation(self.N * self.T, seed=self.seed + 7919 * self.rank, draw_base=self.ctr_perm, out=self.perm)
+            ops.counter_add(self.ctr_perm, 1)
+            self.ctr_mb.zero_()
+            for _ in range(self.n_mb):
+                if self.world == 1:
+                    if self._g_mb is not None:
+                        self._replay(self._g_mb)
+                    else:
+                        self._minibatch_body()
+                else:
+                    import torch.distributed as dist
+                    if self._g_mb_bwd is not None:
+                        self._replay(self._g_mb_bwd)
+                    else:
+                        self._fwd_bwd_body()
+                    dist.all_reduce(self.net.fp.grad)  # the one collective of the path (sum; Adam rescales by 1/world)
+                    if self._g_opt is not None:
+                        self._replay(self._g_opt)
+                    else:
+                        self._opt_body()
+        if not read_metrics:
+            return {}
+        m = self.metrics.tolist()  # the single D2H of the update (ref: 5 .item() per minibatch, :309-322)
+        k = max(m[7], 1.0)
+        return {"policy_loss": m[0] / k, "value_loss": m[1] / k, "entropy": m[2] / k, "clip_frac": m[3] / k,
+                "approx_kl": m[4] / k}
+
+    # ---------------------------------------------------------------- train / eval / test
+    def _anneal(self):
+        if self.cfg.anneal_lr:
+            frac = 1.0 - self.step_count / self.cfg.max_train_steps
+            lr = self.cfg.lr * frac
+            for group in self.optimizer.param_groups:
+                group["lr"] = lr
+
+    def _refresh_episode_rewards(self):
+        mean_ret, _, total = self.env.episode_stats(100)
+        if total > self._episodes_seen:
+            self._episodes_seen = total
+            self.episode_rewards.clear()
+            self.episode_rewards.extend([mean_ret] * int(min(total, 100)))
+        return mean_ret, total
+
+    def train_iteration(self):
+        """One pass of the public training loop body (ref train() :336-346): LR anneal (one 8-byte H2D when the
+        value changes), rollout, update, metrics + episode statistics read back to the host."""
+        self._anneal()
+        self.collect_rollout()
+        metrics = self.update(None)
+        avg_reward, total = self._refresh_episode_rewards()
+        return metrics, avg_reward, total
+
+    def train(self):
+        if self.rank == 0:
+            print("Starting training...")
+        update_count = 0
+        t0 = time.time()
+        while self.step_count < self.cfg.max_train_steps:
+            self._anneal()
+            next_value = self.collect_rollout()
+            metrics = self.update(None)
+            update_count += 1
+            avg_reward, total = self._refresh_episode_rewards()
+            if total > 0 and self.rank == 0:
+                sps = self.step_count / max(time.time() - t0, 1e-9)
+                print(f"Step: {self.step_count:,} | Updates: {update_count} | Avg Reward: {avg_reward:.1f} | "
+                      f"Policy Loss: {metrics['policy_loss']:.4f} | Value Loss: {metrics['value_loss']:.4f} | "
+                      f"Entropy: {metrics['entropy']:.4f} | KL: {metrics['approx_kl']:.4f} | "
+                      f"Clip: {metrics['clip_frac']:.2%} | {sps:,.0f} steps/s")
+            if total >= 100 and avg_reward >= 200.0:
+                if self.rank == 0:
+                    print(f"\nEnvironment solved at step {self.step_count:,}!")
+                break
+        if self.rank == 0:
+            print("Training completed!")
+
+    @torch.no_grad()
+    def select_action(self, state, deterministic: bool = False):
+        """Single-observation convenience path (ref get_action :92-104) through the same kernels."""
+        x = torch.as_tensor(np.asarray(state, dtype=np.float32), device=self.device).reshape(1, -1)
+        acts = getattr(self, "_acts_one", None)
+        if acts is None:
+            acts = self._acts_one = _Acts(1, self.cfg.hidden_dim, self.env.n_actions, self.device, backward=False)
+        A = self.env.n_actions
+        self.net.forward(x, acts, 1)
+        a, lp, _ = ops.sample_categorical(acts.lv[:, :A], seed=self.seed, first_id=1 << 40, draw_base=self.ctr_action,
+                                          deterministic=deterministic)
+        ops.counter_add(self.ctr_action, 1)
+        return int(a.item()), float(lp.item()), float(acts.lv[0, A].item())
+
+    def eval(self, num_episodes: int = 10):
+        """Deterministic (argmax) episodes, one env copy per episode, stepped in lockstep (ref eval :368-399)."""
+        print(f"\nEvaluating for {num_episodes} episodes...")
+        env = ops.VecEnv(self.cfg.env_name, num_episodes, seed=self.seed + 12345, first_env_id=1 << 32)
+        acts = _Acts(num_episodes, self.cfg.hidden_dim, env.n_actions, self.device, backward=False)
+        A = env.n_actions
+        obs = env.reset()
+        action = torch.zeros(num_episodes, device=self.device, dtype=i32)
+        logp = torch.zeros(num_episodes, device=self.device, dtype=f32)
+        ret = torch.zeros(num_episodes, device=self.device, dtype=f64)
+        alive = torch.ones(num_episodes, device=self.device, dtype=torch.bool)
+        for _ in range(env.max_episode_steps):
+            self.net.forward(obs, acts, num_episodes)
+            ops.sample_categorical(acts.lv[:, :A], deterministic=True, action=action, logp=logp)
+            obs, r, term, trunc, _ = env.step(action, want_next_obs=False)
+            ret += torch.where(alive, r.double(), torch.zeros_like(ret))  # logging glue only
+            alive &= ~((term | trunc).bool())
+            if not bool(alive.any()):
+                break
+        rewards = ret.tolist()
+        for i, r in enumerate(rewards):
+            print(f"  Episode {i + 1}: Reward = {r:.1f}")
+        print(f"Evaluation Results: Mean = {np.mean(rewards):.1f} +/- {np.std(rewards):.1f}")
+        env.close()
+        return rewards
+
+    def test(self):
+        self.eval(num_episodes=5)
+        print("\n(visual test skipped: the device env has no renderer)")
+
+
+def main():
+    config = Config()
+    config.num_envs = 4096
+    config.num_steps = 128
+    config.num_minibatches = 32
+    config.max_train_steps = 50_000_000
+    trainer = PPOTrainer(config)
+
+    def signal_handler(signum, frame):
+        print("\n\nTraining interrupted. Starting test...")
+        trainer.test()
+        sys.exit(0)
+
+    signal.signal(signal.SIGINT, signal_handler)
+    try:
+        trainer.train()
+    except KeyboardInterrupt:
+        print("\nTraining interrupted.")
+    trainer.test()
+
+
+if __name__ == "__main__":
+    main()

@@ -21,26 +21,33 @@ void gymrl_count_launch(int n = 1);
 __global__ void __launch_bounds__(32 * GAE_MAX_WARPS)
 gae_scan_kernel(const float* __restrict__ reward, const float* __restrict__ value, const float* __restrict__ v_last,
                 const uint8_t* __restrict__ done, float* __restrict__ adv, float* __restrict__ ret, int T, int N,
-                double gamma, double lam_a, double lam_c, int two_streams) {
+                double gamma, double lam_a, double lam_c, int two_streams, int coef_f32, int boot_f32) {
     __shared__ double sC[2][GAE_MAX_WARPS][32], sD[2][GAE_MAX_WARPS][32];
     const int lane = threadIdx.x & 31, w = threadIdx.x >> 5, W = blockDim.x >> 5;
     const int n = blockIdx.x * 32 + lane;
     const bool valid = n < N;
     const int chunk = (T + W - 1) / W;
     const int t0 = w * chunk, t1 = min(T, t0 + chunk);
+    // NumPy >= 2 (NEP 50) rounding of the reference loops, see the dialect notes in include/gymrl.h:
+    //  coef_f32: gamma*lam*(1-d) is a float32 scalar (ppo_lunarlander.py:181 makes `dones` float32)
+    //  boot_f32: gamma*V_{t+1} is a float32 product (ppo_full stores values as 0-dim float32 tensors)
+    const double gla = coef_f32 ? (double)(float)(gamma * lam_a) : gamma * lam_a;
+    const double glc = coef_f32 ? (double)(float)(gamma * lam_c) : gamma * lam_c;
+    const float gamma_f = (float)gamma;
     // pass 1: fold the chunk backwards into (C, D) for both lambda streams
     double Ca = 1.0, Da = 0.0, Cc = 1.0, Dc = 0.0;
     if (valid) {
         for (int t = t1 - 1; t >= t0; --t) {
             const size_t k = (size_t)t * N + n;
             const double nd = 1.0 - (double)done[k];
-            const double vn = (t == T - 1) ? (double)v_last[n] : (double)value[k + N];
-            const double delta = (double)reward[k] + gamma * vn * nd - (double)value[k];
-            const double ca = gamma * lam_a * nd;
+            const float vnf = (t == T - 1) ? v_last[n] : value[k + N];
+            const double boot = boot_f32 ? (double)(gamma_f * vnf) : gamma * (double)vnf;
+            const double delta = (double)reward[k] + boot * nd - (double)value[k];
+            const double ca = gla * nd;
             Da = delta + ca * Da;
             Ca = ca * Ca;
             if (two_streams) {
-                const double cc = gamma * lam_c * nd;
+                const double cc = glc * nd;
                 Dc = delta + cc * Dc;
                 Cc = cc * Cc;
             }
@@ -61,11 +68,12 @@ gae_scan_kernel(const float* __restrict__ reward, const float* __restrict__ valu
         for (int t = t1 - 1; t >= t0; --t) {
             const size_t k = (size_t)t * N + n;
             const double nd = 1.0 - (double)done[k];
-            const double vn = (t == T - 1) ? (double)v_last[n] : (double)value[k + N];
+            const float vnf = (t == T - 1) ? v_last[n] : value[k + N];
+            const double boot = boot_f32 ? (double)(gamma_f * vnf) : gamma * (double)vnf;
             const double v = (double)value[k];
-            const double delta = (double)reward[k] + gamma * vn * nd - v;
-            Aa = delta + gamma * lam_a * nd * Aa;
-            if (two_streams) Ac = delta + gamma * lam_c * nd * Ac;
+            const double delta = (double)reward[k] + boot * nd - v;
+            Aa = delta + gla * nd * Aa;
+            if (two_streams) Ac = delta + glc * nd * Ac;
             else Ac = Aa;
             adv[k] = (float)Aa;
             ret[k] = (float)(Ac + v);
@@ -95,22 +103,22 @@ __global__ void gae_utils_kernel(const float* __restrict__ reward, const float* 
 }
 
 extern "C" int gymrl_gae(const float* d_reward, const float* d_value, const float* d_v_last_or_next, const uint8_t* d_done,
-                         const uint8_t* d_dw, float* d_adv, float* d_ret, int T, int N, float gamma, float lam_actor,
-                         float lam_critic, int dialect, void* stream) {
+                         const uint8_t* d_dw, float* d_adv, float* d_ret, int T, int N, double gamma, double lam_actor,
+                         double lam_critic, int dialect, void* stream) {
     GYMRL_REQUIRE(d_reward && d_value && d_v_last_or_next && d_done && d_adv && d_ret, "NULL pointer");
     GYMRL_REQUIRE(T > 0 && N > 0, "bad shape T=%d N=%d", T, N);
     cudaStream_t s = as_stream(stream);
-    if (dialect == 0) {
+    if (dialect == 0 || dialect == 2) {
         int W = GAE_MAX_WARPS;
         while (W > 1 && T < 8 * W) W >>= 1;
         const int two = lam_actor != lam_critic;
         gae_scan_kernel<<<ceil_div(N, 32), 32 * W, 0, s>>>(d_reward, d_value, d_v_last_or_next, d_done, d_adv, d_ret, T, N,
-                                                           (double)gamma, (double)lam_actor, (double)lam_critic, two);
+                                                           gamma, lam_actor, lam_critic, two, dialect == 0, dialect == 2);
     } else if (dialect == 1) {
         // float32(gamma * lamda): the Python-float product is rounded once when it meets the f32 array
-        const float gl = (float)((double)gamma * (double)lam_actor);
+        const float gl = (float)(gamma * lam_actor);
         gae_utils_kernel<<<ceil_div(N, 128), 128, 0, s>>>(d_reward, d_value, d_v_last_or_next, d_done, d_dw, d_adv, d_ret, T,
-                                                         N, gamma, gl);
+                                                         N, (float)gamma, gl);
     } else {
         GYMRL_FAIL(GYMRL_EINVAL, "unknown GAE dialect %d", dialect);
     }

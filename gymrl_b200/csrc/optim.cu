@@ -158,3 +158,18 @@ extern "C" int gymrl_counter_add(uint32_t* d_counter, uint32_t inc, void* stream
     GYMRL_LAUNCH_CHECK("counter_add");
     return GYMRL_OK;
 }
+
+// dst[i] = src[block * n + i], block read from device memory: lets one captured minibatch graph walk
+// through the epoch's permutation (replaces indices[start:end], algorithms/ppo_lunarlander.py:264-266).
+__global__ void slice_i32_kernel(int32_t* __restrict__ dst, const int32_t* __restrict__ src, int n,
+                                 const uint32_t* __restrict__ block) {
+    const int i = blockIdx.x * blockDim.x + threadIdx.x;
+    if (i < n) dst[i] = src[(size_t)(*block) * n + i];
+}
+extern "C" int gymrl_slice_i32(int32_t* d_dst, const int32_t* d_src, int n, const uint32_t* d_block_index, void* stream) {
+    GYMRL_REQUIRE(d_dst && d_src && d_block_index && n > 0, "bad arguments");
+    slice_i32_kernel<<<ceil_div(n, 256), 256, 0, as_stream(stream)>>>(d_dst, d_src, n, d_block_index);
+    gymrl_count_launch();
+    GYMRL_LAUNCH_CHECK("slice_i32");
+    return GYMRL_OK;
+}

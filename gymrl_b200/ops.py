@@ -268,3 +268,9 @@ def random_permutation(n, *, seed=0, draw=0, draw_base=None, out=None, device=No
 
 def counter_add(counter, inc=1):
     check(load().gymrl_counter_add(ptr(counter, i32), int(inc), stream_ptr()))
+
+
+def slice_i32(dst, src, block_index):
+    """dst[:] = src[block*n:(block+1)*n] with `block` a device int32 scalar."""
+    check(load().gymrl_slice_i32(ptr(dst, i32), ptr(src, i32), dst.numel(), ptr(block_index, i32), stream_ptr()))
+    return dst

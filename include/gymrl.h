@@ -120,9 +120,12 @@ int gymrl_add_gaussian_noise_clip(const float* d_mu, const float* d_noise, float
 
 /* ------------------------------------------------------------------------------------------------
  * GAE / returns
- * dialect 0 ("algorithms"): PPOTrainer.compute_gae, algorithms/ppo_lunarlander.py:179-196 and
- *   compute_advantages, ppo_full_lunarlander.py:507-535: done masks bootstrap and trace,
- *   V_{T} = v_last[N]; lam_actor / lam_critic decoupled (ret = A(lam_critic) + V).
+ * dialect 0 ("algorithms"): PPOTrainer.compute_gae, algorithms/ppo_lunarlander.py:179-196: done masks
+ *   bootstrap and trace, V_{T} = v_last[N].  float64 recurrence; `dones` is a float32 array there, so under
+ *   NumPy >= 2 the trace coefficient gamma*lam*(1-d) is rounded to float32 before use — reproduced.
+ * dialect 2 ("ppo_full"): compute_advantages, ppo_full_lunarlander.py:507-535: same masking, decoupled
+ *   lam_actor / lam_critic (ret = A(lam_critic) + V), float64 coefficient, but `values` are 0-dim float32
+ *   tensors so gamma*V_{t+1} is a float32 product — reproduced.
  * dialect 1 ("utils"): ReplayBuffer_on_policy.compute_advantage, utils/buffer.py:21-35:
  *   bootstrap masked by dw (terminated), trace by done, per-step next values v_next[T][N].
  * All arrays are [T][N] (time-major); fp32 in/out, fp64 internal recurrence (the reference runs
@@ -130,7 +133,7 @@ int gymrl_add_gaussian_noise_clip(const float* d_mu, const float* d_noise, float
  * ---------------------------------------------------------------------------------------------- */
 int gymrl_gae(const float* d_reward, const float* d_value, const float* d_v_last_or_next,
               const uint8_t* d_done, const uint8_t* d_dw, float* d_adv, float* d_ret, int T, int N,
-              float gamma, float lam_actor, float lam_critic, int dialect, void* stream);
+              double gamma, double lam_actor, double lam_critic, int dialect, void* stream);
 
 /* sums[0] += sum(x), sums[1] += sum(x^2)  (float64 accumulators on device; zero them first).
  * Multi-GPU runs all-reduce `sums` (+count) before normalising. */
@@ -224,6 +227,9 @@ int gymrl_random_permutation(int32_t* d_perm, int n, uint64_t seed, uint32_t dra
 /* *d_counter += inc (device-resident draw / minibatch counters so that captured CUDA graphs advance
  * their RNG streams on every replay). */
 int gymrl_counter_add(uint32_t* d_counter, uint32_t inc, void* stream);
+/* dst[i] = src[(*d_block_index) * n + i], i < n: the minibatch window indices[start:end] of
+ * algorithms/ppo_lunarlander.py:264-266 with the window number resident on the device. */
+int gymrl_slice_i32(int32_t* d_dst, const int32_t* d_src, int n, const uint32_t* d_block_index, void* stream);
 
 #ifdef __cplusplus
 }

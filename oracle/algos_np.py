@@ -1,0 +1,153 @@
+"""NumPy restatements of the learner-side arithmetic of the reference hot path.  TEST INFRASTRUCTURE.
+
+Pinned against tests/golden/*.npz (outputs of the reference's own classes, see oracle/make_golden.py)
+by the `not gpu` tests; the GPU parity tests then compare the CUDA kernels with these functions on
+other seeds / sizes.  Each function cites the reference lines it restates.
+"""
+import numpy as np
+
+
+# ---- GAE (algorithms/ppo_lunarlander.py:179-196; ppo_full_lunarlander.py:507-535) --------------------------
+def gae_algorithms(reward, value, v_last, done, gamma, lam_actor, lam_critic=None, coef_f32=True, boot_f32=False):
+    """[T, N] arrays; float64 recurrence exactly as the reference loop; returns (adv_actor, returns) float64.
+
+    coef_f32: ppo_lunarlander.py builds `dones` as a float32 array (:181), so under NumPy >= 2 (NEP 50, the
+    version in this image) the trace coefficient `gamma * lam * (1 - dones[t])` is a *float32* scalar before it
+    multiplies the float64 `last_gae`.  ppo_full keeps `dones` boolean (:510), so its coefficient stays float64
+    (coef_f32=False) - but it stores `values` as 0-dim float32 tensors, so np.array(values) is float32 and
+    `gamma * values[t + 1]` is a float32 product (boot_f32=True)."""
+    lam_critic = lam_actor if lam_critic is None else lam_critic
+    reward = np.asarray(reward, np.float64); value = np.asarray(value, np.float64)
+    T = reward.shape[0]
+    vals = np.concatenate([value, np.asarray(v_last, np.float64)[None]], axis=0)
+    nd = 1.0 - np.asarray(done, np.float64)
+    adv_a = np.zeros_like(reward); adv_c = np.zeros_like(reward)
+    la = np.zeros_like(reward[0]); lc = np.zeros_like(reward[0])
+    for t in reversed(range(T)):
+        boot = gamma * vals[t + 1]
+        if boot_f32:
+            boot = (np.float32(gamma) * vals[t + 1].astype(np.float32)).astype(np.float64)
+        delta = reward[t] + boot * nd[t] - vals[t]
+        ca, cc = gamma * lam_actor * nd[t], gamma * lam_critic * nd[t]
+        if coef_f32:
+            ca, cc = ca.astype(np.float32).astype(np.float64), cc.astype(np.float32).astype(np.float64)
+        adv_a[t] = la = delta + ca * la
+        adv_c[t] = lc = delta + cc * lc
+    return adv_a, adv_c + vals[:-1]
+
+
+# ---- GAE, utils dialect (utils/buffer.py:21-35): float32 recurrence --------------------------------------
+def gae_utils(reward, value, next_value, done, dw, gamma, lamda):
+    f = np.float32
+    reward, value, next_value = (np.asarray(x, f) for x in (reward, value, next_value))
+    done, dw = np.asarray(done, f), np.asarray(dw, f)
+    td = (reward + (f(gamma) * next_value) * (f(1) - dw)) - value
+    T = reward.shape[0]
+    adv = np.zeros_like(reward)
+    gl = f(gamma * lamda)
+    gae = None
+    for t in reversed(range(T)):
+        gae = td[t] if gae is None else (gl * gae) * (f(1) - done[t]) + td[t]
+        adv[t] = gae
+    return adv, adv + value
+
+
+# ---- Categorical (algorithms/ppo_lunarlander.py:92-117; torch.distributions.Categorical) --------------------
+def categorical(logits, noise=None):
+    """Returns (normalised logits, probs, action or None, entropy) in float32, following torch's op sequence."""
+    z = np.asarray(logits, np.float32)
+    m = z.max(-1, keepdims=True)
+    lse = np.log(np.exp(z - m).sum(-1, keepdims=True, dtype=np.float32)) + m
+    ln = z - lse
+    e = np.exp(ln - ln.max(-1, keepdims=True))
+    p = e / e.sum(-1, keepdims=True, dtype=np.float32)
+    ent = -(np.maximum(ln, np.finfo(np.float32).min) * p).sum(-1, dtype=np.float32)
+    action = None if noise is None else np.argmax(p / np.asarray(noise, np.float32), axis=-1).astype(np.int32)
+    return ln, p, action, ent
+
+
+# ---- PPO losses + analytic gradients (ppo_lunarlander.py:278-300; ppo_full_lunarlander.py:586-633;
+#      ppo_lstm_lunarlander.py:763-771) -----------------------------------------------------------------------
+def ppo_loss_grad(logits, value, action, logp_old, adv, ret, *, mode="dualclip", clip_eps_min=0.2, clip_eps_max=0.2,
+                  dual_clip=3.0, value_coef=0.5, entropy_coef=0.01, entropy_old=None, erc_low=0.06, erc_high=0.06,
+                  value_old=None, vclip_eps_min=0.2, vclip_eps_max=0.2):
+    """float64 restatement with torch's tie conventions (min/max split ties evenly; clamp passes grads on the
+    closed interval).  Returns dict(dlogits, dvalue, policy_loss, value_loss, entropy, clip_frac, approx_kl, erc_frac)."""
+    z = np.asarray(logits, np.float64); V = np.asarray(value, np.float64)
+    B, A = z.shape
+    a = np.asarray(action)
+    ln = z - (np.log(np.exp(z - z.max(-1, keepdims=True)).sum(-1, keepdims=True)) + z.max(-1, keepdims=True))
+    p = np.exp(ln)
+    H = -(p * ln).sum(-1)
+    lp = ln[np.arange(B), a]
+    ratio = np.exp(lp - logp_old)
+    Adv = np.asarray(adv, np.float64); R = np.asarray(ret, np.float64)
+    lo, hi = 1 - clip_eps_min, 1 + clip_eps_max
+    in_range = (ratio >= lo) & (ratio <= hi)
+    surr2 = np.clip(ratio, lo, hi) * Adv
+    g2 = np.where(in_range, Adv, 0.0)
+    mask = np.ones(B)
+    if mode == "full":
+        er = H / (np.asarray(entropy_old, np.float64) + 1e-8)
+        mask = ((er > 1 - erc_low) & (er < 1 + erc_high)).astype(np.float64)
+        surr1 = np.clip(ratio, 0.0, dual_clip) * Adv
+        g1 = np.where((ratio >= 0) & (ratio <= dual_clip), Adv, 0.0)
+        obj = np.minimum(surr1, surr2)
+        g = np.where(surr1 < surr2, g1, np.where(surr1 == surr2, 0.5 * (g1 + g2), g2))
+    else:
+        surr1 = ratio * Adv
+        min_surr = np.minimum(surr1, surr2)
+        gm = np.where(surr1 < surr2, Adv, np.where(surr1 == surr2, 0.5 * (Adv + g2), g2))
+        dc = dual_clip * Adv
+        neg = Adv < 0
+        obj = np.where(neg, np.maximum(min_surr, dc), min_surr)
+        g = np.where(neg, np.where(min_surr > dc, gm, np.where(min_surr == dc, 0.5 * gm, 0.0)), gm)
+    e1 = V - R
+    vterm, dv = e1 * e1, 2 * e1
+    if value_old is not None:
+        vo = np.asarray(value_old, np.float64)
+        dlt = V - vo
+        vcl = vo + np.clip(dlt, -vclip_eps_min, vclip_eps_max)
+        e2 = vcl - R
+        l2 = e2 * e2
+        d2 = 2 * e2 * ((dlt >= -vclip_eps_min) & (dlt <= vclip_eps_max))
+        dv = np.where(l2 > vterm, d2, np.where(l2 == vterm, 0.5 * (dv + d2), dv))
+        vterm = np.maximum(vterm, l2)
+    dL_dlp = -(g * ratio) * mask / B
+    dL_dH = -entropy_coef * mask / B
+    onehot = np.zeros((B, A)); onehot[np.arange(B), a] = 1.0
+    dlogits = dL_dlp[:, None] * (onehot - p) + dL_dH[:, None] * (-p * (ln + H[:, None]))
+    dvalue = value_coef * mask * dv / B
+    return dict(dlogits=dlogits, dvalue=dvalue, policy_loss=(-obj * mask).mean(), value_loss=(value_coef * mask * vterm).mean(),
+                entropy=(H * mask).mean(), clip_frac=(((ratio < lo) | (ratio > hi)) * mask).mean(),
+                approx_kl=(np.asarray(logp_old, np.float64) - lp).mean(), erc_frac=1.0 - mask.mean())
+
+
+# ---- torch.optim.Adam single-tensor update + clip_grad_norm_ (ppo_lunarlander.py:169,304-306) ---------------
+def adam_step(param, grad, m, v, step, lr, beta1=0.9, beta2=0.999, eps=1e-8, max_norm=0.0, clamp=0.0):
+    """float32 arrays; returns (param, m, v) after one step (step = 1-based count after increment)."""
+    f = np.float32
+    g = np.asarray(grad, f).copy()
+    if max_norm > 0:
+        tn = f(np.sqrt((g.astype(np.float64) ** 2).sum()))
+        coef = min(f(max_norm) / (tn + f(1e-6)), f(1.0))
+        g = g * f(coef)
+    if clamp > 0:
+        g = np.clip(g, -f(clamp), f(clamp))
+    m = m + f(1 - beta1) * (g - m)
+    v = v * f(beta2) + (f(1 - beta2) * g) * g
+    bc1 = 1 - beta1 ** step
+    bc2 = 1 - beta2 ** step
+    denom = np.sqrt(v) / f(np.sqrt(bc2)) + f(eps)
+    param = param + (f(-lr / bc1) * m) / denom
+    return param.astype(f), m.astype(f), v.astype(f)
+
+
+def mlp_actor_critic_forward(sd, x):
+    """ActorCritic.forward (algorithms/ppo_lunarlander.py:86-90) in float64 NumPy from a state_dict of arrays."""
+    x = np.asarray(x, np.float64)
+    h = np.tanh(x @ sd["shared.0.weight"].T.astype(np.float64) + sd["shared.0.bias"])
+    h = np.tanh(h @ sd["shared.2.weight"].T.astype(np.float64) + sd["shared.2.bias"])
+    a = np.tanh(h @ sd["actor.0.weight"].T.astype(np.float64) + sd["actor.0.bias"])
+    c = np.tanh(h @ sd["critic.0.weight"].T.astype(np.float64) + sd["critic.0.bias"])
+    return a @ sd["actor.2.weight"].T.astype(np.float64) + sd["actor.2.bias"], (c @ sd["critic.2.weight"].T.astype(np.float64) + sd["critic.2.bias"])[:, 0]

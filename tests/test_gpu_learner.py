@@ -1,0 +1,407 @@
+"""GPU parity of the learner-side kernels (through the C ABI) against
+  (1) the golden vectors produced by the reference's own classes (tests/golden, oracle/make_golden.py),
+  (2) the CPU oracle (oracle/algos_np.py) on other seeds / the BASELINE sizes,
+  (3) a plain PyTorch fp32 CPU reference for the floating-point GEMM / Adam kernels.
+Tolerances are stated per test; integer outputs (action indices, permutations) must be exact.
+"""
+import numpy as np
+import pytest
+import torch
+
+pytestmark = pytest.mark.gpu
+from oracle import algos_np as A  # noqa: E402  (the checker, never the thing under test)
+
+
+def cu(x, dtype=None):
+    t = torch.as_tensor(np.ascontiguousarray(x))
+    if dtype is not None:
+        t = t.to(dtype)
+    return t.cuda()
+
+
+@pytest.fixture(scope="module")
+def ops():
+    from gymrl_b200 import ops
+    return ops
+
+
+# ------------------------------------------------------------------------------------------------ sampling
+def test_categorical_golden_bit_exact_actions(ops, golden):
+    g = golden("categorical.npz")
+    a, lp, ent = ops.sample_categorical(cu(g["logits"]), cu(g["noise"]), want_entropy=True)
+    safe = g["margin"] > 1e-5
+    assert np.array_equal(a.cpu().numpy()[safe], g["action"][safe])          # bit-exact action indices
+    assert (a.cpu().numpy() == g["action"]).mean() > 0.995                    # near-ties flagged, not counted
+    ref_lp = A.categorical(g["logits"])[0][np.arange(len(g["action"])), a.cpu().numpy()]
+    np.testing.assert_allclose(lp.cpu().numpy(), ref_lp, rtol=1e-5, atol=1e-6)
+    np.testing.assert_allclose(ent.cpu().numpy(), g["entropy"], rtol=1e-5, atol=1e-6)
+    a2, _, _ = ops.sample_categorical(cu(g["logits"]), deterministic=True)
+    assert np.array_equal(a2.cpu().numpy()[8:], g["greedy"][8:])
+
+
+def test_categorical_philox_distribution_and_replay_counter(ops):
+    logits = torch.log(torch.tensor([[0.1, 0.2, 0.3, 0.4]], device="cuda")).repeat(200_000, 1).contiguous()
+    a, _, _ = ops.sample_categorical(logits, seed=3, draw=0)
+    freq = torch.bincount(a.long(), minlength=4).float() / a.numel()
+    assert torch.allclose(freq.cpu(), torch.tensor([0.1, 0.2, 0.3, 0.4]), atol=5e-3)
+    ctr = torch.zeros(1, device="cuda", dtype=torch.int32)
+    b0, _, _ = ops.sample_categorical(logits, seed=3, draw_base=ctr)
+    assert torch.equal(a, b0)                                  # draw_base 0 == draw 0
+    ops.counter_add(ctr, 5)
+    b5, _, _ = ops.sample_categorical(logits, seed=3, draw_base=ctr)
+    c5, _, _ = ops.sample_categorical(logits, seed=3, draw=5)
+    assert torch.equal(b5, c5) and not torch.equal(b5, a)
+
+
+def test_eps_greedy(ops):
+    q = torch.randn(100_000, 2, device="cuda")
+    greedy = ops.select_eps_greedy(q, 0.0, seed=1)
+    assert torch.equal(greedy.long(), q.argmax(1))
+    mixed = ops.select_eps_greedy(q, 0.5, seed=1)
+    frac = (mixed.long() != q.argmax(1)).float().mean().item()
+    assert abs(frac - 0.25) < 0.01
+
+
+def test_tanh_gaussian_matches_torch_formula(ops):
+    g = torch.Generator().manual_seed(0)
+    N = 4096
+    mean, ls, noise = torch.randn(N, 1, generator=g), torch.randn(N, 1, generator=g) * 2, torch.randn(N, 1, generator=g)
+    act, lp = ops.sample_tanh_gaussian(mean.cuda(), ls.cuda(), 2.0, -20.0, 2.0, noise.cuda())
+    lsc = ls.clamp(-20, 2); std = lsc.exp()
+    x = mean + std * noise                                                     # Actor.sample, sac_pendulum.py:76-87
+    normal = torch.distributions.Normal(mean, std)
+    ref_lp = (normal.log_prob(x) - torch.log(2.0 * (1 - torch.tanh(x).pow(2)) + 1e-6)).sum(1)
+    torch.testing.assert_close(act.cpu(), torch.tanh(x) * 2.0, rtol=1e-5, atol=1e-6)
+    torch.testing.assert_close(lp.cpu(), ref_lp, rtol=1e-4, atol=1e-4)
+    det, _ = ops.sample_tanh_gaussian(mean.cuda(), ls.cuda(), 2.0, deterministic=True)
+    torch.testing.assert_close(det.cpu(), torch.tanh(mean) * 2.0, rtol=1e-5, atol=1e-6)
+    # device noise is N(0,1)
+    a2, _ = ops.sample_tanh_gaussian(torch.zeros(200_000, 1, device="cuda"), torch.zeros(200_000, 1, device="cuda"), 1.0, seed=5)
+    z = torch.atanh(a2.clamp(-0.999999, 0.999999))
+    assert abs(z.mean().item()) < 0.01 and abs(z.std().item() - 1.0) < 0.01
+
+
+def test_gaussian_noise_clip(ops):
+    mu = torch.randn(1000, 1, device="cuda")
+    nz = torch.randn(1000, 1, device="cuda")
+    out = ops.add_gaussian_noise_clip(mu, 0.2, 2.0, noise_clip=0.5, noise=nz)     # td3_pendulum.py:194-204
+    ref = (mu + (nz * 0.2).clamp(-0.5, 0.5)).clamp(-2.0, 2.0)
+    torch.testing.assert_close(out, ref, rtol=0, atol=1e-7)
+
+
+# ------------------------------------------------------------------------------------------------ GAE
+def test_gae_golden_reference_shape(ops, golden):
+    g = golden("gae_algorithms.npz")
+    adv, ret = ops.gae(cu(g["a_reward"][:, None]), cu(g["a_value"][:, None]), cu(g["a_next_value"][None]), cu(g["a_done"][:, None]),
+                       float(g["a_gamma"]), float(g["a_lam"]))
+    # north_star: returns/advantages within 1e-5 relative fp32 of the reference's float64 loop
+    np.testing.assert_allclose(adv.cpu().numpy()[:, 0], g["a_adv"], rtol=1e-5, atol=1e-6)
+    np.testing.assert_allclose(ret.cpu().numpy()[:, 0], g["a_ret"], rtol=1e-5, atol=1e-6)
+    # in fact the fp64 scan reproduces the float32 rounding of the reference values
+    assert (adv.cpu().numpy()[:, 0] == g["a_adv"].astype(np.float32)).mean() > 0.999
+    adv, ret = ops.gae(cu(g["b_reward"]), cu(g["b_value"]), cu(g["b_next_value"]), cu(g["b_done"]), float(g["a_gamma"]), float(g["a_lam"]))
+    np.testing.assert_allclose(adv.cpu().numpy(), g["b_adv"], rtol=1e-5, atol=1e-6)
+    np.testing.assert_allclose(ret.cpu().numpy(), g["b_ret"], rtol=1e-5, atol=1e-6)
+    adv, ret = ops.gae(cu(g["c_reward"][:, None]), cu(g["c_value"][:, None]), cu(g["c_next_value"][None]), cu(g["c_done"][:, None]),
+                       float(g["c_gamma"]), float(g["c_lam_actor"]), float(g["c_lam_critic"]), dialect=2)
+    np.testing.assert_allclose(adv.cpu().numpy()[:, 0], g["c_adv"], rtol=1e-5, atol=1e-6)
+    np.testing.assert_allclose(ret.cpu().numpy()[:, 0], g["c_ret"], rtol=1e-5, atol=1e-6)
+
+
+def test_gae_utils_dialect_bit_exact(ops, golden):
+    g = golden("gae_utils.npz")
+    adv, ret = ops.gae(cu(g["reward"]), cu(g["value"]), cu(g["next_value"]), cu(g["done"]), float(g["gamma"]), float(g["lamda"]),
+                       dw=cu(g["dw"]), dialect=1)
+    assert np.array_equal(ret.cpu().numpy(), g["v_target"])
+    sums = ops.sum_sumsq(adv)
+    ops.normalize_inplace(adv, sums, adv.numel(), ddof=1, eps=1e-8)      # torch .std(): ddof = 1 (utils/buffer.py:33)
+    np.testing.assert_allclose(adv.cpu().numpy(), g["adv_normalized"], rtol=2e-5, atol=2e-6)
+
+
+@pytest.mark.parametrize("T,N", [(128, 4096), (5, 1), (17, 33), (2048, 1), (1000, 70)])
+def test_gae_vs_oracle_sizes(ops, T, N):
+    rng = np.random.default_rng(T * 7 + N)
+    r, v = rng.standard_normal((T, N)).astype(np.float32), rng.standard_normal((T, N)).astype(np.float32)
+    d = (rng.random((T, N)) < 0.02).astype(np.uint8)
+    vl = rng.standard_normal(N).astype(np.float32)
+    for dialect, kw in ((0, dict(coef_f32=True)), (2, dict(coef_f32=False, boot_f32=True))):
+        ea, er = A.gae_algorithms(r, v, vl, d, 0.99, 0.95, 0.9 if dialect == 2 else None, **kw)
+        adv, ret = ops.gae(cu(r), cu(v), cu(vl), cu(d), 0.99, 0.95, 0.9 if dialect == 2 else None, dialect=dialect)
+        np.testing.assert_allclose(adv.cpu().numpy(), ea, rtol=1e-5, atol=1e-6)
+        np.testing.assert_allclose(ret.cpu().numpy(), er, rtol=1e-5, atol=1e-6)
+
+
+def test_gae_linearity_full_size(ops):
+    """Size-independent property at the BASELINE shape: GAE is linear in (r, V) for fixed done flags."""
+    T, N = 128, 4096
+    g = torch.Generator(device="cuda").manual_seed(0)
+    r1, r2 = (torch.randn(T, N, device="cuda", generator=g) for _ in range(2))
+    v1, v2 = (torch.randn(T, N, device="cuda", generator=g) for _ in range(2))
+    l1, l2 = (torch.randn(N, device="cuda", generator=g) for _ in range(2))
+    d = (torch.rand(T, N, device="cuda", generator=g) < 0.01).to(torch.uint8)
+    a1, _ = ops.gae(r1, v1, l1, d, 0.99, 0.95)
+    a2, _ = ops.gae(r2, v2, l2, d, 0.99, 0.95)
+    a12, _ = ops.gae(r1 + 2 * r2, v1 + 2 * v2, l1 + 2 * l2, d, 0.99, 0.95)
+    torch.testing.assert_close(a12, a1 + 2 * a2, rtol=1e-4, atol=1e-4)
+    # and the normalised advantages have mean 0 / population std 1 (numpy ddof = 0, ppo_lunarlander.py:236)
+    sums = ops.sum_sumsq(a1)
+    ops.normalize_inplace(a1, sums, a1.numel(), ddof=0)
+    assert abs(a1.double().mean().item()) < 1e-6 and abs(a1.double().std(unbiased=False).item() - 1) < 1e-5
+
+
+# ------------------------------------------------------------------------------------------------ PPO loss
+def _loss_cfg(**kw):
+    from gymrl_b200 import _ffi
+    d = dict(mode=0, clip_eps_min=0.2, clip_eps_max=0.2, dual_clip=3.0, value_coef=0.5, entropy_coef=0.01, erc_low=0.06,
+             erc_high=0.06, vclip_eps_min=0.2, vclip_eps_max=0.2)
+    d.update(kw)
+    return _ffi.PPOCfg(**d)
+
+
+def test_ppo_loss_golden_dualclip(ops, golden):
+    g = golden("ppo_loss_dualclip.npz")
+    dl, dv, m = ops.ppo_loss(cu(g["logits"]), cu(g["value"]), cu(g["action"]), cu(g["logp_old"]), cu(g["adv"]), cu(g["ret"]),
+                             _loss_cfg(clip_eps_min=float(g["clip_eps"]), clip_eps_max=float(g["clip_eps"])))
+    np.testing.assert_allclose(dl.cpu().numpy(), g["dlogits"], rtol=2e-4, atol=2e-7)
+    np.testing.assert_allclose(dv.cpu().numpy(), g["dvalue"], rtol=2e-4, atol=2e-7)
+    m = m.cpu().numpy()
+    for i, k in enumerate(("policy_loss", "value_loss", "entropy", "clip_frac", "approx_kl")):
+        np.testing.assert_allclose(m[i], g["m_" + k], rtol=1e-4, atol=1e-6)
+
+
+def test_ppo_loss_golden_full(ops, golden):
+    from gymrl_b200 import _ffi
+    g = golden("ppo_loss_full.npz")
+    cfg = _loss_cfg(mode=_ffi.PPO_FULL, clip_eps_min=float(g["clip_eps_min"]), clip_eps_max=float(g["clip_eps_max"]),
+                    dual_clip=float(g["dual_clip"]), entropy_coef=float(g["entropy_coef"]), erc_low=float(g["erc_low"]),
+                    erc_high=float(g["erc_high"]))
+    dl, dv, m = ops.ppo_loss(cu(g["logits"]), cu(g["value"]), cu(g["action"]), cu(g["logp_old"]), cu(g["adv"]), cu(g["ret"]), cfg,
+                             entropy_old=cu(g["entropy_old"]))
+    np.testing.assert_allclose(dl.cpu().numpy(), g["dlogits"], rtol=2e-4, atol=2e-7)
+    np.testing.assert_allclose(dv.cpu().numpy(), g["dvalue"], rtol=2e-4, atol=2e-7)
+
+
+@pytest.mark.parametrize("mode", ["dualclip", "full", "dualclip+vclip"])
+def test_ppo_loss_vs_oracle_with_gather(ops, mode):
+    from gymrl_b200 import _ffi
+    rng = np.random.default_rng(len(mode))
+    Btot, B, A_ = 5000, 1777, 4
+    idx = rng.permutation(Btot)[:B].astype(np.int32)
+    logits = (rng.standard_normal((B, A_)) * 2).astype(np.float32)
+    value = rng.standard_normal(B).astype(np.float32)
+    act = rng.integers(0, A_, Btot).astype(np.int32)
+    lpo = (-np.abs(rng.standard_normal(Btot)) - 0.5).astype(np.float32)
+    adv, ret = rng.standard_normal(Btot).astype(np.float32), rng.standard_normal(Btot).astype(np.float32)
+    ent_old = (rng.random(Btot) * 1.3 + 0.05).astype(np.float32)
+    v_old = rng.standard_normal(Btot).astype(np.float32)
+    full, vclip = mode.startswith("full"), mode.endswith("vclip")
+    cfg = _loss_cfg(mode=(_ffi.PPO_FULL if full else 0) | (_ffi.PPO_VALUE_CLIP if vclip else 0), clip_eps_max=0.28 if full else 0.2)
+    # logits/value live in a padded [B, 8] buffer like the trainer's fused head output
+    lv = torch.zeros(B, 8, device="cuda"); lv[:, :A_] = cu(logits); lv[:, A_] = cu(value)
+    dlv = torch.zeros(B, 8, device="cuda")
+    _, _, m = ops.ppo_loss(lv[:, :A_], lv[:, A_:A_ + 1], cu(act), cu(lpo), cu(adv), cu(ret), cfg, row_index=cu(idx),
+                           entropy_old=cu(ent_old) if full else None, value_old=cu(v_old) if vclip else None,
+                           dlogits=dlv[:, :A_], dvalue=dlv[:, A_:A_ + 1])
+    r = A.ppo_loss_grad(logits, value, act[idx], lpo[idx], adv[idx], ret[idx], mode="full" if full else "dualclip",
+                        clip_eps_max=0.28 if full else 0.2, entropy_old=ent_old[idx] if full else None,
+                        value_old=v_old[idx] if vclip else None)
+    np.testing.assert_allclose(dlv[:, :A_].cpu().numpy(), r["dlogits"], rtol=3e-4, atol=3e-8)
+    np.testing.assert_allclose(dlv[:, A_].cpu().numpy(), r["dvalue"], rtol=3e-4, atol=3e-8)
+    assert (dlv[:, A_ + 1:] == 0).all()
+    m = m.cpu().numpy()
+    for i, k in enumerate(("policy_loss", "value_loss", "entropy", "clip_frac", "approx_kl", "erc_frac")):
+        np.testing.assert_allclose(m[i], r[k], rtol=2e-4, atol=2e-6)
+
+
+# ------------------------------------------------------------------------------------------------ dense layers
+@pytest.mark.parametrize("M,N,K,act", [(16384, 256, 256, 1), (4096, 512, 256, 1), (4096, 256, 8, 1), (333, 70, 19, 2),
+                                       (4096, 4, 256, 0), (4096, 1, 256, 0), (128, 256, 3, 2), (64, 2, 256, 0), (1, 256, 8, 1)])
+def test_linear_forward_vs_torch(ops, M, N, K, act):
+    g = torch.Generator().manual_seed(M + N + K)
+    x, w, b = torch.randn(M, K, generator=g), torch.randn(N, K, generator=g) / K ** 0.5, torch.randn(N, generator=g)
+    y = ops.linear_forward(x.cuda(), w.cuda(), b.cuda(), act)
+    ref = x @ w.T + b
+    ref = torch.tanh(ref) if act == 1 else (torch.relu(ref) if act == 2 else ref)
+    torch.testing.assert_close(y.cpu(), ref, rtol=2e-5, atol=2e-5)
+
+
+def test_linear_forward_gather_and_strided_views(ops):
+    g = torch.Generator().manual_seed(0)
+    X = torch.randn(10_000, 8, generator=g)
+    idx = torch.randperm(10_000, generator=g)[:4096].to(torch.int32)
+    w, b = torch.randn(256, 8, generator=g), torch.randn(256, generator=g)
+    y = ops.linear_forward(X.cuda(), w.cuda(), b.cuda(), 1, row_index=idx.cuda())
+    torch.testing.assert_close(y.cpu(), torch.tanh(X[idx.long()] @ w.T + b), rtol=2e-5, atol=2e-5)
+    # operand = right half of a [M, 512] buffer, output = columns 4:5 of a [M, 8] buffer (the critic head)
+    ac = torch.randn(4096, 512, generator=g)
+    wc, bc = torch.randn(1, 256, generator=g) / 16, torch.randn(1, generator=g)
+    lv = torch.zeros(4096, 8, device="cuda")
+    ops.linear_forward(ac.cuda()[:, 256:], wc.cuda(), bc.cuda(), 0, out=lv[:, 4:5])
+    torch.testing.assert_close(lv[:, 4].cpu(), (ac[:, 256:] @ wc.T + bc)[:, 0], rtol=2e-5, atol=2e-5)
+    assert (lv[:, :4] == 0).all() and (lv[:, 5:] == 0).all()
+
+
+@pytest.mark.parametrize("M,N,K,act", [(16384, 512, 256, 1), (4096, 256, 256, 2), (4096, 4, 256, 1), (4096, 1, 256, 1), (301, 70, 19, 0)])
+def test_linear_backward_vs_torch_autograd(ops, M, N, K, act):
+    g = torch.Generator().manual_seed(M * 3 + N + K)
+    h_prev = torch.tanh(torch.randn(M, K, generator=g)) if act == 1 else torch.relu(torch.randn(M, K, generator=g))
+    w = (torch.randn(N, K, generator=g) / K ** 0.5)
+    dy = torch.randn(M, N, generator=g) / M
+    # reference: dx = (dy @ w) * act'(h_prev); dw = dy^T @ h_prev; db = dy.sum(0)   (fp32 torch on CPU)
+    dx_ref = dy @ w
+    if act == 1:
+        dx_ref = dx_ref * (1 - h_prev ** 2)
+    elif act == 2:
+        dx_ref = dx_ref * (h_prev > 0)
+    dx = ops.linear_backward_input(dy.cuda(), w.cuda(), h_prev.cuda() if act else None, act)
+    torch.testing.assert_close(dx.cpu(), dx_ref, rtol=1e-4, atol=1e-6 / M ** 0.5 + 1e-8)
+    dw = torch.zeros(N, K, device="cuda"); db = torch.zeros(N, device="cuda")
+    ops.linear_backward_weight(dy.cuda(), h_prev.cuda(), dw, db)
+    torch.testing.assert_close(dw.cpu(), dy.T @ h_prev, rtol=1e-4, atol=2e-6)
+    torch.testing.assert_close(db.cpu(), dy.sum(0), rtol=1e-4, atol=2e-6)
+    # determinism: the split-M partial sums are reduced in a fixed order
+    dw2 = torch.zeros(N, K, device="cuda")
+    ops.linear_backward_weight(dy.cuda(), h_prev.cuda(), dw2, None)
+    assert torch.equal(dw, dw2)
+
+
+def test_linear_backward_weight_gather(ops):
+    g = torch.Generator().manual_seed(5)
+    X = torch.randn(9000, 8, generator=g)
+    idx = torch.randperm(9000, generator=g)[:4096].to(torch.int32)
+    dy = torch.randn(4096, 256, generator=g) / 4096
+    dw = torch.zeros(256, 8, device="cuda"); db = torch.zeros(256, device="cuda")
+    ops.linear_backward_weight(dy.cuda(), X.cuda(), dw, db, row_index=idx.cuda())
+    torch.testing.assert_close(dw.cpu(), dy.T @ X[idx.long()], rtol=1e-4, atol=2e-6)
+    torch.testing.assert_close(db.cpu(), dy.sum(0), rtol=1e-4, atol=2e-6)
+
+
+# ------------------------------------------------------------------------------------------------ optimiser
+def test_adam_matches_torch_optim(ops):
+    g = torch.Generator().manual_seed(0)
+    n = 200_965
+    p0 = torch.randn(n, generator=g)
+    ref_p = torch.nn.Parameter(p0.clone())
+    opt = torch.optim.Adam([ref_p], lr=3e-4, eps=1e-5)
+    p, m, v = p0.clone().cuda(), torch.zeros(n, device="cuda"), torch.zeros(n, device="cuda")
+    lr = torch.tensor([3e-4], device="cuda", dtype=torch.float64)
+    step = torch.zeros(1, device="cuda", dtype=torch.int32)
+    sumsq = torch.zeros(1, device="cuda", dtype=torch.float64)
+    for it in range(5):
+        grad = torch.randn(n, generator=g) * (10.0 if it % 2 else 0.001)
+        ref_p.grad = grad.clone()
+        torch.nn.utils.clip_grad_norm_([ref_p], 0.5)
+        lr_now = 3e-4 * (1 - it / 10)
+        opt.param_groups[0]["lr"] = lr_now
+        opt.step()
+        lr.fill_(lr_now)
+        ops.grad_sumsq(grad.cuda(), out=sumsq)
+        ops.adam_step(p, grad.cuda(), m, v, lr, step, eps=1e-5, sumsq=sumsq, max_norm=0.5)
+        torch.testing.assert_close(p.cpu(), ref_p.data, rtol=2e-6, atol=2e-7)
+    assert step.item() == 5 and sumsq.item() == 0.0
+    # per-element clamp variant (dqn_cartpole.py:163-165)
+    ref_p2 = torch.nn.Parameter(p0.clone()); opt2 = torch.optim.Adam([ref_p2], lr=1e-3)
+    grad = torch.randn(n, generator=g) * 3
+    ref_p2.grad = grad.clone().clamp_(-1, 1); opt2.step()
+    p2, m2, v2 = p0.clone().cuda(), torch.zeros(n, device="cuda"), torch.zeros(n, device="cuda")
+    lr.fill_(1e-3); step.zero_()
+    ops.adam_step(p2, grad.cuda(), m2, v2, lr, step, clamp=1.0)
+    torch.testing.assert_close(p2.cpu(), ref_p2.data, rtol=2e-6, atol=2e-7)
+
+
+def test_polyak_and_hard_copy(ops):
+    t, s = torch.randn(70_000, device="cuda"), torch.randn(70_000, device="cuda")
+    ref = 0.005 * s + (1 - 0.005) * t
+    ops.polyak(t, s, 0.005)
+    torch.testing.assert_close(t, ref, rtol=1e-6, atol=1e-7)
+    ops.polyak(t, s, 1.0)
+    assert torch.equal(t, s)
+
+
+@pytest.mark.parametrize("n", [1, 2, 64, 1000, 524288, 300_001])
+def test_random_permutation_is_bijection(ops, n):
+    p = ops.random_permutation(n, seed=1, draw=3)
+    assert torch.equal(torch.sort(p.long()).values, torch.arange(n, device="cuda"))
+    if n > 100:
+        q = ops.random_permutation(n, seed=1, draw=4)
+        assert (p != q).float().mean() > 0.9
+        assert (p.long() == torch.arange(n, device="cuda")).float().mean() < 0.01
+        # roughly uniform: mean displacement of a random permutation is n/3
+        disp = (p.long() - torch.arange(n, device="cuda")).abs().float().mean().item()
+        assert 0.25 * n < disp < 0.42 * n
+
+
+# ------------------------------------------------------------------------------------------------ end to end
+def _trainer_from_golden(g, use_graph, n_mb, seed=0):
+    from gymrl_b200.algorithms import ppo_lunarlander as P
+    B = g["states"].shape[0]
+    cfg = P.Config()
+    cfg.num_envs, cfg.num_steps, cfg.num_minibatches, cfg.num_epochs = 1, B, n_mb, 1
+    cfg.seed, cfg.use_cuda_graph = seed, use_graph
+    t = P.PPOTrainer(cfg)
+    sd = {k[3:]: torch.as_tensor(g[k]) for k in g.files if k.startswith("w0_")}
+    t.model.load_state_dict(sd)
+    t.net.fp.refresh_views()
+    buf = t.buffer
+    buf.obs[:B, 0].copy_(cu(g["states"]))
+    buf.action[:, 0].copy_(cu(g["action"])); buf.log_prob[:, 0].copy_(cu(g["logp_old"]))
+    buf.value[:, 0].copy_(cu(g["value_old"])); buf.reward[:, 0].copy_(cu(g["reward"])); buf.done[:, 0].copy_(cu(g["done"]))
+    buf.filled = B
+    return t
+
+
+def test_ppo_update_gradients_match_reference(golden):
+    """Forward + fused loss + backward of the whole ActorCritic against the reference's autograd gradients
+    (PPOTrainer.update with one full-batch minibatch, unclipped)."""
+    g = golden("ppo_update.npz")
+    t = _trainer_from_golden(g, use_graph=False, n_mb=1)
+    t.cfg.max_grad_norm = 1e9
+    t.optimizer.param_groups[0]["lr"] = 0.0
+    met = t.update(float(g["next_value"]))
+    for k, p in t.model.named_parameters():
+        ref = g["g_" + k]
+        np.testing.assert_allclose(p.grad.cpu().numpy(), ref, rtol=2e-3, atol=2e-6 + 1e-4 * np.abs(ref).max(), err_msg=k)
+    for k in ("policy_loss", "value_loss", "entropy", "clip_frac", "approx_kl"):
+        np.testing.assert_allclose(met[k], g["m1_" + k], rtol=2e-4, atol=2e-6)
+
+
+@pytest.mark.parametrize("use_graph", [False, True])
+def test_ppo_update_parameters_match_reference(golden, use_graph):
+    """1 epoch x 4 minibatches with clip_grad_norm_(0.5) + Adam(3e-4, eps 1e-5): parameters after the update
+    equal the reference's (same permutation fed in), eager and CUDA-graph paths alike."""
+    g = golden("ppo_update.npz")
+    t = _trainer_from_golden(g, use_graph=use_graph, n_mb=4)
+    from gymrl_b200 import ops as O
+    perm = cu(g["perm"])
+    orig = O.random_permutation
+    try:
+        O.random_permutation = lambda n, **kw: kw["out"].copy_(perm)   # feed the reference's np.random.shuffle result
+        met = t.update(float(g["next_value"]))
+    finally:
+        O.random_permutation = orig
+    for k, v in t.model.state_dict().items():
+        np.testing.assert_allclose(v.cpu().numpy(), g["w1_" + k], rtol=1e-4, atol=3e-6, err_msg=k)
+    for k in ("policy_loss", "value_loss", "entropy", "clip_frac", "approx_kl"):
+        np.testing.assert_allclose(met[k], g["m2_" + k], rtol=5e-4, atol=5e-6)
+
+
+def test_ppo_trainer_rollout_and_update_smoke():
+    """N = 256 envs x 32 steps, graph and eager rollouts produce identical buffers from identical seeds."""
+    from gymrl_b200.algorithms import ppo_lunarlander as P
+    outs = []
+    for use_graph in (False, True):
+        cfg = P.Config()
+        cfg.num_envs, cfg.num_steps, cfg.num_minibatches, cfg.num_epochs, cfg.seed, cfg.use_cuda_graph = 256, 32, 4, 2, 123, use_graph
+        torch.manual_seed(0)
+        t = P.PPOTrainer(cfg)
+        t.collect_rollout()
+        if use_graph:   # the capture warm-up consumed one rollout: compare the *second* eager rollout instead
+            outs.append((t.buffer.obs.clone(), t.buffer.action.clone(), t.buffer.reward.clone()))
+        else:
+            t.collect_rollout()
+            outs.append((t.buffer.obs.clone(), t.buffer.action.clone(), t.buffer.reward.clone()))
+        m = t.update(None)
+        assert all(np.isfinite(v) for v in m.values()) and 1.0 < m["entropy"] < 1.3863 + 1e-3
+        assert t.step_count == 256 * 32 * (1 if use_graph else 2)
+    for a, b in zip(*outs):
+        assert torch.equal(a, b)

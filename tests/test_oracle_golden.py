@@ -1,0 +1,87 @@
+"""Pin the CPU oracle (oracle/algos_np.py, oracle/philox.py) against the golden vectors produced by the
+reference's own classes (oracle/make_golden.py).  No GPU needed."""
+import numpy as np
+import pytest
+
+from oracle import algos_np as A
+from oracle import philox as px
+
+
+def test_philox_known_answers():
+    """Random123 kat_vectors for philox4x32-10."""
+    def kat(ctr, key):
+        out = px.philox((key[1] << 32) | key[0], np.uint64((ctr[3] << 32) | ctr[0]), ctr[1], ctr[2])
+        return [int(x) for x in out]
+    assert kat([0, 0, 0, 0], [0, 0]) == [0x6627e8d5, 0xe169c58d, 0xbc57ac4c, 0x9b00dbd8]
+    assert kat([0xffffffff] * 4, [0xffffffff] * 2) == [0x408f276d, 0x41c83b0e, 0xa20bc7c6, 0x6d5451fd]
+    assert kat([0x243f6a88, 0x85a308d3, 0x13198a2e, 0x03707344], [0xa4093822, 0x299f31d0]) == \
+        [0xd16cfe09, 0x94fdcceb, 0x5001e420, 0x24126ea1]
+
+
+def test_gae_algorithms_dialect(golden):
+    g = golden("gae_algorithms.npz")
+    adv, ret = A.gae_algorithms(g["a_reward"][:, None], g["a_value"][:, None], g["a_next_value"][None], g["a_done"][:, None],
+                                float(g["a_gamma"]), float(g["a_lam"]))
+    np.testing.assert_allclose(adv[:, 0], g["a_adv"], rtol=1e-12, atol=1e-12)
+    np.testing.assert_allclose(ret[:, 0], g["a_ret"], rtol=1e-12, atol=1e-12)
+    adv, ret = A.gae_algorithms(g["b_reward"], g["b_value"], g["b_next_value"], g["b_done"], float(g["a_gamma"]), float(g["a_lam"]))
+    np.testing.assert_allclose(adv, g["b_adv"], rtol=1e-12, atol=1e-12)
+    np.testing.assert_allclose(ret, g["b_ret"], rtol=1e-12, atol=1e-12)
+    adv, ret = A.gae_algorithms(g["c_reward"][:, None], g["c_value"][:, None], g["c_next_value"][None], g["c_done"][:, None],
+                                float(g["c_gamma"]), float(g["c_lam_actor"]), float(g["c_lam_critic"]), coef_f32=False, boot_f32=True)
+    np.testing.assert_allclose(adv[:, 0], g["c_adv"], rtol=1e-12, atol=1e-12)
+    np.testing.assert_allclose(ret[:, 0], g["c_ret"], rtol=1e-12, atol=1e-12)
+
+
+def test_gae_utils_dialect_bit_exact(golden):
+    g = golden("gae_utils.npz")
+    adv, vt = A.gae_utils(g["reward"], g["value"], g["next_value"], g["done"], g["dw"], float(g["gamma"]), float(g["lamda"]))
+    assert np.array_equal(vt, g["v_target"])  # float32 recurrence reproduced bit for bit
+    mean, std = adv.mean(dtype=np.float64), adv.std(ddof=1, dtype=np.float64)  # torch .std() => ddof 1
+    np.testing.assert_allclose((adv - mean) / (std + 1e-8), g["adv_normalized"], rtol=2e-5, atol=2e-6)
+
+
+def test_categorical(golden):
+    g = golden("categorical.npz")
+    ln, p, action, ent = A.categorical(g["logits"], g["noise"])
+    safe = g["margin"] > 1e-5  # near ties are flagged, not counted
+    assert safe.mean() > 0.97
+    assert np.array_equal(action[safe], g["action"][safe])
+    np.testing.assert_allclose(ln[np.arange(len(action)), g["action"]], g["log_prob"], rtol=1e-5, atol=1e-6)
+    np.testing.assert_allclose(ent, g["entropy"], rtol=1e-5, atol=1e-6)
+
+
+def test_ppo_loss_dualclip(golden):
+    g = golden("ppo_loss_dualclip.npz")
+    r = A.ppo_loss_grad(g["logits"], g["value"], g["action"], g["logp_old"], g["adv"], g["ret"], mode="dualclip",
+                        clip_eps_min=float(g["clip_eps"]), clip_eps_max=float(g["clip_eps"]), dual_clip=float(g["dual_clip"]),
+                        value_coef=float(g["value_coef"]), entropy_coef=float(g["entropy_coef"]))
+    np.testing.assert_allclose(r["dlogits"], g["dlogits"], rtol=2e-4, atol=2e-7)
+    np.testing.assert_allclose(r["dvalue"], g["dvalue"], rtol=2e-4, atol=2e-7)
+    for k in ("policy_loss", "value_loss", "entropy", "clip_frac", "approx_kl"):
+        np.testing.assert_allclose(r[k], g["m_" + k], rtol=1e-4, atol=1e-6)
+
+
+def test_ppo_loss_full(golden):
+    g = golden("ppo_loss_full.npz")
+    r = A.ppo_loss_grad(g["logits"], g["value"], g["action"], g["logp_old"], g["adv"], g["ret"], mode="full",
+                        clip_eps_min=float(g["clip_eps_min"]), clip_eps_max=float(g["clip_eps_max"]),
+                        dual_clip=float(g["dual_clip"]), value_coef=0.5, entropy_coef=float(g["entropy_coef"]),
+                        entropy_old=g["entropy_old"], erc_low=float(g["erc_low"]), erc_high=float(g["erc_high"]))
+    assert 0.02 < r["erc_frac"] < 0.9  # the fixture exercises both sides of the ERC mask
+    np.testing.assert_allclose(r["dlogits"], g["dlogits"], rtol=2e-4, atol=2e-7)
+    np.testing.assert_allclose(r["dvalue"], g["dvalue"], rtol=2e-4, atol=2e-7)
+
+
+def test_ppo_update_gradients_via_oracle_forward(golden):
+    """The e2e fixture is self-consistent: oracle forward + oracle loss reproduce the reference's metrics."""
+    g = golden("ppo_update.npz")
+    sd = {k[3:]: g[k] for k in g.files if k.startswith("w0_")}
+    logits, value = A.mlp_actor_critic_forward(sd, g["states"])
+    adv, ret = A.gae_algorithms(g["reward"][:, None], g["value_old"][:, None], g["next_value"][None], g["done"][:, None],
+                                float(g["gamma"]), float(g["lam"]))
+    adv = adv[:, 0]; ret = ret[:, 0]
+    adv = (adv - adv.mean()) / (adv.std() + 1e-8)
+    r = A.ppo_loss_grad(logits, value, g["action"], g["logp_old"], adv, ret)
+    for k in ("policy_loss", "value_loss", "entropy", "clip_frac", "approx_kl"):
+        np.testing.assert_allclose(r[k], g["m1_" + k], rtol=2e-4, atol=2e-6)
