@@ -99,7 +99,7 @@ def run_reference(args, rank, world):
         return
     from oracle.ref_port import run_ppo_port
     cores = os.cpu_count() or 1
-    procs = max(1, min(cores, 64))
+    procs = max(1, cores)
     vals = []
     t0 = time.perf_counter()
     for _ in range(args.warmup + args.steps):
@@ -234,7 +234,7 @@ def run_ours(args, rank, world, local_rank):
     if world == 1:
         from oracle.ref_port import run_ppo_port   # bench's cpu_baseline leg: the oracle is the thing timed here
         cores = os.cpu_count() or 1
-        r = run_ppo_port(n_rollouts=1, update_freq=2048, processes=min(cores, 64))
+        r = run_ppo_port(n_rollouts=1, update_freq=2048, processes=cores)
         cpu = {"value": r["value"], "unit": "env-steps/s", "cores": r["cores"], "kind": "port", "sample": r["sample"]}
     out = {"metric": "env_steps_per_sec", "value": value, "unit": "env-steps/s", "n_gpus": world, "steps": args.steps,
            "warmup": args.warmup, "ms_per_step": dev_ms / args.steps, "higher_is_better": True, "scaling": "weak",

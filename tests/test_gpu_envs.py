@@ -47,7 +47,7 @@ def test_cartpole_parity():
         np.testing.assert_allclose(a, b, rtol=0, atol=1e-6, err_msg=tag)
     # a stabilising-ish policy so that some episodes run into the 500-step TimeLimit
     def act(t, obs):
-        good = (obs[:, 2] + 0.3 * obs[:, 3] > 0).astype(np.int64)
+        good = (obs[:, 2] * 10 + obs[:, 3] * 2 + obs[:, 0] * 0.5 + obs[:, 1] * 1.0 > 0).astype(np.int64)
         rnd = rng.integers(0, 2, N)
         return np.where(np.arange(N) % 3 == 0, good, rnd)
     _run_pair(dev, ora, 650, act, True, check)
