@@ -66,6 +66,26 @@ SIGNATURES = {
     "gymrl_random_permutation": (c_int, [_P, c_int, c_u64, c_u32, _P, _P]),
     "gymrl_counter_add": (c_int, [_P, c_u32, _P]),
     "gymrl_slice_i32": (c_int, [_P, _P, c_int, _P, _P]),
+    "gymrl_replay_sample_indices": (c_int, [_P, c_int, _P, c_u64, c_u32, _P, _P]),
+    "gymrl_replay_store": (c_int, [_P, _P, c_int, c_int, c_int, c_int, _P, _P]),
+    "gymrl_replay_advance": (c_int, [_P, c_int, c_int, _P]),
+    "gymrl_gather_concat": (c_int, [_P, c_int, _P, c_int, c_int, _P, _P, c_int, c_int, _P, c_int, _P]),
+    "gymrl_nstep_push": (c_int, [_P] * 12 + [c_int, c_int, c_int, c_double, _P] + [_P] * 5 + [c_int, _P, _P]),
+    "gymrl_sumtree_update": (c_int, [_P, c_int, _P, _P, _P, c_int, c_float, c_float, c_float, _P, _P]),
+    "gymrl_sumtree_store_new": (c_int, [_P, c_int, c_int, _P, _P, _P]),
+    "gymrl_sumtree_sample": (c_int, [_P, c_int, c_int, _P, _P, _P, _P, _P, _P, _P, c_int, c_u64, c_u32, _P, _P]),
+    "gymrl_dqn_loss": (c_int, [_P, c_int] * 6 + [_P] * 5 + [_P, c_int, _P, c_int, _P, _P, c_int, c_int, c_float, _P]),
+    "gymrl_twin_q_target": (c_int, [_P, _P, _P, _P, c_int, _P, c_int, _P, _P, c_float, _P, c_int, _P]),
+    "gymrl_twin_q_loss": (c_int, [_P, c_int, _P, c_int, _P, _P, c_int, _P, c_int, _P, c_int, _P]),
+    "gymrl_min_q_grad": (c_int, [_P, c_int, _P, c_int, _P, c_int, _P, c_int, c_int, c_int, _P, _P]),
+    "gymrl_sac_actor_grad": (c_int, [_P, _P, _P, c_int, _P, c_int, _P, c_float, c_float, c_float, _P, _P, c_int, _P, _P, c_int, c_int, _P]),
+    "gymrl_sac_alpha_step": (c_int, [_P, _P, _P, c_int, c_double, c_double, _P, _P]),
+    "gymrl_tanh_bound": (c_int, [_P, c_int, _P, c_float, c_int, c_int, _P]),
+    "gymrl_tanh_bound_grad": (c_int, [_P, _P, c_int, _P, c_int, c_float, c_int, c_int, _P]),
+    "gymrl_fill_normal": (c_int, [_P, c_int, c_u64, c_u64, c_u32, _P, _P]),
+    "gymrl_noisy_sample": (c_int, [_P, _P, c_int, c_u64, c_u64, c_u32, _P, _P]),
+    "gymrl_noisy_compose": (c_int, [_P] * 8 + [c_int, c_int, _P]),
+    "gymrl_noisy_backward": (c_int, [_P] * 8 + [c_int, c_int, c_int, _P]),
 }
 
 

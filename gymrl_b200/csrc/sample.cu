@@ -207,3 +207,21 @@ extern "C" int gymrl_add_gaussian_noise_clip(const float* d_mu, const float* d_n
     GYMRL_LAUNCH_CHECK("gaussian_noise_clip");
     return GYMRL_OK;
 }
+
+// out[i] ~ N(0,1) from Philox (entity = entity0 + i/4): the noise buffers of Actor.sample's rsample (sac :80) and of
+// torch.randn_like (td3 :195), kept so the backward pass can reuse the exact draw.
+__global__ void fill_normal_kernel(float* __restrict__ out, int n, uint64_t seed, uint64_t entity0, uint32_t draw,
+                                   const uint32_t* __restrict__ draw_base, uint32_t stream_id) {
+    const int i = blockIdx.x * blockDim.x + threadIdx.x;
+    if (i >= n) return;
+    if (draw_base) draw += *draw_base;
+    out[i] = philox_normal(seed, entity0 + (uint64_t)(i >> 2), draw, stream_id, i & 3);
+}
+extern "C" int gymrl_fill_normal(float* d_out, int n, uint64_t seed, uint64_t entity0, uint32_t draw, const uint32_t* d_draw_base,
+                                 void* stream) {
+    GYMRL_REQUIRE(d_out && n > 0, "bad arguments");
+    fill_normal_kernel<<<ceil_div(n, 256), 256, 0, as_stream(stream)>>>(d_out, n, seed, entity0, draw, d_draw_base, PHILOX_UPDATE);
+    gymrl_count_launch();
+    GYMRL_LAUNCH_CHECK("fill_normal");
+    return GYMRL_OK;
+}

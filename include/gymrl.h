@@ -231,6 +231,109 @@ int gymrl_counter_add(uint32_t* d_counter, uint32_t inc, void* stream);
  * algorithms/ppo_lunarlander.py:264-266 with the window number resident on the device. */
 int gymrl_slice_i32(int32_t* d_dst, const int32_t* d_src, int n, const uint32_t* d_block_index, void* stream);
 
+/* ------------------------------------------------------------------------------------------------
+ * Replay memory.  All storage is caller-owned (torch tensors); the ring's
+ * {cursor, size} live in a device int32[2] so stores/samples are CUDA-graph capturable.
+ * ---------------------------------------------------------------------------------------------- */
+/* idx[i] = i-th image of a keyed random bijection on [0, size): a uniform sample WITHOUT replacement
+ * (random.sample(self.buffer, batch_size), algorithms/dqn_cartpole.py:75-77; same in sac/td3/ddpg). */
+int gymrl_replay_sample_indices(int32_t* d_idx, int batch, const int32_t* d_ring_state, uint64_t seed,
+                                uint32_t draw, const uint32_t* d_draw_base, void* stream);
+/* dst[(cursor + i) % capacity][0:width] = src[i][0:width] for one field (4-byte elements, or uint8 -> float32
+ * when src_is_u8) — ReplayBuffer.push (dqn_cartpole.py:72-73) for N lockstep transitions at once. */
+int gymrl_replay_store(void* d_dst, const void* d_src, int n, int width, int src_is_u8, int capacity,
+                       const int32_t* d_ring_state, void* stream);
+/* cursor = (cursor + n) % capacity; size = min(capacity, size + n)  (deque(maxlen=capacity) semantics). */
+int gymrl_replay_advance(int32_t* d_ring_state, int n, int capacity, void* stream);
+/* dst[i] = [a[idx_a[i]][0:width_a], b[idx_b[i]][0:width_b]]: batch gather fused with
+ * torch.cat([state, action], dim=1) (Critic.forward, algorithms/sac_pendulum.py:112). idx_*, b nullable. */
+int gymrl_gather_concat(void* d_dst, int ld_dst, const void* d_a, int width_a, int ld_a, const int32_t* d_idx_a,
+                        const void* d_b, int width_b, int ld_b, const int32_t* d_idx_b, int n, void* stream);
+/* PrioritizedNStepBuffer.store_transition + _get_n_step_transition (rainbow_dqn_cartpole.py:179-218) for N
+ * envs in lockstep: append to each env's n-slot window (planes [n][N][...]), and once the window is full
+ * fold R = sum gamma^k r_k back-to-front (cut at done; s'/terminal from the earliest done) and write the
+ * n-step transition into ring row (cursor + env).  Caller then calls gymrl_sumtree_store_new +
+ * gymrl_replay_advance iff the window was full (pushed + 1 >= n_steps, known on the host). */
+int gymrl_nstep_push(float* w_obs, int32_t* w_act, float* w_rew, float* w_nobs, uint8_t* w_term, uint8_t* w_done,
+                     const float* d_obs, const int32_t* d_act, const float* d_rew, const float* d_nobs,
+                     const uint8_t* d_term, const uint8_t* d_done, int n_envs, int obs_dim, int n_steps, double gamma,
+                     int32_t* d_pushed, float* r_obs, int32_t* r_act, float* r_rew, float* r_nobs, float* r_term,
+                     int capacity, const int32_t* d_ring_state, void* stream);
+/* SumTree (rainbow_dqn_cartpole.py:116-152): float64 binary heap of 2*capacity-1 nodes, leaf i at
+ * capacity-1+i — identical layout and tie rule, so results match the reference for any capacity.
+ * update: batch of (data index, priority) with last-writer-wins for duplicates (update_priorities :258-261);
+ * pass d_priority (float64) OR d_td_error (float32): priority = min(|td| + eps, clip_max?)^alpha evaluated in
+ * float32 like the reference's NumPy expression (clip_max <= 0 disables the min; ddqn_per_cartpole.py:142-147
+ * uses eps 1e-4, clip 1, alpha 0.6).  d_winner_scratch: int32[capacity] initialised to -1 once. */
+int gymrl_sumtree_update(double* d_tree, int capacity, const int32_t* d_idx, const double* d_priority,
+                         const float* d_td_error, int n, float eps, float alpha, float clip_max,
+                         int32_t* d_winner_scratch, void* stream);
+/* New transitions at ring rows [cursor, cursor+n) get priority max(all leaves) (1.0 while the tree is empty):
+ * rainbow :201-202 with the O(capacity) max scan done as a device reduction. */
+int gymrl_sumtree_store_new(double* d_tree, int capacity, int n, const int32_t* d_ring_state, double* d_max_scratch,
+                            void* stream);
+/* PrioritizedNStepBuffer.sample (rainbow :220-256): stratified v_i ~ U(seg*i, seg*(i+1)), root->leaf descent,
+ * is_weight = (size * p/total)^(-beta) / max.  d_uniforms: optional pre-drawn U[0,1) float64[B] (parity).
+ * return_tree_index bit 0: return tree indices like dialect B (ddqn_per_cartpole.py:94-106); bit 1: d_uniforms holds
+ * raw prefix values v (a batch of SumTree.get_index(v) calls). */
+int gymrl_sumtree_sample(const double* d_tree, int capacity, int batch, const double* d_uniforms,
+                         const int32_t* d_ring_state, const double* d_beta, int32_t* d_out_idx, float* d_out_is_weight,
+                         double* d_out_priority, uint32_t* d_scratch_u32, int return_tree_index, uint64_t seed,
+                         uint32_t draw, const uint32_t* d_draw_base, void* stream);
+
+/* ------------------------------------------------------------------------------------------------
+ * TD targets / losses.  Each writes dL/d(network outputs); the dense-layer backward
+ * kernels take it from there.  Loss accumulators are device float[2] = {sum of losses, #calls}.
+ * ---------------------------------------------------------------------------------------------- */
+/* DQN (algorithms/dqn_cartpole.py:149-157): y = r + gamma*max_a' Qt(s')*(1-d), mse.  Pass d_qnext_online for
+ * double-Q (rainbow_dqn_cartpole.py:319-338: a* = argmax online(s'), y = R + gamma^n (1-terminal) Qt(s')[a*],
+ * loss = mean(w * td^2), td exported).  Pass the d_v* value streams for the dueling head
+ * Q = V + A - mean(A) (rainbow :108-113); then d_q* are the advantage streams and d_dq/d_dv their gradients. */
+int gymrl_dqn_loss(const float* d_q, int ld_q, const float* d_v, int ld_v, const float* d_qnext_target, int ld_qt,
+                   const float* d_vnext_target, int ld_vt, const float* d_qnext_online, int ld_qo,
+                   const float* d_vnext_online, int ld_vo, const int32_t* d_row_index, const int32_t* d_action,
+                   const float* d_reward, const float* d_done, const float* d_is_weight, float* d_dq, int ld_dq,
+                   float* d_dv, int ld_dv, float* d_td_error, float* d_loss_acc, int batch, int n_actions,
+                   float gamma_n, void* stream);
+/* y = r + gamma (1-d) (min(Q1t, Q2t) - alpha logpi')   (sac_pendulum.py:233-237; logp_next NULL -> TD3 :200-204) */
+int gymrl_twin_q_target(const float* d_reward, const float* d_done, const int32_t* d_row_index, const float* d_q1t,
+                        int ld_q1t, const float* d_q2t, int ld_q2t, const float* d_logp_next, const double* d_log_alpha,
+                        float gamma, float* d_y, int batch, void* stream);
+/* mse(q1, y) + mse(q2, y) and its gradients (sac :239-242, td3 :206-209) */
+int gymrl_twin_q_loss(const float* d_q1, int ld_q1, const float* d_q2, int ld_q2, const float* d_y, float* d_dq1,
+                      int ld_dq1, float* d_dq2, int ld_dq2, float* d_loss_acc, int batch, void* stream);
+/* d/dq of -mean(min(q1, q2)) (sac :250-251, ties split like torch.min) or of -mean(q1) (q1_only; td3 :216);
+ * *d_acc += that loss term (nullable). */
+int gymrl_min_q_grad(const float* d_q1, int ld_q1, const float* d_q2, int ld_q2, float* d_dq1, int ld_dq1, float* d_dq2,
+                     int ld_dq2, int batch, int q1_only, float* d_acc, void* stream);
+/* SAC actor (sac :76-87, :248-251): gradient of mean(alpha*logpi - minQ) wrt (mean, log_std) through
+ * x = mean + exp(clamp(log_std))*xi, a = tanh(x)*bound, given d(-minQ/B)/da from the critic's input gradient.
+ * d_acc[0] += alpha*mean(logpi), d_acc[1] += sum(logpi) (consumed by gymrl_sac_alpha_step). */
+int gymrl_sac_actor_grad(const float* d_pre_tanh, const float* d_noise, const float* d_log_std, int ld_log_std,
+                         const float* d_dq_daction, int ld_dq, const double* d_log_alpha, float bound, float log_std_min,
+                         float log_std_max, float* d_dmean, float* d_dlog_std, int ld_out, const float* d_logp,
+                         float* d_acc, int batch, int act_dim, void* stream);
+/* alpha_loss = -mean(log_alpha*(logpi + target_entropy)) and one Adam step (lr, default betas/eps) on the float64
+ * scalar log_alpha (sac :257-263). d_adam_state = float64[3] {exp_avg, exp_avg_sq, step}. */
+int gymrl_sac_alpha_step(double* d_log_alpha, double* d_adam_state, const float* d_acc, int batch, double target_entropy,
+                         double lr, float* d_loss_out, void* stream);
+/* a = tanh(z)*bound (td3_pendulum.py:59-62) and its backward dz = da * bound * (1 - (a/bound)^2) (td3 :215-217). */
+int gymrl_tanh_bound(const float* d_z, int ld_z, float* d_action, float bound, int batch, int act_dim, void* stream);
+int gymrl_tanh_bound_grad(const float* d_action, const float* d_dq_daction, int ld_dq, float* d_dz, int ld_dz, float bound,
+                          int batch, int act_dim, void* stream);
+/* N(0,1) draws kept in a buffer (Normal.rsample / torch.randn_like) so forward and backward share them. */
+int gymrl_fill_normal(float* d_out, int n, uint64_t seed, uint64_t entity0, uint32_t draw, const uint32_t* d_draw_base,
+                      void* stream);
+/* NoisyLinear (rainbow_dqn_cartpole.py:51-97): eps = sign(xi) sqrt|xi| (d_xi optional pre-drawn normals);
+ * W = mu + sigma*outer(eps_out, eps_in), b = b_mu + b_sigma*eps_out; and the backward of that composition. */
+int gymrl_noisy_sample(float* d_eps, const float* d_xi, int n, uint64_t seed, uint64_t entity, uint32_t draw,
+                       const uint32_t* d_draw_base, void* stream);
+int gymrl_noisy_compose(const float* d_w_mu, const float* d_w_sigma, const float* d_eps_in, const float* d_eps_out,
+                        const float* d_b_mu, const float* d_b_sigma, float* d_w, float* d_b, int N, int K, void* stream);
+int gymrl_noisy_backward(const float* d_dw, const float* d_db, const float* d_eps_in, const float* d_eps_out,
+                         float* d_dw_mu, float* d_dw_sigma, float* d_db_mu, float* d_db_sigma, int N, int K,
+                         int accumulate, void* stream);
+
 #ifdef __cplusplus
 }
 #endif
