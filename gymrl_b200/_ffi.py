@@ -56,6 +56,8 @@ SIGNATURES = {
     "gymrl_sum_sumsq": (c_int, [_P, c_ll, _P, _P]),
     "gymrl_normalize_inplace": (c_int, [_P, c_ll, _P, c_double, c_int, c_float, _P]),
     "gymrl_ppo_loss": (c_int, [_P, c_int, _P, c_int, _P, _P, _P, _P, _P, _P, _P, _P, c_int, _P, c_int, _P, c_int, c_int, _P, _P]),
+    "gymrl_set_gemm_mode": (c_int, [c_int]),
+    "gymrl_get_gemm_mode": (c_int, []),
     "gymrl_linear_forward": (c_int, [_P, c_int, _P, _P, _P, _P, c_int, c_int, c_int, c_int, c_int, _P]),
     "gymrl_linear_backward_input": (c_int, [_P, c_int, _P, _P, c_int, _P, c_int, c_int, c_int, c_int, c_int, c_int, _P]),
     "gymrl_linear_backward_weight_workspace": (c_size_t, [c_int, c_int, c_int]),

@@ -35,6 +35,7 @@ SOURCES = {
     "sample.cu": [],
     "ppo_loss.cu": [],
     "linear.cu": [],
+    "linear_tc.cu": [],
     "optim.cu": [],
     "replay.cu": [],
     "qlearn.cu": [],

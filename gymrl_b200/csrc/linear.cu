@@ -17,8 +17,28 @@
 // deterministic split-M partial sums + fused column sums for db (backward weight; reduced by
 // reduce_partials_kernel so results do not depend on atomics ordering).
 #include "common.cuh"
+#include "linear_tc.cuh"
+
+#include <cstdlib>
+#include <cstring>
 
 void gymrl_count_launch(int n = 1);
+
+// GEMM engine selection: 0 = fp32 FFMA tiles (this file), 1 = tcgen05 3xTF32 (linear_tc.cu) where the shape gate allows.
+static int g_gemm_mode = -1;
+static int gemm_mode() {
+    if (g_gemm_mode < 0) {
+        const char* e = getenv("GYMRL_GEMM");
+        g_gemm_mode = (e && strcmp(e, "ffma") == 0) ? 0 : 1;
+    }
+    return g_gemm_mode;
+}
+extern "C" int gymrl_set_gemm_mode(int mode) {
+    GYMRL_REQUIRE(mode == 0 || mode == 1, "mode must be 0 (ffma) or 1 (tcgen05 3xTF32)");
+    g_gemm_mode = mode;
+    return GYMRL_OK;
+}
+extern "C" int gymrl_get_gemm_mode(void) { return gemm_mode(); }
 
 struct GemmParams {
     const float* A; int lda; const int32_t* a_rows;
@@ -282,6 +302,18 @@ extern "C" int gymrl_linear_forward(const float* d_x, int ldx, const int32_t* d_
     p.k_chunk = K; p.c_split_stride = 0;
     p.vecA = aligned16(d_x) && (ldx % 4 == 0);
     p.vecB = aligned16(d_w) && (K % 4 == 0);
+    if (gemm_mode() == 1) {
+        TcGemmParams t;
+        memset(&t, 0, sizeof(t));
+        t.A = d_x; t.lda = ldx; t.a_rows = d_row_index; t.B = d_w; t.ldb = K; t.C = d_y; t.ldc = ldy;
+        t.M = M; t.N = N; t.K = K; t.bias = d_b; t.act = act; t.k_chunk = K;
+        if (tc_gemm_supported(t, true, true)) {
+            int rc = tc_gemm_launch(t, true, true, 1, as_stream(stream));
+            if (rc != GYMRL_OK) return rc;
+            GYMRL_LAUNCH_CHECK("linear_forward(tc)");
+            return GYMRL_OK;
+        }
+    }
     launch_gemm<true, true>(p, 1, as_stream(stream));
     GYMRL_LAUNCH_CHECK("linear_forward");
     return GYMRL_OK;
@@ -304,6 +336,18 @@ extern "C" int gymrl_linear_backward_input(const float* d_dy, int lddy, const fl
     p.k_chunk = N;
     p.vecA = aligned16(d_dy) && (lddy % 4 == 0);
     p.vecB = aligned16(d_w) && (K % 4 == 0);
+    if (gemm_mode() == 1 && !accumulate) {
+        TcGemmParams t;
+        memset(&t, 0, sizeof(t));
+        t.A = d_dy; t.lda = lddy; t.B = d_w; t.ldb = K; t.C = d_dx; t.ldc = lddx;
+        t.M = M; t.N = K; t.K = N; t.H = d_h_in; t.ldh = ldh; t.act_in = act_in; t.k_chunk = N;
+        if (tc_gemm_supported(t, true, false) && (!d_h_in || (ldh % 4 == 0))) {
+            int rc = tc_gemm_launch(t, true, false, 1, as_stream(stream));
+            if (rc != GYMRL_OK) return rc;
+            GYMRL_LAUNCH_CHECK("linear_backward_input(tc)");
+            return GYMRL_OK;
+        }
+    }
     launch_gemm<true, false>(p, 1, as_stream(stream));
     GYMRL_LAUNCH_CHECK("linear_backward_input");
     return GYMRL_OK;
@@ -323,6 +367,23 @@ static int dw_splits(int M, int N, int K) {
 extern "C" size_t gymrl_linear_backward_weight_workspace(int M, int N, int K) {
     const int s = dw_splits(M, N, K);
     return (size_t)s * ((size_t)N * K + (size_t)N) * sizeof(float);
+}
+
+// db[n] (+)= sum_m dY[m][n]: used when the tensor-core dW path (which has no fused column sums) is taken
+__global__ void colsum_kernel(const float* __restrict__ dy, int lddy, int M, int N, float* __restrict__ db, int accumulate) {
+    __shared__ float sm[8][33];
+    const int n = blockIdx.x * 32 + (threadIdx.x & 31), g = threadIdx.x >> 5;
+    float s = 0.f;
+    if (n < N)
+        for (int m = g; m < M; m += 8) s += dy[(size_t)m * lddy + n];
+    sm[g][threadIdx.x & 31] = s;
+    __syncthreads();
+    if (g == 0 && n < N) {
+        float tot = 0.f;
+#pragma unroll
+        for (int k = 0; k < 8; ++k) tot += sm[k][threadIdx.x];
+        db[n] = accumulate ? db[n] + tot : tot;
+    }
 }
 
 __global__ void reduce_partials_kernel(const float* __restrict__ ws, long long count, int splits, float* __restrict__ out,
@@ -357,6 +418,28 @@ extern "C" int gymrl_linear_backward_weight(const float* d_dy, int lddy, const f
     p.rowsum = d_db ? ws_db : nullptr;
     p.vecA = aligned16(d_dy) && (lddy % 4 == 0);
     p.vecB = aligned16(d_x) && (ldx % 4 == 0);
+    if (gemm_mode() == 1) {
+        TcGemmParams t;
+        memset(&t, 0, sizeof(t));
+        t.A = d_dy; t.lda = lddy; t.B = d_x; t.ldb = ldx; t.b_rows = d_row_index; t.C = ws; t.ldc = K;
+        t.M = N; t.N = K; t.K = M;
+        int tsplits = splits, tchunk = ceil_div(ceil_div(M, tsplits), 32) * 32;
+        t.k_chunk = tchunk; t.c_split_stride = (long long)N * K;
+        if ((M % 32 == 0) && tc_gemm_supported(t, false, false)) {
+            int rc = tc_gemm_launch(t, false, false, tsplits, s);
+            if (rc != GYMRL_OK) return rc;
+            GYMRL_LAUNCH_CHECK("linear_backward_weight(tc)");
+            const long long cnt2 = (long long)N * K;
+            reduce_partials_kernel<<<(unsigned)ceil_div_ll(cnt2, 256), 256, 0, s>>>(ws, cnt2, tsplits, d_dw, accumulate);
+            gymrl_count_launch();
+            if (d_db) {
+                colsum_kernel<<<ceil_div(N, 32), 256, 0, s>>>(d_dy, lddy, M, N, d_db, accumulate);
+                gymrl_count_launch();
+            }
+            GYMRL_LAUNCH_CHECK("reduce_partials(tc)");
+            return GYMRL_OK;
+        }
+    }
     {
         dim3 grid(ceil_div(K, 64), ceil_div(N, 64), splits);
         gemm_kernel<64, 64, 4, 4, false, false><<<grid, 256, 0, s>>>(p);

@@ -1,0 +1,292 @@
+// linear_tc.cu — tcgen05 (5th-gen tensor core) path of the dense layers: fp32-accurate GEMM by 3xTF32 splitting.
+//
+//   C[M][N] (+epilogue) = sum_k A(m,k) B(n,k),  A/B fp32 in global memory, accumulation in TMEM (fp32).
+//
+// Every fp32 operand x is split in registers into hi = tf32(x) and lo = tf32(x - hi); the product is
+// accumulated as  A_lo*B_hi + A_hi*B_lo + A_hi*B_hi  (the dropped lo*lo term is ~2^-22 relative), which keeps
+// the reference's fp32 parity bar while running on the tensor pipe (kind::tf32, UMMA 128 x BN x 8).
+//
+// One CTA (4 warps) owns a 128 x BN output tile (BN = 64/128/256 -> 64..256 TMEM columns):
+//   stage loop over K in slabs of 32 floats (= one 128-byte swizzle span), two smem stages:
+//     all 128 threads: LDG.128 the A/B slab (row gather fused for A), split hi/lo, STS.128 into the canonical
+//                      UMMA shared-memory layout (SWIZZLE_128B; K-major: 8-row x 128 B atoms, MN-major: 8 k-rows x 128 B
+//                      atoms), fence.proxy.async, __syncthreads
+//     one elected thread: 4 k-steps x 3 tcgen05.mma (descriptors advance 32 B inside the swizzle atom for K-major,
+//                      one atom row-block per k-step for MN-major), tcgen05.commit -> mbarrier that frees the stage
+//   so the tensor core works on stage s while the threads fill stage s^1 (operands never round-trip through HBM
+//   in split form).  Epilogue: tcgen05.ld 32 lanes x 32 columns per warp -> bias / tanh / relu / act'(h) -> global.
+//   Backward-weight runs split-K over blockIdx.z with deterministic partial tiles (reduced by linear.cu).
+// No TMA: the operands need the register pass for the split (and the minibatch row gather), so a bulk tensor
+// copy cannot produce them; staging is plain coalesced 128 B row reads instead.
+// All mbarrier waits are bounded (trap on timeout) so a descriptor bug cannot hang the GPU.
+#include "common.cuh"
+
+void gymrl_count_launch(int n = 1);
+
+#include "linear_tc.cuh"
+
+__device__ __forceinline__ uint32_t smem_u32(const void* p) { return (uint32_t)__cvta_generic_to_shared(p); }
+
+__device__ __forceinline__ void mbar_init(uint64_t* bar, uint32_t count) {
+    asm volatile("mbarrier.init.shared::cta.b64 [%0], %1;" ::"r"(smem_u32(bar)), "r"(count));
+}
+__device__ __forceinline__ void mbar_wait(uint64_t* bar, uint32_t parity) {
+    const uint32_t addr = smem_u32(bar);
+    for (uint32_t it = 0; it < (1u << 24); ++it) {
+        uint32_t done;
+        asm volatile("{\n.reg .pred p;\nmbarrier.try_wait.parity.shared::cta.b64 p, [%1], %2;\nselp.b32 %0, 1, 0, p;\n}\n"
+                     : "=r"(done) : "r"(addr), "r"(parity) : "memory");
+        if (done) return;
+    }
+    __trap();  // bounded wait: fail loudly instead of hanging the GPU
+}
+__device__ __forceinline__ void umma_commit(uint64_t* bar) {
+    asm volatile("tcgen05.commit.cta_group::1.mbarrier::arrive::one.shared::cluster.b64 [%0];" ::"r"(smem_u32(bar)) : "memory");
+}
+__device__ __forceinline__ void umma_tf32(uint32_t tmem_d, uint64_t desc_a, uint64_t desc_b, uint32_t idesc, uint32_t accumulate) {
+    asm volatile("{\n.reg .pred p;\nsetp.ne.b32 p, %4, 0;\ntcgen05.mma.cta_group::1.kind::tf32 [%0], %1, %2, %3, p;\n}\n"
+                 ::"r"(tmem_d), "l"(desc_a), "l"(desc_b), "r"(idesc), "r"(accumulate) : "memory");
+}
+// shared-memory matrix descriptor (cute::UMMA::SmemDescriptor, sm_100): SWIZZLE_128B, version 1
+__device__ __forceinline__ uint64_t make_desc(uint32_t smem_addr, uint32_t lbo_bytes, uint32_t sbo_bytes, uint32_t layout_type = 2) {
+    uint64_t d = 0;
+    d |= (uint64_t)((smem_addr >> 4) & 0x3FFF);
+    d |= (uint64_t)((lbo_bytes >> 4) & 0x3FFF) << 16;
+    d |= (uint64_t)((sbo_bytes >> 4) & 0x3FFF) << 32;
+    d |= (uint64_t)1 << 46;             // version = 1 (Blackwell)
+    d |= (uint64_t)layout_type << 61;   // 2 = SWIZZLE_128B (K-major), 1 = SWIZZLE_128B_BASE32B (tf32 MN-major)
+    return d;
+}
+// MN-major tf32 slab [ROWS x 32 k]: block (k-atom jk of 4 rows, MN-atom i of 32 elements) at (jk*ROWS/32 + i)*512 B.
+// One UMMA k-step (8 k) = k-atoms 2j, 2j+1:  LBO = 512 B between MN atoms, SBO = ROWS/32 * 512 B between k-atoms.
+template <int ROWS>
+__device__ __forceinline__ uint64_t make_desc_mn(uint32_t base, int j) {
+    return make_desc(base + (uint32_t)(2 * j * (ROWS / 32)) * 512u, 512u, (uint32_t)(ROWS / 32) * 512u, 1u);
+}
+__device__ __forceinline__ uint32_t to_tf32(float x) {
+    uint32_t r;
+    asm("cvt.rna.tf32.f32 %0, %1;" : "=r"(r) : "f"(x));
+    return r;
+}
+__device__ __forceinline__ void split4(const float4 v, uint4& hi, uint4& lo) {
+    hi.x = to_tf32(v.x); hi.y = to_tf32(v.y); hi.z = to_tf32(v.z); hi.w = to_tf32(v.w);
+    lo.x = to_tf32(v.x - __uint_as_float(hi.x)); lo.y = to_tf32(v.y - __uint_as_float(hi.y));
+    lo.z = to_tf32(v.z - __uint_as_float(hi.z)); lo.w = to_tf32(v.w - __uint_as_float(hi.w));
+}
+
+// Stage one [ROWS x 32] operand slab into smem (hi and lo images).
+//  KMAJOR: global rows are the MN index (128 B = 32 k per row);  smem atom = 8 MN-rows x 128 B, atoms stacked along MN (1024 B).
+//  !KMAJOR: global rows are the k index (contiguous MN);         smem block(j, i) = k-atom j (8 k-rows x 128 B) of MN-atom i
+//           (32 MN elements), at ((j * ROWS/32) + i) * 1024.
+template <int ROWS, bool KMAJOR>
+__device__ __forceinline__ void stage_operand(uint8_t* s_hi, uint8_t* s_lo, const float* __restrict__ g, int ld,
+                                              const int32_t* __restrict__ rows, int mn0, int mn_total, int k0, int k_end) {
+    const int t = threadIdx.x;
+    constexpr int PASSES = ROWS * 8 / 128;  // float4 per thread
+    float4 v[PASSES];
+    if (KMAJOR) {
+#pragma unroll
+        for (int i = 0; i < PASSES; ++i) {
+            const int r = (t >> 3) + 16 * i, c = t & 7;
+            const int mn = mn0 + r;
+            v[i] = make_float4(0.f, 0.f, 0.f, 0.f);
+            if (mn < mn_total && k0 + c * 4 < k_end) {
+                const long long gr = rows ? (long long)rows[mn] : (long long)mn;
+                v[i] = *reinterpret_cast<const float4*>(g + gr * ld + k0 + c * 4);
+            }
+        }
+#pragma unroll
+        for (int i = 0; i < PASSES; ++i) {
+            const int r = (t >> 3) + 16 * i, c = t & 7;
+            const uint32_t off = (uint32_t)(r >> 3) * 1024u + (uint32_t)(r & 7) * 128u + (uint32_t)((c ^ (r & 7)) << 4);
+            uint4 hi, lo;
+            split4(v[i], hi, lo);
+            *reinterpret_cast<uint4*>(s_hi + off) = hi;
+            *reinterpret_cast<uint4*>(s_lo + off) = lo;
+        }
+    } else {
+        // 32 k-rows x ROWS contiguous MN: thread handles k = (t / (ROWS/4)) + step, MN chunk = t % (ROWS/4)
+        constexpr int CH = ROWS / 4;            // float4 per k-row
+        constexpr int KSTEP = 128 / CH;         // k-rows covered per pass (ROWS=128: 4, ROWS=256: 2, ROWS=64: 8)
+#pragma unroll
+        for (int i = 0; i < PASSES; ++i) {
+            const int kk = (t / CH) + KSTEP * i, c = t % CH;
+            const int k = k0 + kk, mn = mn0 + c * 4;
+            v[i] = make_float4(0.f, 0.f, 0.f, 0.f);
+            if (k < k_end && mn < mn_total) {
+                const long long gr = rows ? (long long)rows[k] : (long long)k;
+                v[i] = *reinterpret_cast<const float4*>(g + gr * ld + mn);
+            }
+        }
+#pragma unroll
+        for (int i = 0; i < PASSES; ++i) {
+            const int kk = (t / CH) + KSTEP * i, c = t % CH;
+            // tf32 MN-major operands must use SWIZZLE_128B_BASE32B (cutlass sm100_common.inl:92): atoms of 4 k-rows x 128 B,
+            // Swizzle<2,5,2> = the 32-byte chunk index is XOR-ed with the k-row index inside the atom
+            const int jk = kk >> 2, kr = kk & 3, ai = c >> 3, c16 = c & 7;   // k-atom, row in atom, MN-atom, 16 B chunk in row
+            const uint32_t off = (uint32_t)(jk * (ROWS / 32) + ai) * 512u + (uint32_t)kr * 128u +
+                                 (uint32_t)((((c16 >> 1) ^ kr) << 5) | ((c16 & 1) << 4));
+            uint4 hi, lo;
+            split4(v[i], hi, lo);
+            *reinterpret_cast<uint4*>(s_hi + off) = hi;
+            *reinterpret_cast<uint4*>(s_lo + off) = lo;
+        }
+    }
+}
+
+template <int BN, bool A_KMAJOR, bool B_KMAJOR>
+__global__ void __launch_bounds__(128, 1) gemm_tf32x3_kernel(const TcGemmParams p) {
+    constexpr int BM = 128;
+    constexpr uint32_t A_BYTES = BM * 128, B_BYTES = BN * 128;           // one image (hi or lo) of one 32-k slab
+    constexpr uint32_t STAGE_BYTES = 2 * A_BYTES + 2 * B_BYTES;
+    extern __shared__ __align__(1024) uint8_t smem_raw[];
+    uint8_t* smem = reinterpret_cast<uint8_t*>((reinterpret_cast<uintptr_t>(smem_raw) + 1023) & ~(uintptr_t)1023);
+    __shared__ __align__(8) uint64_t bar_free[2];
+    __shared__ __align__(8) uint64_t bar_acc;
+    __shared__ uint32_t tmem_base_s;
+
+    const int t = threadIdx.x, warp = t >> 5;
+    const int m0 = blockIdx.y * BM, n0 = blockIdx.x * BN;
+    const int kbeg = blockIdx.z * p.k_chunk;
+    const int kend = min(p.K, kbeg + p.k_chunk);
+    const int nslab = (kend - kbeg + 31) / 32;
+
+    if (t == 0) {
+        mbar_init(&bar_free[0], 1);
+        mbar_init(&bar_free[1], 1);
+        mbar_init(&bar_acc, 1);
+        asm volatile("fence.mbarrier_init.release.cluster;" ::: "memory");
+    }
+    if (warp == 0) {
+        asm volatile("tcgen05.alloc.cta_group::1.sync.aligned.shared::cta.b32 [%0], %1;" ::"r"(smem_u32(&tmem_base_s)), "n"(BN) : "memory");
+        asm volatile("tcgen05.relinquish_alloc_permit.cta_group::1.sync.aligned;" ::: "memory");
+    }
+    asm volatile("tcgen05.fence::before_thread_sync;" ::: "memory");
+    __syncthreads();
+    asm volatile("tcgen05.fence::after_thread_sync;" ::: "memory");
+    const uint32_t tmem_d = tmem_base_s;
+
+    // instruction descriptor (cute::UMMA::InstrDescriptor): D=F32, A=B=TF32, majors, N>>3, M>>4
+    constexpr uint32_t IDESC = (1u << 4) | (2u << 7) | (2u << 10) | ((A_KMAJOR ? 0u : 1u) << 15) | ((B_KMAJOR ? 0u : 1u) << 16) |
+                               ((uint32_t)(BN >> 3) << 17) | ((uint32_t)(BM >> 4) << 24);
+
+    for (int kb = 0; kb < nslab; ++kb) {
+        const int s = kb & 1, use = kb >> 1;
+        if (use >= 1) mbar_wait(&bar_free[s], (uint32_t)((use - 1) & 1));   // MMAs that read this stage have retired
+        uint8_t* st = smem + (size_t)s * STAGE_BYTES;
+        uint8_t *a_hi = st, *a_lo = st + A_BYTES, *b_hi = st + 2 * A_BYTES, *b_lo = st + 2 * A_BYTES + B_BYTES;
+        const int k0 = kbeg + kb * 32;
+        stage_operand<BM, A_KMAJOR>(a_hi, a_lo, p.A, p.lda, p.a_rows, m0, p.M, k0, kend);
+        stage_operand<BN, B_KMAJOR>(b_hi, b_lo, p.B, p.ldb, p.b_rows, n0, p.N, k0, kend);
+        asm volatile("fence.proxy.async.shared::cta;" ::: "memory");   // generic-proxy smem writes -> visible to the tensor core
+        __syncthreads();
+        if (t == 0) {
+            asm volatile("tcgen05.fence::after_thread_sync;" ::: "memory");
+            const uint32_t ah = smem_u32(a_hi), al = smem_u32(a_lo), bh = smem_u32(b_hi), bl = smem_u32(b_lo);
+#pragma unroll
+            for (int j = 0; j < 4; ++j) {   // 4 k-steps of 8
+                // K-major: +32 B inside the 128 B swizzle span (LBO = 16 B unused, SBO = 1024 B between 8-row atoms)
+                // MN-major: k-atom j starts at j * (ROWS/32) KiB; LBO = 1024 B between MN atoms, SBO = k-atom stride
+                const uint64_t dah = A_KMAJOR ? make_desc(ah + j * 32, 16, 1024) : make_desc_mn<BM>(ah, j);
+                const uint64_t dal = A_KMAJOR ? make_desc(al + j * 32, 16, 1024) : make_desc_mn<BM>(al, j);
+                const uint64_t dbh = B_KMAJOR ? make_desc(bh + j * 32, 16, 1024) : make_desc_mn<BN>(bh, j);
+                const uint64_t dbl = B_KMAJOR ? make_desc(bl + j * 32, 16, 1024) : make_desc_mn<BN>(bl, j);
+                umma_tf32(tmem_d, dal, dbh, IDESC, (kb | j) ? 1u : 0u);
+                umma_tf32(tmem_d, dah, dbl, IDESC, 1u);
+                umma_tf32(tmem_d, dah, dbh, IDESC, 1u);
+            }
+            umma_commit(&bar_free[s]);
+            if (kb == nslab - 1) umma_commit(&bar_acc);
+        }
+    }
+
+    // ---- epilogue: TMEM -> registers -> global ----
+    if (nslab > 0) mbar_wait(&bar_acc, 0);
+    asm volatile("tcgen05.fence::after_thread_sync;" ::: "memory");
+    const int m = m0 + t;   // thread t owns accumulator row (TMEM lane) t
+    float* Cbase = p.C + (long long)blockIdx.z * p.c_split_stride;
+#pragma unroll 1
+    for (int c0 = 0; c0 < BN; c0 += 32) {
+        uint32_t r[32];
+        const uint32_t taddr = tmem_d + ((uint32_t)(warp * 32) << 16) + (uint32_t)c0;
+        asm volatile(
+            "tcgen05.ld.sync.aligned.32x32b.x32.b32 "
+            "{%0, %1, %2, %3, %4, %5, %6, %7, %8, %9, %10, %11, %12, %13, %14, %15, "
+            "%16, %17, %18, %19, %20, %21, %22, %23, %24, %25, %26, %27, %28, %29, %30, %31}, [%32];"
+            : "=r"(r[0]), "=r"(r[1]), "=r"(r[2]), "=r"(r[3]), "=r"(r[4]), "=r"(r[5]), "=r"(r[6]), "=r"(r[7]), "=r"(r[8]), "=r"(r[9]),
+              "=r"(r[10]), "=r"(r[11]), "=r"(r[12]), "=r"(r[13]), "=r"(r[14]), "=r"(r[15]), "=r"(r[16]), "=r"(r[17]), "=r"(r[18]),
+              "=r"(r[19]), "=r"(r[20]), "=r"(r[21]), "=r"(r[22]), "=r"(r[23]), "=r"(r[24]), "=r"(r[25]), "=r"(r[26]), "=r"(r[27]),
+              "=r"(r[28]), "=r"(r[29]), "=r"(r[30]), "=r"(r[31])
+            : "r"(taddr));
+        asm volatile("tcgen05.wait::ld.sync.aligned;" ::: "memory");
+        if (m < p.M) {
+#pragma unroll
+            for (int q = 0; q < 8; ++q) {
+                const int n = n0 + c0 + q * 4;
+                if (n >= p.N) continue;
+                float o[4];
+#pragma unroll
+                for (int e = 0; e < 4; ++e) {
+                    float v = nslab > 0 ? __uint_as_float(r[q * 4 + e]) : 0.f;
+                    if (p.bias) v += p.bias[n + e];
+                    if (p.act == GYMRL_ACT_TANH) v = tanhf(v);
+                    else if (p.act == GYMRL_ACT_RELU) v = fmaxf(v, 0.f);
+                    if (p.H) {
+                        const float h = p.H[(long long)m * p.ldh + n + e];
+                        if (p.act_in == GYMRL_ACT_TANH) v *= (1.0f - h * h);
+                        else if (p.act_in == GYMRL_ACT_RELU) v = h > 0.f ? v : 0.f;
+                    }
+                    o[e] = v;
+                }
+                *reinterpret_cast<float4*>(Cbase + (long long)m * p.ldc + n) = make_float4(o[0], o[1], o[2], o[3]);
+            }
+        }
+    }
+    asm volatile("tcgen05.fence::before_thread_sync;" ::: "memory");
+    __syncthreads();
+    if (warp == 0) {
+        asm volatile("tcgen05.dealloc.cta_group::1.sync.aligned.b32 %0, %1;" ::"r"(tmem_d), "n"(BN) : "memory");
+    }
+}
+
+// ---- host side ------------------------------------------------------------------------------------------
+template <int BN, bool AK, bool BKM>
+static int launch_tc(const TcGemmParams& p, int splits, cudaStream_t s) {
+    constexpr size_t SMEM = 2 * (2 * 128 * 128 + 2 * BN * 128) + 1024;
+    static bool configured = false;
+    if (!configured) {
+        cudaError_t e = cudaFuncSetAttribute(gemm_tf32x3_kernel<BN, AK, BKM>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)SMEM);
+        if (e != cudaSuccess) GYMRL_FAIL(GYMRL_ECUDA, "cudaFuncSetAttribute(smem=%zu) failed: %s", SMEM, cudaGetErrorString(e));
+        configured = true;
+    }
+    dim3 grid(p.N / BN, ceil_div(p.M, 128), splits);
+    gemm_tf32x3_kernel<BN, AK, BKM><<<grid, 128, SMEM, s>>>(p);
+    gymrl_count_launch();
+    return GYMRL_OK;
+}
+
+static inline bool al16(const void* ptr) { return (reinterpret_cast<uintptr_t>(ptr) & 15) == 0; }
+
+// Shape / alignment gate for the tensor-core path (anything else stays on the FFMA kernel in linear.cu).
+bool tc_gemm_supported(const TcGemmParams& p, bool a_kmajor, bool b_kmajor) {
+    if (p.N % 64 != 0 || p.K % 32 != 0 || p.k_chunk % 32 != 0) return false;
+    if (!al16(p.A) || !al16(p.B) || !al16(p.C) || (p.lda & 3) || (p.ldb & 3) || (p.ldc & 3)) return false;
+    if (!a_kmajor && (p.M % 4 != 0)) return false;
+    if (p.H && (!al16(p.H))) return false;
+    return p.M >= 128;
+}
+
+int tc_gemm_launch(const TcGemmParams& p, bool a_kmajor, bool b_kmajor, int splits, cudaStream_t s) {
+    const int bn = (p.N % 256 == 0) ? 256 : (p.N % 128 == 0 ? 128 : 64);
+#define TC_DISPATCH(AK, BKM)                                             \
+    switch (bn) {                                                        \
+        case 256: return launch_tc<256, AK, BKM>(p, splits, s);          \
+        case 128: return launch_tc<128, AK, BKM>(p, splits, s);          \
+        default: return launch_tc<64, AK, BKM>(p, splits, s);            \
+    }
+    if (a_kmajor && b_kmajor) { TC_DISPATCH(true, true) }
+    if (a_kmajor && !b_kmajor) { TC_DISPATCH(true, false) }
+    if (!a_kmajor && !b_kmajor) { TC_DISPATCH(false, false) }
+#undef TC_DISPATCH
+    GYMRL_FAIL(GYMRL_EINVAL, "unsupported operand major combination");
+}

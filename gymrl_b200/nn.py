@@ -27,11 +27,15 @@ def flatten_module(module: nn.Module, order: Optional[Sequence[str]] = None, dev
     names = list(order) if order is not None else list(named.keys())
     assert sorted(names) == sorted(named.keys()), "order must list every parameter exactly once"
     device = device or next(iter(named.values())).device
-    # keep every segment 16-byte aligned so GEMM operand loads can be float4
+    # matrices start 16-byte aligned so GEMM operand loads can be float4; vectors (biases) are packed back to
+    # back so that sibling heads' biases stay contiguous (FlatParams.span views them as one vector)
     offsets, total = {}, 0
     for n in names:
+        if named[n].dim() >= 2:
+            total = (total + 3) // 4 * 4
         offsets[n] = total
-        total += (named[n].numel() + 3) // 4 * 4
+        total += named[n].numel()
+    total = (total + 3) // 4 * 4
     flat = torch.zeros(total, device=device, dtype=torch.float32)
     grad = torch.zeros(total, device=device, dtype=torch.float32)
     views: Dict[str, tuple] = {}
@@ -70,6 +74,11 @@ class FlatParams:
         """View consecutive parameters [first .. last] as one [rows, cols] matrix (e.g. actor.0.weight and
         critic.0.weight stacked into a single [512, 256] GEMM operand)."""
         o0 = self.views[first][0]
+        o1, shape1 = self.views[last]
+        n1 = 1
+        for s in shape1:
+            n1 *= s
+        assert o1 + n1 - o0 == rows * cols, f"parameters {first}..{last} are not contiguous in the flat buffer"
         buf = self.grad if grad else self.flat
         return buf[o0:o0 + rows * cols].view(rows, cols)
 

@@ -184,6 +184,13 @@ int gymrl_ppo_loss(const float* d_logits, int ld_logits, const float* d_value, i
 #define GYMRL_ACT_TANH 1
 #define GYMRL_ACT_RELU 2
 
+/* GEMM engine: 1 (default) = tcgen05 3xTF32 tensor-core kernel (fp32-accurate: every operand split into
+ * tf32 hi + lo, three MMAs per product, fp32 accumulation in TMEM) wherever the shape gate allows
+ * (M >= 128, N % 64 == 0, K % 32 == 0, 16 B-aligned rows), fp32 FFMA tiles elsewhere; 0 = FFMA tiles only.
+ * Also selectable with the environment variable GYMRL_GEMM=ffma. */
+int gymrl_set_gemm_mode(int mode);
+int gymrl_get_gemm_mode(void);
+
 int gymrl_linear_forward(const float* d_x, int ldx, const int32_t* d_row_index, const float* d_w,
                          const float* d_b, float* d_y, int ldy, int M, int N, int K, int act,
                          void* stream);
