@@ -34,6 +34,7 @@ def _run_pair(dev_env, ora_env, steps, action_fn, discrete, check):
         check(f"reward@{t}", r.cpu().numpy(), orr)
         assert np.array_equal(te.cpu().numpy(), ote), f"terminated@{t}"
         assert np.array_equal(tr.cpu().numpy(), otr), f"truncated@{t}"
+        obs_o = oo
 
 
 def test_cartpole_parity():

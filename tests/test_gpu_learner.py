@@ -332,22 +332,7 @@ def test_random_permutation_is_bijection(ops, n):
 
 
 # ------------------------------------------------------------------------------------------------ end to end
-def _trainer_from_golden(g, use_graph, n_mb, seed=0):
-    from gymrl_b200.algorithms import ppo_lunarlander as P
-    B = g["states"].shape[0]
-    cfg = P.Config()
-    cfg.num_envs, cfg.num_steps, cfg.num_minibatches, cfg.num_epochs = 1, B, n_mb, 1
-    cfg.seed, cfg.use_cuda_graph = seed, use_graph
-    t = P.PPOTrainer(cfg)
-    sd = {k[3:]: torch.as_tensor(g[k]) for k in g.files if k.startswith("w0_")}
-    t.model.load_state_dict(sd)
-    t.net.fp.refresh_views()
-    buf = t.buffer
-    buf.obs[:B, 0].copy_(cu(g["states"]))
-    buf.action[:, 0].copy_(cu(g["action"])); buf.log_prob[:, 0].copy_(cu(g["logp_old"]))
-    buf.value[:, 0].copy_(cu(g["value_old"])); buf.reward[:, 0].copy_(cu(g["reward"])); buf.done[:, 0].copy_(cu(g["done"]))
-    buf.filled = B
-    return t
+from conftest import trainer_from_golden as _trainer_from_golden  # noqa: E402
 
 
 def test_ppo_update_gradients_match_reference(golden):

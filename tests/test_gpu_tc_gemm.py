@@ -78,7 +78,7 @@ def test_tc_backward_accuracy(modes, M, N, K, act):
 
 def test_tc_and_ffma_trainers_agree(modes, golden):
     """The PPO reference-parity fixture passes on both engines (the tolerance is the reference's, not loosened)."""
-    from tests.test_gpu_learner import _trainer_from_golden
+    from conftest import trainer_from_golden as _trainer_from_golden
     g = golden("ppo_update.npz")
     for mode in (0, 1):
         modes.gymrl_set_gemm_mode(mode)
