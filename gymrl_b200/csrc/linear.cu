@@ -365,24 +365,28 @@ static int dw_splits(int M, int N, int K) {
 }
 
 extern "C" size_t gymrl_linear_backward_weight_workspace(int M, int N, int K) {
-    const int s = dw_splits(M, N, K);
+    int s = dw_splits(M, N, K);
+    if (s < 64 && M >= 256) s = 64;   // the tensor-core path may use up to 64 split-M partial tiles
     return (size_t)s * ((size_t)N * K + (size_t)N) * sizeof(float);
 }
 
-// db[n] (+)= sum_m dY[m][n]: used when the tensor-core dW path (which has no fused column sums) is taken
-__global__ void colsum_kernel(const float* __restrict__ dy, int lddy, int M, int N, float* __restrict__ db, int accumulate) {
+// partial[z][n] = sum over the z-th row chunk of dY[m][n]: column sums for db when the tensor-core dW path (which has no
+// fused column sums) is taken; the chunks are then folded by reduce_partials_kernel (deterministic order).
+__global__ void colsum_partial_kernel(const float* __restrict__ dy, int lddy, int M, int N, int rows_per_chunk,
+                                      float* __restrict__ partial) {
     __shared__ float sm[8][33];
     const int n = blockIdx.x * 32 + (threadIdx.x & 31), g = threadIdx.x >> 5;
+    const int m_beg = blockIdx.y * rows_per_chunk, m_end = min(M, m_beg + rows_per_chunk);
     float s = 0.f;
     if (n < N)
-        for (int m = g; m < M; m += 8) s += dy[(size_t)m * lddy + n];
+        for (int m = m_beg + g; m < m_end; m += 8) s += dy[(size_t)m * lddy + n];
     sm[g][threadIdx.x & 31] = s;
     __syncthreads();
     if (g == 0 && n < N) {
         float tot = 0.f;
 #pragma unroll
         for (int k = 0; k < 8; ++k) tot += sm[k][threadIdx.x];
-        db[n] = accumulate ? db[n] + tot : tot;
+        partial[(size_t)blockIdx.y * N + n] = tot;
     }
 }
 
@@ -423,7 +427,12 @@ extern "C" int gymrl_linear_backward_weight(const float* d_dy, int lddy, const f
         memset(&t, 0, sizeof(t));
         t.A = d_dy; t.lda = lddy; t.B = d_x; t.ldb = ldx; t.b_rows = d_row_index; t.C = ws; t.ldc = K;
         t.M = N; t.N = K; t.K = M;
-        int tsplits = splits, tchunk = ceil_div(ceil_div(M, tsplits), 32) * 32;
+        const int tc_tiles = ceil_div(N, 128) * ceil_div(K, 256);
+        int tsplits = GYMRL_NUM_SMS / tc_tiles;
+        if (tsplits > 64) tsplits = 64;
+        if (tsplits > M / 256) tsplits = M / 256;
+        if (tsplits < 1) tsplits = 1;
+        int tchunk = ceil_div(ceil_div(M, tsplits), 32) * 32;
         t.k_chunk = tchunk; t.c_split_stride = (long long)N * K;
         if ((M % 32 == 0) && tc_gemm_supported(t, false, false)) {
             int rc = tc_gemm_launch(t, false, false, tsplits, s);
@@ -433,8 +442,11 @@ extern "C" int gymrl_linear_backward_weight(const float* d_dy, int lddy, const f
             reduce_partials_kernel<<<(unsigned)ceil_div_ll(cnt2, 256), 256, 0, s>>>(ws, cnt2, tsplits, d_dw, accumulate);
             gymrl_count_launch();
             if (d_db) {
-                colsum_kernel<<<ceil_div(N, 32), 256, 0, s>>>(d_dy, lddy, M, N, d_db, accumulate);
-                gymrl_count_launch();
+                const int chunks = 64, rpc = ceil_div(M, chunks);
+                float* ws_db2 = ws + (size_t)tsplits * N * K;   // behind the dW partial tiles (workspace is sized for 64 splits)
+                colsum_partial_kernel<<<dim3(ceil_div(N, 32), chunks), 256, 0, s>>>(d_dy, lddy, M, N, rpc, ws_db2);
+                reduce_partials_kernel<<<ceil_div(N, 256), 256, 0, s>>>(ws_db2, N, chunks, d_db, accumulate);
+                gymrl_count_launch(2);
             }
             GYMRL_LAUNCH_CHECK("reduce_partials(tc)");
             return GYMRL_OK;

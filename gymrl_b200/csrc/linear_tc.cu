@@ -7,6 +7,7 @@
 // the reference's fp32 parity bar while running on the tensor pipe (kind::tf32, UMMA 128 x BN x 8).
 //
 // One CTA (4 warps) owns a 128 x BN output tile (BN = 64/128/256 -> 64..256 TMEM columns):
+//   (8 warps / 256 threads since v2)
 //   stage loop over K in slabs of 32 floats (= one 128-byte swizzle span), two smem stages:
 //     all 128 threads: LDG.128 the A/B slab (row gather fused for A), split hi/lo, STS.128 into the canonical
 //                      UMMA shared-memory layout (SWIZZLE_128B; K-major: 8-row x 128 B atoms, MN-major: 8 k-rows x 128 B
@@ -78,16 +79,34 @@ __device__ __forceinline__ void split4(const float4 v, uint4& hi, uint4& lo) {
 //  KMAJOR: global rows are the MN index (128 B = 32 k per row);  smem atom = 8 MN-rows x 128 B, atoms stacked along MN (1024 B).
 //  !KMAJOR: global rows are the k index (contiguous MN);         smem block(j, i) = k-atom j (8 k-rows x 128 B) of MN-atom i
 //           (32 MN elements), at ((j * ROWS/32) + i) * 1024.
+#define TC_THREADS 256   // 8 warps: two warps per TMEM lane quarter, so staging and the epilogue have latency-hiding partners
+
+// tanh with fp32-grade accuracy (|rel err| < ~5e-7) in ~10 instructions: odd polynomial near 0, 1 - 2/(e^{2|x|}+1) elsewhere.
+// (libdevice tanhf costs ~40 dependent instructions per element, which made the 4-warp epilogue the bottleneck.)
+__device__ __forceinline__ float tanh_fast(float x) {
+    const float ax = fabsf(x);
+    if (ax < 0.25f) {
+        const float x2 = x * x;
+        float p = 62.0f / 2835.0f;
+        p = fmaf(p, x2, -17.0f / 315.0f);
+        p = fmaf(p, x2, 2.0f / 15.0f);
+        p = fmaf(p, x2, -1.0f / 3.0f);
+        return fmaf(x * x2, p, x);
+    }
+    const float e = __expf(2.0f * ax);
+    return copysignf(1.0f - __fdividef(2.0f, e + 1.0f), x);
+}
+
 template <int ROWS, bool KMAJOR>
 __device__ __forceinline__ void stage_operand(uint8_t* s_hi, uint8_t* s_lo, const float* __restrict__ g, int ld,
                                               const int32_t* __restrict__ rows, int mn0, int mn_total, int k0, int k_end) {
     const int t = threadIdx.x;
-    constexpr int PASSES = ROWS * 8 / 128;  // float4 per thread
+    constexpr int PASSES = ROWS * 8 / TC_THREADS;  // float4 per thread
     float4 v[PASSES];
     if (KMAJOR) {
 #pragma unroll
         for (int i = 0; i < PASSES; ++i) {
-            const int r = (t >> 3) + 16 * i, c = t & 7;
+            const int r = (t >> 3) + (TC_THREADS / 8) * i, c = t & 7;
             const int mn = mn0 + r;
             v[i] = make_float4(0.f, 0.f, 0.f, 0.f);
             if (mn < mn_total && k0 + c * 4 < k_end) {
@@ -97,7 +116,7 @@ __device__ __forceinline__ void stage_operand(uint8_t* s_hi, uint8_t* s_lo, cons
         }
 #pragma unroll
         for (int i = 0; i < PASSES; ++i) {
-            const int r = (t >> 3) + 16 * i, c = t & 7;
+            const int r = (t >> 3) + (TC_THREADS / 8) * i, c = t & 7;
             const uint32_t off = (uint32_t)(r >> 3) * 1024u + (uint32_t)(r & 7) * 128u + (uint32_t)((c ^ (r & 7)) << 4);
             uint4 hi, lo;
             split4(v[i], hi, lo);
@@ -107,7 +126,7 @@ __device__ __forceinline__ void stage_operand(uint8_t* s_hi, uint8_t* s_lo, cons
     } else {
         // 32 k-rows x ROWS contiguous MN: thread handles k = (t / (ROWS/4)) + step, MN chunk = t % (ROWS/4)
         constexpr int CH = ROWS / 4;            // float4 per k-row
-        constexpr int KSTEP = 128 / CH;         // k-rows covered per pass (ROWS=128: 4, ROWS=256: 2, ROWS=64: 8)
+        constexpr int KSTEP = TC_THREADS / CH;  // k-rows covered per pass
 #pragma unroll
         for (int i = 0; i < PASSES; ++i) {
             const int kk = (t / CH) + KSTEP * i, c = t % CH;
@@ -135,7 +154,7 @@ __device__ __forceinline__ void stage_operand(uint8_t* s_hi, uint8_t* s_lo, cons
 }
 
 template <int BN, bool A_KMAJOR, bool B_KMAJOR>
-__global__ void __launch_bounds__(128, 1) gemm_tf32x3_kernel(const TcGemmParams p) {
+__global__ void __launch_bounds__(TC_THREADS, 1) gemm_tf32x3_kernel(const TcGemmParams p) {
     constexpr int BM = 128;
     constexpr uint32_t A_BYTES = BM * 128, B_BYTES = BN * 128;           // one image (hi or lo) of one 32-k slab
     constexpr uint32_t STAGE_BYTES = 2 * A_BYTES + 2 * B_BYTES;
@@ -203,12 +222,13 @@ __global__ void __launch_bounds__(128, 1) gemm_tf32x3_kernel(const TcGemmParams 
     // ---- epilogue: TMEM -> registers -> global ----
     if (nslab > 0) mbar_wait(&bar_acc, 0);
     asm volatile("tcgen05.fence::after_thread_sync;" ::: "memory");
-    const int m = m0 + t;   // thread t owns accumulator row (TMEM lane) t
+    const int lane_q = warp & 3, col_half = warp >> 2;    // a warp may only touch TMEM lanes 32*(warp%4) .. +31
+    const int m = m0 + lane_q * 32 + (t & 31);            // accumulator row = TMEM lane
     float* Cbase = p.C + (long long)blockIdx.z * p.c_split_stride;
 #pragma unroll 1
-    for (int c0 = 0; c0 < BN; c0 += 32) {
+    for (int c0 = col_half * (BN / 2); c0 < (col_half + 1) * (BN / 2); c0 += 32) {
         uint32_t r[32];
-        const uint32_t taddr = tmem_d + ((uint32_t)(warp * 32) << 16) + (uint32_t)c0;
+        const uint32_t taddr = tmem_d + ((uint32_t)(lane_q * 32) << 16) + (uint32_t)c0;
         asm volatile(
             "tcgen05.ld.sync.aligned.32x32b.x32.b32 "
             "{%0, %1, %2, %3, %4, %5, %6, %7, %8, %9, %10, %11, %12, %13, %14, %15, "
@@ -229,7 +249,7 @@ __global__ void __launch_bounds__(128, 1) gemm_tf32x3_kernel(const TcGemmParams 
                 for (int e = 0; e < 4; ++e) {
                     float v = nslab > 0 ? __uint_as_float(r[q * 4 + e]) : 0.f;
                     if (p.bias) v += p.bias[n + e];
-                    if (p.act == GYMRL_ACT_TANH) v = tanhf(v);
+                    if (p.act == GYMRL_ACT_TANH) v = tanh_fast(v);
                     else if (p.act == GYMRL_ACT_RELU) v = fmaxf(v, 0.f);
                     if (p.H) {
                         const float h = p.H[(long long)m * p.ldh + n + e];
@@ -260,7 +280,7 @@ static int launch_tc(const TcGemmParams& p, int splits, cudaStream_t s) {
         configured = true;
     }
     dim3 grid(p.N / BN, ceil_div(p.M, 128), splits);
-    gemm_tf32x3_kernel<BN, AK, BKM><<<grid, 128, SMEM, s>>>(p);
+    gemm_tf32x3_kernel<BN, AK, BKM><<<grid, TC_THREADS, SMEM, s>>>(p);
     gymrl_count_launch();
     return GYMRL_OK;
 }
