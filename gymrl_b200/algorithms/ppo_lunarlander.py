@@ -30,7 +30,7 @@ import numpy as np
 import torch
 import torch.nn as nn
 
-from .. import _ffi, ops
+from .. import _ffi, dist as gdist, ops
 from ..nn import FlatParams, FusedAdam, layer_init
 
 f32, i32, u8, f64 = torch.float32, torch.int32, torch.uint8, torch.float64
@@ -202,19 +202,12 @@ class RolloutBuffer:
         return self.filled * self.N
 
 
-def _dist_info():
-    import torch.distributed as dist
-    if dist.is_available() and dist.is_initialized():
-        return dist.get_rank(), dist.get_world_size()
-    return 0, 1
-
-
 class PPOTrainer:
     def __init__(self, config: Config):
         _ffi.require_cuda()
         self.cfg = cfg = config
         self.device = torch.device("cuda", torch.cuda.current_device())
-        self.rank, self.world = _dist_info()
+        self.rank, self.world = gdist.info()
         N = int(cfg.num_envs)
         T = int(cfg.num_steps) if cfg.num_steps else max(1, int(cfg.update_freq) // N)
         self.N, self.T = N, T
@@ -224,15 +217,10 @@ class PPOTrainer:
         self.reset_each_rollout = (N == 1) if cfg.reset_each_rollout is None else bool(cfg.reset_each_rollout)
         self.seed = int(cfg.seed) if cfg.seed is not None else int(time.time_ns() & 0x7FFFFFFF)
 
-        self.env = ops.VecEnv(cfg.env_name, N, seed=self.seed, first_env_id=self.rank * N)
+        self.env = ops.VecEnv(cfg.env_name, N, seed=self.seed, first_env_id=gdist.shard(N, self.rank)[0])
         state_dim, action_dim = self.env.obs_dim, self.env.n_actions
         self.model = ActorCritic(state_dim, action_dim, cfg.hidden_dim)
-        if self.world > 1:  # identical replicas: rank 0's initialisation everywhere
-            import torch.distributed as dist
-            for p in self.model.parameters():
-                t = p.data.to(self.device)
-                dist.broadcast(t, 0)
-                p.data = t
+        gdist.broadcast_module_(self.model, self.device)   # identical replicas: rank 0's initialisation everywhere
         self.net = self.model.to_engine(self.device)
         self.optimizer = FusedAdam(self.net.fp, lr=cfg.lr, eps=1e-5)
         self.buffer = RolloutBuffer(T, N, state_dim, self.device)
@@ -383,12 +371,7 @@ class PPOTrainer:
         # advantage normalisation, numpy semantics (ddof = 0, ref :236); global over all shards
         self.adv_sums.zero_()
         ops.sum_sumsq(adv, self.adv_sums[:2])
-        count = float(adv.numel())
-        if self.world > 1:
-            import torch.distributed as dist
-            self.adv_sums[2] = count
-            dist.all_reduce(self.adv_sums)
-            count = float(adv.numel() * self.world)
+        count = gdist.global_moments_(self.adv_sums, adv.numel())
         ops.normalize_inplace(adv, self.adv_sums, count, ddof=0, eps=1e-8)
 
         self.optimizer.sync_lr()
@@ -405,12 +388,11 @@ class PPOTrainer:
                     else:
                         self._minibatch_body()
                 else:
-                    import torch.distributed as dist
                     if self._g_mb_bwd is not None:
                         self._replay(self._g_mb_bwd)
                     else:
                         self._fwd_bwd_body()
-                    dist.all_reduce(self.net.fp.grad)  # the one collective of the path (sum; Adam rescales by 1/world)
+                    gdist.allreduce_sum_(self.net.fp.grad)  # the one collective of the path (sum; Adam rescales by 1/world)
                     if self._g_opt is not None:
                         self._replay(self._g_opt)
                     else:

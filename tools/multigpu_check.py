@@ -1,0 +1,74 @@
+"""2-rank NCCL parity check of the sharded PPO path (run under torch.distributed.run, one rank per GPU):
+
+  * each rank rolls out N envs with global ids [rank*N, (rank+1)*N) -> the concatenation equals a single-GPU
+    rollout of 2N envs (trajectories do not depend on the GPU count);
+  * one optimizer step with the gradient sum-all-reduce (+ global advantage normalisation) leaves every rank
+    with the same parameters as the single-GPU step on the concatenated batch.
+
+    python -m torch.distributed.run --nnodes=1 --nproc-per-node 2 --master-addr 127.0.0.1 --master-port 29533 tools/multigpu_check.py
+"""
+import os
+import sys
+from pathlib import Path
+
+import torch
+import torch.distributed as dist
+
+sys.path.insert(0, str(Path(__file__).resolve().parent.parent))
+
+
+def make_trainer(P, n_envs, graph=False):
+    cfg = P.Config()
+    cfg.num_envs, cfg.num_steps, cfg.num_minibatches, cfg.num_epochs, cfg.seed, cfg.use_cuda_graph = n_envs, 16, 1, 1, 11, graph
+    torch.manual_seed(0)
+    return P.PPOTrainer(cfg)
+
+
+def main():
+    rank, world, local = int(os.environ["RANK"]), int(os.environ["WORLD_SIZE"]), int(os.environ["LOCAL_RANK"])
+    torch.cuda.set_device(local)
+    dist.init_process_group("nccl", device_id=torch.device("cuda", local))
+    from gymrl_b200.algorithms import ppo_lunarlander as P
+    N = 256
+    tr = make_trainer(P, N)
+    tr.collect_rollout()
+    tr.update(None)
+    flat = tr.net.fp.flat.clone()
+    # every rank must hold identical parameters after the step
+    ref = flat.clone()
+    dist.broadcast(ref, 0)
+    same = torch.tensor([float(torch.equal(ref, flat))], device="cuda")
+    dist.all_reduce(same, op=dist.ReduceOp.MIN)
+    # gather shards on rank 0
+    obs = [torch.zeros_like(tr.buffer.obs) for _ in range(world)]
+    act = [torch.zeros_like(tr.buffer.action) for _ in range(world)]
+    dist.all_gather(obs, tr.buffer.obs)
+    dist.all_gather(act, tr.buffer.action)
+    ok = True
+    if rank == 0:
+        # single-GPU run of the concatenated problem, outside the process group's view
+        import gymrl_b200.dist as gd
+        real_info = gd.info
+        gd.info = lambda: (0, 1)
+        try:
+            one = make_trainer(P, N * world)
+            one.collect_rollout()
+            one.update(None)
+        finally:
+            gd.info = real_info
+        cat_obs, cat_act = torch.cat(obs, dim=1), torch.cat(act, dim=1)
+        e_obs = bool(torch.equal(cat_obs, one.buffer.obs))
+        e_act = bool(torch.equal(cat_act, one.buffer.action))
+        dpar = (one.net.fp.flat - flat).abs().max().item()
+        scale = one.net.fp.flat.abs().max().item()
+        print(f"ranks identical after step: {bool(same.item())}; shard rollout == single-GPU rollout: obs {e_obs}, actions {e_act}; "
+              f"max |param diff| vs single GPU on the concatenated batch: {dpar:.3e} (param scale {scale:.2f})")
+        ok = bool(same.item()) and e_obs and e_act and dpar < 2e-5
+        print("MULTIGPU_CHECK", "PASS" if ok else "FAIL")
+    dist.barrier()
+    dist.destroy_process_group()
+    sys.exit(0 if ok else 1)
+
+
+if __name__ == "__main__":
+    main()
