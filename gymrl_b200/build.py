@@ -36,6 +36,7 @@ SOURCES = {
     "ppo_loss.cu": [],
     "linear.cu": [],
     "linear_tc.cu": [],
+    "linear_skinny.cu": [],
     "optim.cu": [],
     "replay.cu": [],
     "qlearn.cu": [],

@@ -16,6 +16,15 @@ struct gymrl_env {
     float* ll_f;
     int32_t* ll_i;
     double* ll_d;
+    // LunarLander spares: pre-built next episode per env (same plane layout), its first observation, and the refill queues
+    float* ll_sf;
+    int32_t* ll_si;
+    double* ll_sd;
+    float* spare_obs;        // [N][8]
+    int32_t* spare_ready;    // [N]
+    int32_t* refill_list;    // [3][N]
+    int32_t* refill_count;   // [3] (+ tick at [3])
+    int32_t* tick;           // step counter mod-3 addressing of the refill queues
     // shared bookkeeping, all [N]
     int32_t* elapsed;     // TimeLimit counter
     uint32_t* episode;    // episodes started so far (keys the reset draws)

@@ -24,12 +24,32 @@
 
 void gymrl_count_launch(int n = 1);
 
+// linear_skinny.cu: degenerate shapes (heads with N <= 8/16 outputs, observation layer with K in {3,4,8})
+bool skinny_forward_supported(const float* x, int ldx, int N, int K);
+int skinny_forward(const float* x, int ldx, const int32_t* rows, const float* w, const float* b, float* y, int ldy, int M, int N, int K,
+                   int act, cudaStream_t s);
+bool skinny_backward_input_supported(int N, int K, const float* h, int ldh, const float* dx, int lddx);
+int skinny_backward_input(const float* dy, int lddy, const float* w, const float* h, int ldh, float* dx, int lddx, int M, int N, int K,
+                          int act_in, int accumulate, cudaStream_t s);
+bool skinny_dw_supported(int N);
+int skinny_dw(const float* dy, int lddy, const float* x, int ldx, const int32_t* rows, float* part_w, float* part_b, int M, int N, int K,
+              int chunks, cudaStream_t s);
+bool smallk_forward_supported(int K);
+int smallk_forward(const float* x, int ldx, const int32_t* rows, const float* w, const float* b, float* y, int ldy, int M, int N, int K,
+                   int act, cudaStream_t s);
+bool smallk_dw_supported(int K);
+int smallk_dw(const float* dy, int lddy, const float* x, int ldx, const int32_t* rows, float* part_w, float* part_b, int M, int N, int K,
+              int chunks, cudaStream_t s);
+static int g_skinny = 1;   // GYMRL_SKINNY=0 disables the degenerate-shape kernels (debug / A-B comparison)
+
 // GEMM engine selection: 0 = fp32 FFMA tiles (this file), 1 = tcgen05 3xTF32 (linear_tc.cu) where the shape gate allows.
 static int g_gemm_mode = -1;
 static int gemm_mode() {
     if (g_gemm_mode < 0) {
         const char* e = getenv("GYMRL_GEMM");
         g_gemm_mode = (e && strcmp(e, "ffma") == 0) ? 0 : 1;
+        const char* k = getenv("GYMRL_SKINNY");
+        g_skinny = (k && strcmp(k, "0") == 0) ? 0 : 1;
     }
     return g_gemm_mode;
 }
@@ -302,6 +322,17 @@ extern "C" int gymrl_linear_forward(const float* d_x, int ldx, const int32_t* d_
     p.k_chunk = K; p.c_split_stride = 0;
     p.vecA = aligned16(d_x) && (ldx % 4 == 0);
     p.vecB = aligned16(d_w) && (K % 4 == 0);
+    (void)gemm_mode();
+    if (g_skinny && N <= 8 && skinny_forward_supported(d_x, ldx, N, K)) {
+        skinny_forward(d_x, ldx, d_row_index, d_w, d_b, d_y, ldy, M, N, K, act, as_stream(stream));
+        GYMRL_LAUNCH_CHECK("linear_forward(skinny)");
+        return GYMRL_OK;
+    }
+    if (g_skinny && N >= 32 && smallk_forward_supported(K)) {
+        smallk_forward(d_x, ldx, d_row_index, d_w, d_b, d_y, ldy, M, N, K, act, as_stream(stream));
+        GYMRL_LAUNCH_CHECK("linear_forward(small-K)");
+        return GYMRL_OK;
+    }
     if (gemm_mode() == 1) {
         TcGemmParams t;
         memset(&t, 0, sizeof(t));
@@ -336,6 +367,12 @@ extern "C" int gymrl_linear_backward_input(const float* d_dy, int lddy, const fl
     p.k_chunk = N;
     p.vecA = aligned16(d_dy) && (lddy % 4 == 0);
     p.vecB = aligned16(d_w) && (K % 4 == 0);
+    (void)gemm_mode();
+    if (g_skinny && N <= 16 && skinny_backward_input_supported(N, K, d_h_in, ldh, d_dx, lddx)) {
+        skinny_backward_input(d_dy, lddy, d_w, d_h_in, ldh, d_dx, lddx, M, N, K, act_in, accumulate, as_stream(stream));
+        GYMRL_LAUNCH_CHECK("linear_backward_input(skinny)");
+        return GYMRL_OK;
+    }
     if (gemm_mode() == 1 && !accumulate) {
         TcGemmParams t;
         memset(&t, 0, sizeof(t));
@@ -365,8 +402,7 @@ static int dw_splits(int M, int N, int K) {
 }
 
 extern "C" size_t gymrl_linear_backward_weight_workspace(int M, int N, int K) {
-    int s = dw_splits(M, N, K);
-    if (s < 64 && M >= 256) s = 64;   // the tensor-core path may use up to 64 split-M partial tiles
+    const int s = 64;   // every engine (FFMA split-M, tensor-core split-M, skinny row chunks) uses at most 64 partial slices
     return (size_t)s * ((size_t)N * K + (size_t)N) * sizeof(float);
 }
 
@@ -422,6 +458,25 @@ extern "C" int gymrl_linear_backward_weight(const float* d_dy, int lddy, const f
     p.rowsum = d_db ? ws_db : nullptr;
     p.vecA = aligned16(d_dy) && (lddy % 4 == 0);
     p.vecB = aligned16(d_x) && (ldx % 4 == 0);
+    (void)gemm_mode();
+    if (g_skinny && ((N <= 8 && skinny_dw_supported(N)) || (N >= 32 && smallk_dw_supported(K)))) {
+        int chunks = ceil_div(M, 32);
+        if (chunks > 64) chunks = 64;
+        float* part_w = ws;
+        float* part_b = ws + (size_t)chunks * N * K;
+        if (N <= 8) skinny_dw(d_dy, lddy, d_x, ldx, d_row_index, part_w, d_db ? part_b : nullptr, M, N, K, chunks, s);
+        else smallk_dw(d_dy, lddy, d_x, ldx, d_row_index, part_w, d_db ? part_b : nullptr, M, N, K, chunks, s);
+        GYMRL_LAUNCH_CHECK("linear_backward_weight(skinny)");
+        const long long cnt3 = (long long)N * K;
+        reduce_partials_kernel<<<(unsigned)ceil_div_ll(cnt3, 256), 256, 0, s>>>(part_w, cnt3, chunks, d_dw, accumulate);
+        gymrl_count_launch();
+        if (d_db) {
+            reduce_partials_kernel<<<ceil_div(N, 256), 256, 0, s>>>(part_b, N, chunks, d_db, accumulate);
+            gymrl_count_launch();
+        }
+        GYMRL_LAUNCH_CHECK("reduce_partials(skinny)");
+        return GYMRL_OK;
+    }
     if (gemm_mode() == 1) {
         TcGemmParams t;
         memset(&t, 0, sizeof(t));

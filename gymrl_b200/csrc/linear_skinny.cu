@@ -1,0 +1,267 @@
+// linear_skinny.cu — dense layers whose GEMM degenerates: tiny fan-out (policy/value/Q heads, N <= 16) or tiny fan-in
+// (the observation layer, K <= 16).  A 64x64 tile is >90 % padding for these shapes (they cost ~30 % of the update in
+// the round-1 launch list, profiles/r1_launches_ffma.md), while the work is a bandwidth-bound sweep over the [M, 256]
+// activation: one pass, coalesced, weights in shared memory.
+//   skinny-N forward   y[M][N]  = act(x[M][K] W[N][K]^T + b)        warp per row, lanes split K, shuffle reduce
+//   skinny-N backward  dx[M][K] = (dy[M][N] W[N][K]) * act'(h)       thread per 4 outputs, W in smem
+//   skinny-N dW/db     dW[N][K] = sum_m dy[m][n] x[m][k]             thread per k, row chunks -> partials -> reduce
+//   small-K forward    y[M][N]  = act(x[M][K] W[N][K]^T + b)         thread per output, W in smem (row gather on x)
+//   small-K dW/db      dW[N][K] = sum_m dy[m][n] x[idx[m]][k]        thread per n, row chunks -> partials -> reduce
+// fp32 FMA throughout (these are < 1 % of the flops).
+#include "common.cuh"
+
+void gymrl_count_launch(int n = 1);
+
+#define SK_MAXN 16
+#define SK_MAXK 16
+
+__device__ __forceinline__ float apply_act(float v, int act) {
+    if (act == GYMRL_ACT_TANH) return tanhf(v);
+    if (act == GYMRL_ACT_RELU) return fmaxf(v, 0.f);
+    return v;
+}
+
+// ---- skinny-N forward: one warp per row ------------------------------------------------------------------------
+template <int N>
+__global__ void __launch_bounds__(256) skinny_fwd_kernel(const float* __restrict__ x, int ldx, const int32_t* __restrict__ rows,
+                                                         const float* __restrict__ w, const float* __restrict__ b,
+                                                         float* __restrict__ y, int ldy, int M, int K, int act) {
+    extern __shared__ float sw[];   // [N][K]
+    for (int i = threadIdx.x; i < N * K; i += blockDim.x) sw[i] = w[i];
+    __syncthreads();
+    const int lane = threadIdx.x & 31, warp = threadIdx.x >> 5, wpb = blockDim.x >> 5;
+    for (int m = blockIdx.x * wpb + warp; m < M; m += gridDim.x * wpb) {
+        const float* xr = x + (size_t)(rows ? rows[m] : m) * ldx;
+        float acc[N];
+#pragma unroll
+        for (int n = 0; n < N; ++n) acc[n] = 0.f;
+        for (int k = lane * 4; k < K; k += 128) {   // K % 4 == 0 (checked by the launcher)
+            const float4 v = *reinterpret_cast<const float4*>(xr + k);
+#pragma unroll
+            for (int n = 0; n < N; ++n) {
+                const float4 ww = *reinterpret_cast<const float4*>(&sw[n * K + k]);
+                acc[n] = fmaf(v.x, ww.x, fmaf(v.y, ww.y, fmaf(v.z, ww.z, fmaf(v.w, ww.w, acc[n]))));
+            }
+        }
+#pragma unroll
+        for (int n = 0; n < N; ++n) acc[n] = warp_sum(acc[n]);
+        if (lane == 0) {
+#pragma unroll
+            for (int n = 0; n < N; ++n) y[(size_t)m * ldy + n] = apply_act(acc[n] + (b ? b[n] : 0.f), act);
+        }
+    }
+}
+
+template <int N>
+static void launch_skinny_fwd(const float* x, int ldx, const int32_t* rows, const float* w, const float* b, float* y, int ldy, int M,
+                              int K, int act, cudaStream_t s) {
+    int blocks = ceil_div(M, 8 * 8);   // 8 warps per block, ~8 rows per warp
+    if (blocks > GYMRL_NUM_SMS * 8) blocks = GYMRL_NUM_SMS * 8;
+    skinny_fwd_kernel<N><<<blocks, 256, (size_t)N * K * sizeof(float), s>>>(x, ldx, rows, w, b, y, ldy, M, K, act);
+}
+
+bool skinny_forward_supported(const float* x, int ldx, int N, int K) {
+    return N >= 1 && N <= 8 && K % 4 == 0 && K <= 2048 && (ldx % 4 == 0) && ((reinterpret_cast<uintptr_t>(x) & 15) == 0);
+}
+int skinny_forward(const float* x, int ldx, const int32_t* rows, const float* w, const float* b, float* y, int ldy, int M, int N, int K,
+                   int act, cudaStream_t s) {
+    switch (N) {
+        case 1: launch_skinny_fwd<1>(x, ldx, rows, w, b, y, ldy, M, K, act, s); break;
+        case 2: launch_skinny_fwd<2>(x, ldx, rows, w, b, y, ldy, M, K, act, s); break;
+        case 3: launch_skinny_fwd<3>(x, ldx, rows, w, b, y, ldy, M, K, act, s); break;
+        case 4: launch_skinny_fwd<4>(x, ldx, rows, w, b, y, ldy, M, K, act, s); break;
+        case 5: launch_skinny_fwd<5>(x, ldx, rows, w, b, y, ldy, M, K, act, s); break;
+        case 6: launch_skinny_fwd<6>(x, ldx, rows, w, b, y, ldy, M, K, act, s); break;
+        case 7: launch_skinny_fwd<7>(x, ldx, rows, w, b, y, ldy, M, K, act, s); break;
+        default: launch_skinny_fwd<8>(x, ldx, rows, w, b, y, ldy, M, K, act, s); break;
+    }
+    gymrl_count_launch();
+    return GYMRL_OK;
+}
+
+// ---- skinny-N backward input: dx[m][k..k+3] = (sum_n dy[m][n] W[n][k..]) * act'(h) -------------------------------------
+__global__ void __launch_bounds__(256) skinny_bwd_input_kernel(const float* __restrict__ dy, int lddy, const float* __restrict__ w,
+                                                               const float* __restrict__ h, int ldh, float* __restrict__ dx, int lddx,
+                                                               int M, int N, int K, int act_in, int accumulate) {
+    extern __shared__ float sw[];   // [N][K]
+    for (int i = threadIdx.x; i < N * K; i += blockDim.x) sw[i] = w[i];
+    __syncthreads();
+    const int kq = K >> 2;
+    const long long total = (long long)M * kq;
+    for (long long t = (long long)blockIdx.x * blockDim.x + threadIdx.x; t < total; t += (long long)gridDim.x * blockDim.x) {
+        const int m = (int)(t / kq), k = (int)(t % kq) * 4;
+        float4 acc = make_float4(0.f, 0.f, 0.f, 0.f);
+        for (int n = 0; n < N; ++n) {
+            const float g = dy[(size_t)m * lddy + n];
+            const float4 ww = *reinterpret_cast<const float4*>(&sw[n * K + k]);
+            acc.x = fmaf(g, ww.x, acc.x); acc.y = fmaf(g, ww.y, acc.y); acc.z = fmaf(g, ww.z, acc.z); acc.w = fmaf(g, ww.w, acc.w);
+        }
+        if (h) {
+            const float4 hv = *reinterpret_cast<const float4*>(h + (size_t)m * ldh + k);
+            if (act_in == GYMRL_ACT_TANH) {
+                acc.x *= (1.0f - hv.x * hv.x); acc.y *= (1.0f - hv.y * hv.y); acc.z *= (1.0f - hv.z * hv.z); acc.w *= (1.0f - hv.w * hv.w);
+            } else if (act_in == GYMRL_ACT_RELU) {
+                acc.x = hv.x > 0.f ? acc.x : 0.f; acc.y = hv.y > 0.f ? acc.y : 0.f; acc.z = hv.z > 0.f ? acc.z : 0.f; acc.w = hv.w > 0.f ? acc.w : 0.f;
+            }
+        }
+        float4* dst = reinterpret_cast<float4*>(dx + (size_t)m * lddx + k);
+        if (accumulate) { const float4 o = *dst; acc.x += o.x; acc.y += o.y; acc.z += o.z; acc.w += o.w; }
+        *dst = acc;
+    }
+}
+
+bool skinny_backward_input_supported(int N, int K, const float* h, int ldh, const float* dx, int lddx) {
+    const bool al = ((reinterpret_cast<uintptr_t>(dx) & 15) == 0) && (lddx % 4 == 0) && (!h || (((reinterpret_cast<uintptr_t>(h) & 15) == 0) && ldh % 4 == 0));
+    return N >= 1 && N <= SK_MAXN && K % 4 == 0 && N * K <= 8192 && al;
+}
+int skinny_backward_input(const float* dy, int lddy, const float* w, const float* h, int ldh, float* dx, int lddx, int M, int N, int K,
+                          int act_in, int accumulate, cudaStream_t s) {
+    long long blocks = ceil_div_ll((long long)M * (K >> 2), 256 * 4);
+    if (blocks > GYMRL_NUM_SMS * 8) blocks = GYMRL_NUM_SMS * 8;
+    if (blocks < 1) blocks = 1;
+    skinny_bwd_input_kernel<<<(int)blocks, 256, (size_t)N * K * sizeof(float), s>>>(dy, lddy, w, h, ldh, dx, lddx, M, N, K, act_in, accumulate);
+    gymrl_count_launch();
+    return GYMRL_OK;
+}
+
+// ---- skinny-N dW / db: thread per k, block per row chunk, partial [chunk][N][K] (+ [chunk][N]) --------------------------
+template <int N>
+__global__ void __launch_bounds__(256) skinny_dw_kernel(const float* __restrict__ dy, int lddy, const float* __restrict__ x, int ldx,
+                                                        const int32_t* __restrict__ rows, float* __restrict__ part_w,
+                                                        float* __restrict__ part_b, int M, int K, int rows_per_chunk) {
+    const int m_beg = blockIdx.y * rows_per_chunk, m_end = min(M, m_beg + rows_per_chunk);
+    const int k = blockIdx.x * blockDim.x + threadIdx.x;
+    __shared__ float sdy[32][N];
+    float acc[N], accb[N];
+#pragma unroll
+    for (int n = 0; n < N; ++n) { acc[n] = 0.f; accb[n] = 0.f; }
+    for (int m0 = m_beg; m0 < m_end; m0 += 32) {
+        __syncthreads();
+        for (int i = threadIdx.x; i < 32 * N; i += blockDim.x) {
+            const int mm = m0 + i / N;
+            sdy[i / N][i % N] = mm < m_end ? dy[(size_t)mm * lddy + (i % N)] : 0.f;
+        }
+        __syncthreads();
+        const int lim = min(32, m_end - m0);
+        for (int r = 0; r < lim; ++r) {
+            const float xv = k < K ? x[(size_t)(rows ? rows[m0 + r] : (m0 + r)) * ldx + k] : 0.f;
+#pragma unroll
+            for (int n = 0; n < N; ++n) {
+                acc[n] = fmaf(sdy[r][n], xv, acc[n]);
+                accb[n] += sdy[r][n];
+            }
+        }
+    }
+    if (k < K) {
+#pragma unroll
+        for (int n = 0; n < N; ++n) part_w[((size_t)blockIdx.y * N + n) * K + k] = acc[n];
+    }
+    if (part_b && blockIdx.x == 0 && threadIdx.x == 0) {
+#pragma unroll
+        for (int n = 0; n < N; ++n) part_b[(size_t)blockIdx.y * N + n] = accb[n];
+    }
+}
+
+bool skinny_dw_supported(int N) { return N >= 1 && N <= 8; }
+// workspace floats: chunks * (N*K + N)
+int skinny_dw(const float* dy, int lddy, const float* x, int ldx, const int32_t* rows, float* part_w, float* part_b, int M, int N, int K,
+              int chunks, cudaStream_t s) {
+    const int rpc = ceil_div(M, chunks);
+    dim3 grid(ceil_div(K, 256), chunks);
+#define SK_DW(NN) skinny_dw_kernel<NN><<<grid, 256, 0, s>>>(dy, lddy, x, ldx, rows, part_w, part_b, M, K, rpc)
+    switch (N) {
+        case 1: SK_DW(1); break; case 2: SK_DW(2); break; case 3: SK_DW(3); break; case 4: SK_DW(4); break;
+        case 5: SK_DW(5); break; case 6: SK_DW(6); break; case 7: SK_DW(7); break; default: SK_DW(8); break;
+    }
+#undef SK_DW
+    gymrl_count_launch();
+    return GYMRL_OK;
+}
+
+// ---- small-K forward: thread per output column, rows looped; W[N][K] in smem --------------------------------------------------
+template <int K>
+__global__ void __launch_bounds__(256) smallk_fwd_kernel(const float* __restrict__ x, int ldx, const int32_t* __restrict__ rows,
+                                                         const float* __restrict__ w, const float* __restrict__ b,
+                                                         float* __restrict__ y, int ldy, int M, int N, int act, int rows_per_block) {
+    const int n = blockIdx.x * blockDim.x + threadIdx.x;
+    float wr[K];
+#pragma unroll
+    for (int k = 0; k < K; ++k) wr[k] = n < N ? w[(size_t)n * K + k] : 0.f;
+    const float bias = (b && n < N) ? b[n] : 0.f;
+    const int m_beg = blockIdx.y * rows_per_block, m_end = min(M, m_beg + rows_per_block);
+    __shared__ float sx[16][K];
+    for (int m0 = m_beg; m0 < m_end; m0 += 16) {
+        __syncthreads();
+        for (int i = threadIdx.x; i < 16 * K; i += blockDim.x) {
+            const int mm = m0 + i / K;
+            sx[i / K][i % K] = mm < m_end ? x[(size_t)(rows ? rows[mm] : mm) * ldx + (i % K)] : 0.f;
+        }
+        __syncthreads();
+        const int lim = min(16, m_end - m0);
+        if (n < N)
+            for (int r = 0; r < lim; ++r) {
+                float acc = bias;
+#pragma unroll
+                for (int k = 0; k < K; ++k) acc = fmaf(sx[r][k], wr[k], acc);
+                y[(size_t)(m0 + r) * ldy + n] = apply_act(acc, act);
+            }
+    }
+}
+
+bool smallk_forward_supported(int K) { return K == 3 || K == 4 || K == 8; }
+int smallk_forward(const float* x, int ldx, const int32_t* rows, const float* w, const float* b, float* y, int ldy, int M, int N, int K,
+                   int act, cudaStream_t s) {
+    const int rpb = 64;
+    dim3 grid(ceil_div(N, 256), ceil_div(M, rpb));
+    if (K == 3) smallk_fwd_kernel<3><<<grid, 256, 0, s>>>(x, ldx, rows, w, b, y, ldy, M, N, act, rpb);
+    else if (K == 4) smallk_fwd_kernel<4><<<grid, 256, 0, s>>>(x, ldx, rows, w, b, y, ldy, M, N, act, rpb);
+    else smallk_fwd_kernel<8><<<grid, 256, 0, s>>>(x, ldx, rows, w, b, y, ldy, M, N, act, rpb);
+    gymrl_count_launch();
+    return GYMRL_OK;
+}
+
+// ---- small-K dW / db: thread per output unit n, K (+1) accumulators, row chunks -> partials ------------------------------------
+template <int K>
+__global__ void __launch_bounds__(256) smallk_dw_kernel(const float* __restrict__ dy, int lddy, const float* __restrict__ x, int ldx,
+                                                        const int32_t* __restrict__ rows, float* __restrict__ part_w,
+                                                        float* __restrict__ part_b, int M, int N, int rows_per_chunk) {
+    const int n = blockIdx.x * blockDim.x + threadIdx.x;
+    const int m_beg = blockIdx.y * rows_per_chunk, m_end = min(M, m_beg + rows_per_chunk);
+    __shared__ float sx[32][K];
+    float acc[K], accb = 0.f;
+#pragma unroll
+    for (int k = 0; k < K; ++k) acc[k] = 0.f;
+    for (int m0 = m_beg; m0 < m_end; m0 += 32) {
+        __syncthreads();
+        for (int i = threadIdx.x; i < 32 * K; i += blockDim.x) {
+            const int mm = m0 + i / K;
+            sx[i / K][i % K] = mm < m_end ? x[(size_t)(rows ? rows[mm] : mm) * ldx + (i % K)] : 0.f;
+        }
+        __syncthreads();
+        const int lim = min(32, m_end - m0);
+        if (n < N)
+            for (int r = 0; r < lim; ++r) {
+                const float g = dy[(size_t)(m0 + r) * lddy + n];
+                accb += g;
+#pragma unroll
+                for (int k = 0; k < K; ++k) acc[k] = fmaf(g, sx[r][k], acc[k]);
+            }
+    }
+    if (n < N) {
+#pragma unroll
+        for (int k = 0; k < K; ++k) part_w[((size_t)blockIdx.y * N + n) * K + k] = acc[k];
+        if (part_b) part_b[(size_t)blockIdx.y * N + n] = accb;
+    }
+}
+
+bool smallk_dw_supported(int K) { return K == 3 || K == 4 || K == 8; }
+int smallk_dw(const float* dy, int lddy, const float* x, int ldx, const int32_t* rows, float* part_w, float* part_b, int M, int N, int K,
+              int chunks, cudaStream_t s) {
+    const int rpc = ceil_div(M, chunks);
+    dim3 grid(ceil_div(N, 256), chunks);
+    if (K == 3) smallk_dw_kernel<3><<<grid, 256, 0, s>>>(dy, lddy, x, ldx, rows, part_w, part_b, M, N, rpc);
+    else if (K == 4) smallk_dw_kernel<4><<<grid, 256, 0, s>>>(dy, lddy, x, ldx, rows, part_w, part_b, M, N, rpc);
+    else smallk_dw_kernel<8><<<grid, 256, 0, s>>>(dy, lddy, x, ldx, rows, part_w, part_b, M, N, rpc);
+    gymrl_count_launch();
+    return GYMRL_OK;
+}
