@@ -97,61 +97,80 @@ __device__ __forceinline__ float tanh_fast(float x) {
     return copysignf(1.0f - __fdividef(2.0f, e + 1.0f), x);
 }
 
+// One operand's [ROWS x 32 k] slab pipeline: global -> registers (load) and registers -> hi/lo tf32 images in the
+// canonical UMMA smem layout (store).  Loads are unconditional (out-of-range MN rows are clamped onto valid ones:
+// they only feed output rows/columns the epilogue never writes) and addressed through per-thread pointers set up
+// once, so the compiler keeps every LDG.128 of a slab in flight at once; the kernel holds two register sets so
+// the loads of slab k+1 are issued before slab k is converted.
+//  KMAJOR: global rows are the MN index (128 B = 32 k per row);  smem atom = 8 MN-rows x 128 B, atoms stacked along MN (1024 B).
+//  !KMAJOR: global rows are the k index (contiguous MN);  tf32 MN-major operands must use SWIZZLE_128B_BASE32B
+//           (cutlass sm100_common.inl:92): atoms of 4 k-rows x 128 B, Swizzle<2,5,2> = the 32-byte chunk index is XOR-ed
+//           with the k-row index inside the atom; block (k-atom jk, MN-atom i) at (jk * ROWS/32 + i) * 512 B.
 template <int ROWS, bool KMAJOR>
-__device__ __forceinline__ void stage_operand(uint8_t* s_hi, uint8_t* s_lo, const float* __restrict__ g, int ld,
-                                              const int32_t* __restrict__ rows, int mn0, int mn_total, int k0, int k_end) {
-    const int t = threadIdx.x;
-    constexpr int PASSES = ROWS * 8 / TC_THREADS;  // float4 per thread
-    float4 v[PASSES];
-    if (KMAJOR) {
+struct Stager {
+    static constexpr int PASSES = ROWS * 8 / TC_THREADS;   // float4 per thread per slab
+    static constexpr int CH = ROWS / 4;                    // MN-major: float4 per k-row
+    static constexpr int KSTEP = TC_THREADS / CH;          // MN-major: k-rows covered per pass (multiple of 4)
+    const float* ptr[KMAJOR ? PASSES : 1];
+    const int32_t* rows;
+    long long ld;
+    int k;          // MN-major + gather: next k-row of this thread's first pass
+    uint32_t soff;  // byte offset of pass 0 inside an image; pass i adds a compile-time stride
+
+    __device__ __forceinline__ void init(const float* g, int ld_, const int32_t* rows_, int mn0, int mn_total, int kbeg) {
+        const int t = threadIdx.x;
+        ld = ld_;
+        rows = rows_;
+        if (KMAJOR) {
+            const int r0 = t >> 3, c = t & 7;
 #pragma unroll
-        for (int i = 0; i < PASSES; ++i) {
-            const int r = (t >> 3) + (TC_THREADS / 8) * i, c = t & 7;
-            const int mn = mn0 + r;
-            v[i] = make_float4(0.f, 0.f, 0.f, 0.f);
-            if (mn < mn_total && k0 + c * 4 < k_end) {
-                const long long gr = rows ? (long long)rows[mn] : (long long)mn;
-                v[i] = *reinterpret_cast<const float4*>(g + gr * ld + k0 + c * 4);
+            for (int i = 0; i < PASSES; ++i) {
+                const int mn = min(mn0 + r0 + (TC_THREADS / 8) * i, mn_total - 1);
+                const long long gr = rows_ ? (long long)rows_[mn] : (long long)mn;
+                ptr[i] = g + gr * ld + kbeg + c * 4;
             }
-        }
-#pragma unroll
-        for (int i = 0; i < PASSES; ++i) {
-            const int r = (t >> 3) + (TC_THREADS / 8) * i, c = t & 7;
-            const uint32_t off = (uint32_t)(r >> 3) * 1024u + (uint32_t)(r & 7) * 128u + (uint32_t)((c ^ (r & 7)) << 4);
-            uint4 hi, lo;
-            split4(v[i], hi, lo);
-            *reinterpret_cast<uint4*>(s_hi + off) = hi;
-            *reinterpret_cast<uint4*>(s_lo + off) = lo;
-        }
-    } else {
-        // 32 k-rows x ROWS contiguous MN: thread handles k = (t / (ROWS/4)) + step, MN chunk = t % (ROWS/4)
-        constexpr int CH = ROWS / 4;            // float4 per k-row
-        constexpr int KSTEP = TC_THREADS / CH;  // k-rows covered per pass
-#pragma unroll
-        for (int i = 0; i < PASSES; ++i) {
-            const int kk = (t / CH) + KSTEP * i, c = t % CH;
-            const int k = k0 + kk, mn = mn0 + c * 4;
-            v[i] = make_float4(0.f, 0.f, 0.f, 0.f);
-            if (k < k_end && mn < mn_total) {
-                const long long gr = rows ? (long long)rows[k] : (long long)k;
-                v[i] = *reinterpret_cast<const float4*>(g + gr * ld + mn);
-            }
-        }
-#pragma unroll
-        for (int i = 0; i < PASSES; ++i) {
-            const int kk = (t / CH) + KSTEP * i, c = t % CH;
-            // tf32 MN-major operands must use SWIZZLE_128B_BASE32B (cutlass sm100_common.inl:92): atoms of 4 k-rows x 128 B,
-            // Swizzle<2,5,2> = the 32-byte chunk index is XOR-ed with the k-row index inside the atom
-            const int jk = kk >> 2, kr = kk & 3, ai = c >> 3, c16 = c & 7;   // k-atom, row in atom, MN-atom, 16 B chunk in row
-            const uint32_t off = (uint32_t)(jk * (ROWS / 32) + ai) * 512u + (uint32_t)kr * 128u +
-                                 (uint32_t)((((c16 >> 1) ^ kr) << 5) | ((c16 & 1) << 4));
-            uint4 hi, lo;
-            split4(v[i], hi, lo);
-            *reinterpret_cast<uint4*>(s_hi + off) = hi;
-            *reinterpret_cast<uint4*>(s_lo + off) = lo;
+            soff = (uint32_t)(r0 >> 3) * 1024u + (uint32_t)(r0 & 7) * 128u + (uint32_t)((c ^ (r0 & 7)) << 4);
+        } else {
+            const int kk = t / CH, c = t % CH;
+            const int mn = min(mn0 + c * 4, mn_total - 4);
+            k = kbeg + kk;
+            ptr[0] = g + mn + (rows_ ? 0ll : (long long)k * ld);
+            const int jk = kk >> 2, kr = kk & 3, ai = c >> 3, c16 = c & 7;
+            soff = (uint32_t)(jk * (ROWS / 32) + ai) * 512u + (uint32_t)kr * 128u + (uint32_t)((((c16 >> 1) ^ kr) << 5) | ((c16 & 1) << 4));
         }
     }
-}
+    // issue the loads of the next slab and advance
+    __device__ __forceinline__ void load(float4 (&v)[PASSES]) {
+        if (KMAJOR) {
+#pragma unroll
+            for (int i = 0; i < PASSES; ++i) {
+                v[i] = __ldg(reinterpret_cast<const float4*>(ptr[i]));
+                ptr[i] += 32;
+            }
+        } else if (rows == nullptr) {
+#pragma unroll
+            for (int i = 0; i < PASSES; ++i) v[i] = __ldg(reinterpret_cast<const float4*>(ptr[0] + (long long)(KSTEP * i) * ld));
+            ptr[0] += 32 * ld;
+        } else {
+            int32_t ri[PASSES];
+#pragma unroll
+            for (int i = 0; i < PASSES; ++i) ri[i] = __ldg(rows + k + KSTEP * i);
+#pragma unroll
+            for (int i = 0; i < PASSES; ++i) v[i] = __ldg(reinterpret_cast<const float4*>(ptr[0] + (long long)ri[i] * ld));
+            k += 32;
+        }
+    }
+    __device__ __forceinline__ void store(uint8_t* s_hi, uint8_t* s_lo, const float4 (&v)[PASSES]) const {
+        constexpr uint32_t STRIDE = KMAJOR ? (uint32_t)(TC_THREADS / 64) * 1024u : (uint32_t)(KSTEP / 4) * (ROWS / 32) * 512u;
+#pragma unroll
+        for (int i = 0; i < PASSES; ++i) {
+            uint4 hi, lo;
+            split4(v[i], hi, lo);
+            *reinterpret_cast<uint4*>(s_hi + soff + STRIDE * i) = hi;
+            *reinterpret_cast<uint4*>(s_lo + soff + STRIDE * i) = lo;
+        }
+    }
+};
 
 template <int BN, bool A_KMAJOR, bool B_KMAJOR>
 __global__ void __launch_bounds__(TC_THREADS, 1) gemm_tf32x3_kernel(const TcGemmParams p) {
@@ -189,14 +208,21 @@ __global__ void __launch_bounds__(TC_THREADS, 1) gemm_tf32x3_kernel(const TcGemm
     constexpr uint32_t IDESC = (1u << 4) | (2u << 7) | (2u << 10) | ((A_KMAJOR ? 0u : 1u) << 15) | ((B_KMAJOR ? 0u : 1u) << 16) |
                                ((uint32_t)(BN >> 3) << 17) | ((uint32_t)(BM >> 4) << 24);
 
-    for (int kb = 0; kb < nslab; ++kb) {
+    Stager<BM, A_KMAJOR> sa;
+    Stager<BN, B_KMAJOR> sb;
+    sa.init(p.A, p.lda, p.a_rows, m0, p.M, kbeg);
+    sb.init(p.B, p.ldb, p.b_rows, n0, p.N, kbeg);
+    float4 va0[Stager<BM, A_KMAJOR>::PASSES], vb0[Stager<BN, B_KMAJOR>::PASSES];
+    float4 va1[Stager<BM, A_KMAJOR>::PASSES], vb1[Stager<BN, B_KMAJOR>::PASSES];
+
+    // convert one slab from registers into stage kb & 1 and hand it to the tensor core
+    auto consume = [&](int kb, const float4 (&va)[Stager<BM, A_KMAJOR>::PASSES], const float4 (&vb)[Stager<BN, B_KMAJOR>::PASSES]) {
         const int s = kb & 1, use = kb >> 1;
         if (use >= 1) mbar_wait(&bar_free[s], (uint32_t)((use - 1) & 1));   // MMAs that read this stage have retired
         uint8_t* st = smem + (size_t)s * STAGE_BYTES;
         uint8_t *a_hi = st, *a_lo = st + A_BYTES, *b_hi = st + 2 * A_BYTES, *b_lo = st + 2 * A_BYTES + B_BYTES;
-        const int k0 = kbeg + kb * 32;
-        stage_operand<BM, A_KMAJOR>(a_hi, a_lo, p.A, p.lda, p.a_rows, m0, p.M, k0, kend);
-        stage_operand<BN, B_KMAJOR>(b_hi, b_lo, p.B, p.ldb, p.b_rows, n0, p.N, k0, kend);
+        sa.store(a_hi, a_lo, va);
+        sb.store(b_hi, b_lo, vb);
         asm volatile("fence.proxy.async.shared::cta;" ::: "memory");   // generic-proxy smem writes -> visible to the tensor core
         __syncthreads();
         if (t == 0) {
@@ -205,7 +231,7 @@ __global__ void __launch_bounds__(TC_THREADS, 1) gemm_tf32x3_kernel(const TcGemm
 #pragma unroll
             for (int j = 0; j < 4; ++j) {   // 4 k-steps of 8
                 // K-major: +32 B inside the 128 B swizzle span (LBO = 16 B unused, SBO = 1024 B between 8-row atoms)
-                // MN-major: k-atom j starts at j * (ROWS/32) KiB; LBO = 1024 B between MN atoms, SBO = k-atom stride
+                // MN-major: k-atom pair j; LBO = 512 B between MN atoms, SBO = k-atom stride
                 const uint64_t dah = A_KMAJOR ? make_desc(ah + j * 32, 16, 1024) : make_desc_mn<BM>(ah, j);
                 const uint64_t dal = A_KMAJOR ? make_desc(al + j * 32, 16, 1024) : make_desc_mn<BM>(al, j);
                 const uint64_t dbh = B_KMAJOR ? make_desc(bh + j * 32, 16, 1024) : make_desc_mn<BN>(bh, j);
@@ -216,6 +242,16 @@ __global__ void __launch_bounds__(TC_THREADS, 1) gemm_tf32x3_kernel(const TcGemm
             }
             umma_commit(&bar_free[s]);
             if (kb == nslab - 1) umma_commit(&bar_acc);
+        }
+    };
+
+    if (nslab > 0) { sa.load(va0); sb.load(vb0); }
+    for (int kb = 0; kb < nslab; kb += 2) {
+        if (kb + 1 < nslab) { sa.load(va1); sb.load(vb1); }
+        consume(kb, va0, vb0);
+        if (kb + 1 < nslab) {
+            if (kb + 2 < nslab) { sa.load(va0); sb.load(vb0); }
+            consume(kb + 1, va1, vb1);
         }
     }
 
@@ -240,19 +276,29 @@ __global__ void __launch_bounds__(TC_THREADS, 1) gemm_tf32x3_kernel(const TcGemm
             : "r"(taddr));
         asm volatile("tcgen05.wait::ld.sync.aligned;" ::: "memory");
         if (m < p.M) {
+            // bias / h loads first: they are independent of the accumulator, so their latency overlaps the math
+            float4 b4[8], h4[8];
+#pragma unroll
+            for (int q = 0; q < 8; ++q) {
+                const int n = min(n0 + c0 + q * 4, p.N - 4);
+                b4[q] = p.bias ? __ldg(reinterpret_cast<const float4*>(p.bias + n)) : make_float4(0.f, 0.f, 0.f, 0.f);
+                if (p.H) h4[q] = __ldg(reinterpret_cast<const float4*>(p.H + (long long)m * p.ldh + n));
+            }
 #pragma unroll
             for (int q = 0; q < 8; ++q) {
                 const int n = n0 + c0 + q * 4;
                 if (n >= p.N) continue;
+                const float bq[4] = {b4[q].x, b4[q].y, b4[q].z, b4[q].w};
+                const float hq[4] = {h4[q].x, h4[q].y, h4[q].z, h4[q].w};
                 float o[4];
 #pragma unroll
                 for (int e = 0; e < 4; ++e) {
                     float v = nslab > 0 ? __uint_as_float(r[q * 4 + e]) : 0.f;
-                    if (p.bias) v += p.bias[n + e];
+                    v += bq[e];
                     if (p.act == GYMRL_ACT_TANH) v = tanh_fast(v);
                     else if (p.act == GYMRL_ACT_RELU) v = fmaxf(v, 0.f);
                     if (p.H) {
-                        const float h = p.H[(long long)m * p.ldh + n + e];
+                        const float h = hq[e];
                         if (p.act_in == GYMRL_ACT_TANH) v *= (1.0f - h * h);
                         else if (p.act_in == GYMRL_ACT_RELU) v = h > 0.f ? v : 0.f;
                     }
@@ -292,7 +338,8 @@ bool tc_gemm_supported(const TcGemmParams& p, bool a_kmajor, bool b_kmajor) {
     if (p.N % 64 != 0 || p.K % 32 != 0 || p.k_chunk % 32 != 0) return false;
     if (!al16(p.A) || !al16(p.B) || !al16(p.C) || (p.lda & 3) || (p.ldb & 3) || (p.ldc & 3)) return false;
     if (!a_kmajor && (p.M % 4 != 0)) return false;
-    if (p.H && (!al16(p.H))) return false;
+    if (p.H && (!al16(p.H) || (p.ldh & 3))) return false;
+    if (p.bias && !al16(p.bias)) return false;
     return p.M >= 128;
 }
 

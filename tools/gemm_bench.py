@@ -26,10 +26,20 @@ def timeit(fn, sets, reps=4):
 
 
 def main():
+    import argparse
+    ap = argparse.ArgumentParser()
+    ap.add_argument("--shape", default=None, help="N,K: only this shape")
+    ap.add_argument("--product", default=None, help="only this product: fwd+tanh | fwd | dX*act | dW+db")
+    ap.add_argument("--engine", default=None, help="ffma | tc")
+    ap.add_argument("--M", type=int, default=16384)
+    a = ap.parse_args()
     lib = _ffi.load()
-    M = 16384
+    M = a.M
     sets = 5
     shapes = [(256, 256), (512, 256)]          # (N_out, K_in)
+    if a.shape:
+        shapes = [tuple(int(v) for v in a.shape.split(","))]
+    want = lambda prod: a.product is None or a.product == prod
     print(f"{'product':10s} {'M':>6s} {'N':>4s} {'K':>4s} {'engine':>6s} {'ms':>8s} {'TFLOP/s':>8s}")
     for N, K in shapes:
         xs = [torch.randn(M, K, device="cuda") for _ in range(sets)]
@@ -42,15 +52,21 @@ def main():
         ws = torch.empty(ops.backward_weight_workspace(M, N, K), device="cuda", dtype=torch.uint8)
         fl = 2.0 * M * N * K
         for mode, name in ((0, "ffma"), (1, "tc")):
+            if a.engine and a.engine != name:
+                continue
             lib.gymrl_set_gemm_mode(mode)
-            t = timeit(lambda i: ops.linear_forward(xs[i], w, b, 1, out=ys[i]), sets)
-            print(f"{'fwd+tanh':10s} {M:6d} {N:4d} {K:4d} {name:>6s} {t:8.4f} {fl / t / 1e9:8.1f}")
-            t = timeit(lambda i: ops.linear_forward(xs[i], w, b, 0, out=ys[i]), sets)
-            print(f"{'fwd':10s} {M:6d} {N:4d} {K:4d} {name:>6s} {t:8.4f} {fl / t / 1e9:8.1f}")
-            t = timeit(lambda i: ops.linear_backward_input(dys[i], w, hs[i], 1, out=dxs[i]), sets)
-            print(f"{'dX*act':10s} {M:6d} {N:4d} {K:4d} {name:>6s} {t:8.4f} {fl / t / 1e9:8.1f}")
-            t = timeit(lambda i: ops.linear_backward_weight(dys[i], hs[i], dw, db, workspace=ws), sets)
-            print(f"{'dW+db':10s} {M:6d} {N:4d} {K:4d} {name:>6s} {t:8.4f} {fl / t / 1e9:8.1f}")
+            if want('fwd+tanh'):
+                t = timeit(lambda i: ops.linear_forward(xs[i], w, b, 1, out=ys[i]), sets)
+                print(f"{'fwd+tanh':10s} {M:6d} {N:4d} {K:4d} {name:>6s} {t:8.4f} {fl / t / 1e9:8.1f}")
+            if want('fwd'):
+                t = timeit(lambda i: ops.linear_forward(xs[i], w, b, 0, out=ys[i]), sets)
+                print(f"{'fwd':10s} {M:6d} {N:4d} {K:4d} {name:>6s} {t:8.4f} {fl / t / 1e9:8.1f}")
+            if want('dX*act'):
+                t = timeit(lambda i: ops.linear_backward_input(dys[i], w, hs[i], 1, out=dxs[i]), sets)
+                print(f"{'dX*act':10s} {M:6d} {N:4d} {K:4d} {name:>6s} {t:8.4f} {fl / t / 1e9:8.1f}")
+            if want('dW+db'):
+                t = timeit(lambda i: ops.linear_backward_weight(dys[i], hs[i], dw, db, workspace=ws), sets)
+                print(f"{'dW+db':10s} {M:6d} {N:4d} {K:4d} {name:>6s} {t:8.4f} {fl / t / 1e9:8.1f}")
     lib.gymrl_set_gemm_mode(1)
 
 
