@@ -62,6 +62,7 @@ SIGNATURES = {
     "gymrl_linear_backward_input": (c_int, [_P, c_int, _P, _P, c_int, _P, c_int, c_int, c_int, c_int, c_int, c_int, _P]),
     "gymrl_linear_backward_weight_workspace": (c_size_t, [c_int, c_int, c_int]),
     "gymrl_linear_backward_weight": (c_int, [_P, c_int, _P, c_int, _P, _P, _P, c_int, c_int, c_int, c_int, _P, c_size_t, _P]),
+    "gymrl_linear_backward": (c_int, [_P, c_int, _P, c_int, _P, _P, _P, _P, _P, c_int, c_int, c_int, c_int, c_int, c_int, _P, c_size_t, _P]),
     "gymrl_grad_sumsq": (c_int, [_P, c_ll, _P, _P]),
     "gymrl_adam_step": (c_int, [_P, _P, _P, _P, c_ll, _P, c_float, c_float, c_float, _P, _P, c_float, c_float, c_float, _P]),
     "gymrl_polyak": (c_int, [_P, _P, c_ll, c_float, _P]),

@@ -152,16 +152,11 @@ class ActorCriticEngine:
         """Given acts.dlv[:M] = dL/d(logits, value), fill the flat gradient buffer."""
         T, H, A, ws = _ffi.ACT_TANH, self.H, self.A, self.workspace
         dl, dv = acts.dlv[:, :A], acts.dlv[:, A:A + 1]
-        ops.linear_backward_weight(dl, acts.ac[:, :H], self.gWa2, self.gba2, workspace=ws, M=M)
-        ops.linear_backward_weight(dv, acts.ac[:, H:], self.gWc2, self.gbc2, workspace=ws, M=M)
-        ops.linear_backward_input(dl[:M], self.Wa2, acts.ac[:, :H], T, out=acts.dac[:, :H])
-        ops.linear_backward_input(dv[:M], self.Wc2, acts.ac[:, H:], T, out=acts.dac[:, H:])
-        ops.linear_backward_weight(acts.dac, acts.h2, self.gWac, self.gbac, workspace=ws, M=M)
-        ops.linear_backward_input(acts.dac[:M], self.Wac, acts.h2, T, out=acts.dh2)
-        ops.linear_backward_weight(acts.dh2, acts.h1, self.gW2, self.gb2, workspace=ws, M=M)
-        ops.linear_backward_input(acts.dh2[:M], self.W2, acts.h1, T, out=acts.dh1)
-        ops.linear_backward_weight(acts.dh1, x, self.gW1, self.gb1, row_index=row_index, workspace=ws, M=M)
-
+        ops.linear_backward(dl, acts.ac[:, :H], self.Wa2, self.gWa2, self.gba2, dx=acts.dac[:, :H], act_in=T, workspace=ws, M=M)
+        ops.linear_backward(dv, acts.ac[:, H:], self.Wc2, self.gWc2, self.gbc2, dx=acts.dac[:, H:], act_in=T, workspace=ws, M=M)
+        ops.linear_backward(acts.dac, acts.h2, self.Wac, self.gWac, self.gbac, dx=acts.dh2, act_in=T, workspace=ws, M=M)
+        ops.linear_backward(acts.dh2, acts.h1, self.W2, self.gW2, self.gb2, dx=acts.dh1, act_in=T, workspace=ws, M=M)
+        ops.linear_backward(acts.dh1, x, self.W1, self.gW1, self.gb1, row_index=row_index, workspace=ws, M=M)
 
 class RolloutBuffer:
     """Device-resident [T][N] SoA rollout store (ref RolloutBuffer :120-154 keeps Python lists).

@@ -38,6 +38,12 @@ bool smallk_forward_supported(int K);
 int smallk_forward(const float* x, int ldx, const int32_t* rows, const float* w, const float* b, float* y, int ldy, int M, int N, int K,
                    int act, cudaStream_t s);
 bool smallk_dw_supported(int K);
+bool skinny_bwd_fused_supported(const float* dy, const float* x, int ldx, const float* dx, int lddx, int N, int K);
+int skinny_bwd_fused_chunks(int M);
+int skinny_bwd_fused(const float* dy, int lddy, const float* x, int ldx, const float* w, float* part, float* dx, int lddx, int M, int N,
+                     int K, int act_in, int acc_dx, int chunks, cudaStream_t s);
+void reduce_pair(const float* part_w, long long stride_w, const float* part_b, long long stride_b, int splits, long long cnt_w, int cnt_b,
+                 float* out_w, float* out_b, int accumulate, cudaStream_t s);
 int smallk_dw(const float* dy, int lddy, const float* x, int ldx, const int32_t* rows, float* part_w, float* part_b, int M, int N, int K,
               int chunks, cudaStream_t s);
 static int g_skinny = 1;   // GYMRL_SKINNY=0 disables the degenerate-shape kernels (debug / A-B comparison)
@@ -402,7 +408,9 @@ static int dw_splits(int M, int N, int K) {
 }
 
 extern "C" size_t gymrl_linear_backward_weight_workspace(int M, int N, int K) {
-    const int s = 64;   // every engine (FFMA split-M, tensor-core split-M, skinny row chunks) uses at most 64 partial slices
+    // FFMA / tensor-core split-M use at most 64 partial slices; the bandwidth-bound skinny sweeps (tiny fan-out or
+    // fan-in) cut the rows into up to 512 chunks so that every SM streams
+    const int s = (N <= 8 || K <= 8) ? 512 : 64;
     return (size_t)s * ((size_t)N * K + (size_t)N) * sizeof(float);
 }
 
@@ -461,20 +469,14 @@ extern "C" int gymrl_linear_backward_weight(const float* d_dy, int lddy, const f
     (void)gemm_mode();
     if (g_skinny && ((N <= 8 && skinny_dw_supported(N)) || (N >= 32 && smallk_dw_supported(K)))) {
         int chunks = ceil_div(M, 32);
-        if (chunks > 64) chunks = 64;
+        if (chunks > 512) chunks = 512;
         float* part_w = ws;
         float* part_b = ws + (size_t)chunks * N * K;
         if (N <= 8) skinny_dw(d_dy, lddy, d_x, ldx, d_row_index, part_w, d_db ? part_b : nullptr, M, N, K, chunks, s);
         else smallk_dw(d_dy, lddy, d_x, ldx, d_row_index, part_w, d_db ? part_b : nullptr, M, N, K, chunks, s);
         GYMRL_LAUNCH_CHECK("linear_backward_weight(skinny)");
-        const long long cnt3 = (long long)N * K;
-        reduce_partials_kernel<<<(unsigned)ceil_div_ll(cnt3, 256), 256, 0, s>>>(part_w, cnt3, chunks, d_dw, accumulate);
-        gymrl_count_launch();
-        if (d_db) {
-            reduce_partials_kernel<<<ceil_div(N, 256), 256, 0, s>>>(part_b, N, chunks, d_db, accumulate);
-            gymrl_count_launch();
-        }
-        GYMRL_LAUNCH_CHECK("reduce_partials(skinny)");
+        reduce_pair(part_w, (long long)N * K, part_b, N, chunks, (long long)N * K, N, d_dw, d_db, accumulate, s);
+        GYMRL_LAUNCH_CHECK("reduce_pair(skinny)");
         return GYMRL_OK;
     }
     if (gemm_mode() == 1) {
@@ -489,21 +491,14 @@ extern "C" int gymrl_linear_backward_weight(const float* d_dy, int lddy, const f
         if (tsplits < 1) tsplits = 1;
         int tchunk = ceil_div(ceil_div(M, tsplits), 32) * 32;
         t.k_chunk = tchunk; t.c_split_stride = (long long)N * K;
+        float* ws_db2 = ws + (size_t)tsplits * N * K;   // behind the dW partial tiles
+        t.colsum = d_db ? ws_db2 : nullptr;
         if ((M % 32 == 0) && tc_gemm_supported(t, false, false)) {
             int rc = tc_gemm_launch(t, false, false, tsplits, s);
             if (rc != GYMRL_OK) return rc;
             GYMRL_LAUNCH_CHECK("linear_backward_weight(tc)");
-            const long long cnt2 = (long long)N * K;
-            reduce_partials_kernel<<<(unsigned)ceil_div_ll(cnt2, 256), 256, 0, s>>>(ws, cnt2, tsplits, d_dw, accumulate);
-            gymrl_count_launch();
-            if (d_db) {
-                const int chunks = 64, rpc = ceil_div(M, chunks);
-                float* ws_db2 = ws + (size_t)tsplits * N * K;   // behind the dW partial tiles (workspace is sized for 64 splits)
-                colsum_partial_kernel<<<dim3(ceil_div(N, 32), chunks), 256, 0, s>>>(d_dy, lddy, M, N, rpc, ws_db2);
-                reduce_partials_kernel<<<ceil_div(N, 256), 256, 0, s>>>(ws_db2, N, chunks, d_db, accumulate);
-                gymrl_count_launch(2);
-            }
-            GYMRL_LAUNCH_CHECK("reduce_partials(tc)");
+            reduce_pair(ws, (long long)N * K, ws_db2, N, tsplits, (long long)N * K, N, d_dw, d_db, accumulate, s);
+            GYMRL_LAUNCH_CHECK("reduce_pair(tc)");
             return GYMRL_OK;
         }
     }
@@ -514,12 +509,36 @@ extern "C" int gymrl_linear_backward_weight(const float* d_dy, int lddy, const f
     }
     GYMRL_LAUNCH_CHECK("linear_backward_weight");
     const long long cnt = (long long)N * K;
-    reduce_partials_kernel<<<(unsigned)ceil_div_ll(cnt, 256), 256, 0, s>>>(ws, cnt, splits, d_dw, accumulate);
-    gymrl_count_launch();
-    if (d_db) {
-        reduce_partials_kernel<<<ceil_div(N, 256), 256, 0, s>>>(ws_db, N, splits, d_db, accumulate);
-        gymrl_count_launch();
-    }
-    GYMRL_LAUNCH_CHECK("reduce_partials");
+    reduce_pair(ws, cnt, ws_db, N, splits, cnt, N, d_dw, d_db, accumulate, s);
+    GYMRL_LAUNCH_CHECK("reduce_pair");
     return GYMRL_OK;
+}
+
+// Whole backward of one dense layer: dW, db and (optionally) dX = (dY W) * act'(x), x being the previous layer's
+// activation output.  Skinny heads take the fused single-sweep kernel; every other shape is the two calls above.
+extern "C" int gymrl_linear_backward(const float* d_dy, int lddy, const float* d_x, int ldx, const int32_t* d_row_index,
+                                     const float* d_w, float* d_dw, float* d_db, float* d_dx, int lddx, int M, int N, int K,
+                                     int act_in, int accumulate, void* d_workspace, size_t workspace_bytes, void* stream) {
+    GYMRL_REQUIRE(d_dy && d_x && d_w && d_dw && d_workspace, "NULL pointer");
+    GYMRL_REQUIRE(M > 0 && N > 0 && K > 0 && lddy >= N && ldx >= K, "bad shape");
+    GYMRL_REQUIRE(!(d_dx && d_row_index), "dX of a row-gathered input is not defined (scatter): pass d_dx = NULL");
+    GYMRL_REQUIRE(!d_dx || lddx >= K, "lddx < K");
+    GYMRL_REQUIRE(workspace_bytes >= gymrl_linear_backward_weight_workspace(M, N, K), "workspace too small");
+    (void)gemm_mode();
+    if (g_skinny && !d_row_index && skinny_bwd_fused_supported(d_dy, d_x, ldx, d_dx, lddx, N, K)) {
+        cudaStream_t s = as_stream(stream);
+        const int chunks = skinny_bwd_fused_chunks(M);
+        float* part = (float*)d_workspace;
+        int rc = skinny_bwd_fused(d_dy, lddy, d_x, ldx, d_w, part, d_dx, lddx, M, N, K, act_in, 0, chunks, s);
+        if (rc != GYMRL_OK) return rc;
+        GYMRL_LAUNCH_CHECK("linear_backward(skinny fused)");
+        const long long stride = (long long)N * K + N;
+        reduce_pair(part, stride, part + (size_t)N * K, stride, chunks, (long long)N * K, N, d_dw, d_db, accumulate, s);
+        GYMRL_LAUNCH_CHECK("reduce_pair(skinny fused)");
+        return GYMRL_OK;
+    }
+    int rc = gymrl_linear_backward_weight(d_dy, lddy, d_x, ldx, d_row_index, d_dw, d_db, M, N, K, accumulate, d_workspace, workspace_bytes,
+                                          stream);
+    if (rc != GYMRL_OK || !d_dx) return rc;
+    return gymrl_linear_backward_input(d_dy, lddy, d_w, d_x, ldx, d_dx, lddx, M, N, K, act_in, 0, stream);
 }

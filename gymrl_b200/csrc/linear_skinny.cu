@@ -143,12 +143,28 @@ __global__ void __launch_bounds__(256) skinny_dw_kernel(const float* __restrict_
         }
         __syncthreads();
         const int lim = min(32, m_end - m0);
-        for (int r = 0; r < lim; ++r) {
-            const float xv = k < K ? x[(size_t)(rows ? rows[m0 + r] : (m0 + r)) * ldx + k] : 0.f;
+        if (lim == 32 && k < K) {
+            // full group: issue the 32 row loads back to back (the sweep over x is bandwidth-bound; one load in
+            // flight per thread left it latency-bound at 64 blocks)
+            float xv[32];
 #pragma unroll
-            for (int n = 0; n < N; ++n) {
-                acc[n] = fmaf(sdy[r][n], xv, acc[n]);
-                accb[n] += sdy[r][n];
+            for (int r = 0; r < 32; ++r) xv[r] = x[(size_t)(rows ? rows[m0 + r] : (m0 + r)) * ldx + k];
+#pragma unroll
+            for (int r = 0; r < 32; ++r) {
+#pragma unroll
+                for (int n = 0; n < N; ++n) {
+                    acc[n] = fmaf(sdy[r][n], xv[r], acc[n]);
+                    accb[n] += sdy[r][n];
+                }
+            }
+        } else {
+            for (int r = 0; r < lim; ++r) {
+                const float xv = k < K ? x[(size_t)(rows ? rows[m0 + r] : (m0 + r)) * ldx + k] : 0.f;
+#pragma unroll
+                for (int n = 0; n < N; ++n) {
+                    acc[n] = fmaf(sdy[r][n], xv, acc[n]);
+                    accb[n] += sdy[r][n];
+                }
             }
         }
     }
@@ -239,13 +255,26 @@ __global__ void __launch_bounds__(256) smallk_dw_kernel(const float* __restrict_
         }
         __syncthreads();
         const int lim = min(32, m_end - m0);
-        if (n < N)
-            for (int r = 0; r < lim; ++r) {
-                const float g = dy[(size_t)(m0 + r) * lddy + n];
-                accb += g;
+        if (n < N) {
+            if (lim == 32) {
+                float g[32];
 #pragma unroll
-                for (int k = 0; k < K; ++k) acc[k] = fmaf(g, sx[r][k], acc[k]);
+                for (int r = 0; r < 32; ++r) g[r] = dy[(size_t)(m0 + r) * lddy + n];
+#pragma unroll
+                for (int r = 0; r < 32; ++r) {
+                    accb += g[r];
+#pragma unroll
+                    for (int k = 0; k < K; ++k) acc[k] = fmaf(g[r], sx[r][k], acc[k]);
+                }
+            } else {
+                for (int r = 0; r < lim; ++r) {
+                    const float g = dy[(size_t)(m0 + r) * lddy + n];
+                    accb += g;
+#pragma unroll
+                    for (int k = 0; k < K; ++k) acc[k] = fmaf(g, sx[r][k], acc[k]);
+                }
             }
+        }
     }
     if (n < N) {
 #pragma unroll
@@ -264,4 +293,141 @@ int smallk_dw(const float* dy, int lddy, const float* x, int ldx, const int32_t*
     else smallk_dw_kernel<8><<<grid, 256, 0, s>>>(dy, lddy, x, ldx, rows, part_w, part_b, M, N, rpc);
     gymrl_count_launch();
     return GYMRL_OK;
+}
+
+// ---- skinny-N fused backward: one sweep over x[M][K] yields dW, db partials AND dx = (dy W) * act'(x) ---------------------------
+// The heads' input x is the previous layer's activation output, so it is both the dW operand and the h of act'(h).
+// Warp per row (8 rows in flight per block), lane owns KC float4 column groups (K = 128 KC); W and the dW accumulators
+// live in registers.  Block partials [chunk][N*K + N] are folded by reduce_pair_kernel (deterministic order).
+template <int N, int KC>
+__global__ void __launch_bounds__(256) skinny_bwd_fused_kernel(const float* __restrict__ dy, int lddy, const float* __restrict__ x, int ldx,
+                                                               const float* __restrict__ w, float* __restrict__ part, float* __restrict__ dx,
+                                                               int lddx, int M, int act_in, int accumulate_dx, int rows_per_chunk) {
+    constexpr int K = 128 * KC;
+    extern __shared__ float red[];   // [8 warps][N*K + N]
+    const int lane = threadIdx.x & 31, warp = threadIdx.x >> 5;
+    const int m_beg = blockIdx.x * rows_per_chunk, m_end = min(M, m_beg + rows_per_chunk);
+    float4 wr[N][KC], acc[N][KC];
+    float accb[N];
+#pragma unroll
+    for (int n = 0; n < N; ++n) {
+        accb[n] = 0.f;
+#pragma unroll
+        for (int j = 0; j < KC; ++j) {
+            wr[n][j] = *reinterpret_cast<const float4*>(w + (size_t)n * K + j * 128 + lane * 4);
+            acc[n][j] = make_float4(0.f, 0.f, 0.f, 0.f);
+        }
+    }
+    for (int m = m_beg + warp; m < m_end; m += 8) {
+        float g[N];
+#pragma unroll
+        for (int n = 0; n < N; ++n) g[n] = dy[(size_t)m * lddy + n];
+        float4 xv[KC];
+#pragma unroll
+        for (int j = 0; j < KC; ++j) xv[j] = *reinterpret_cast<const float4*>(x + (size_t)m * ldx + j * 128 + lane * 4);
+#pragma unroll
+        for (int n = 0; n < N; ++n) accb[n] += g[n];
+#pragma unroll
+        for (int j = 0; j < KC; ++j) {
+            float4 d = make_float4(0.f, 0.f, 0.f, 0.f);
+#pragma unroll
+            for (int n = 0; n < N; ++n) {
+                acc[n][j].x = fmaf(g[n], xv[j].x, acc[n][j].x); acc[n][j].y = fmaf(g[n], xv[j].y, acc[n][j].y);
+                acc[n][j].z = fmaf(g[n], xv[j].z, acc[n][j].z); acc[n][j].w = fmaf(g[n], xv[j].w, acc[n][j].w);
+                d.x = fmaf(g[n], wr[n][j].x, d.x); d.y = fmaf(g[n], wr[n][j].y, d.y);
+                d.z = fmaf(g[n], wr[n][j].z, d.z); d.w = fmaf(g[n], wr[n][j].w, d.w);
+            }
+            if (dx) {
+                if (act_in == GYMRL_ACT_TANH) {
+                    d.x *= (1.0f - xv[j].x * xv[j].x); d.y *= (1.0f - xv[j].y * xv[j].y);
+                    d.z *= (1.0f - xv[j].z * xv[j].z); d.w *= (1.0f - xv[j].w * xv[j].w);
+                } else if (act_in == GYMRL_ACT_RELU) {
+                    d.x = xv[j].x > 0.f ? d.x : 0.f; d.y = xv[j].y > 0.f ? d.y : 0.f;
+                    d.z = xv[j].z > 0.f ? d.z : 0.f; d.w = xv[j].w > 0.f ? d.w : 0.f;
+                }
+                float4* dst = reinterpret_cast<float4*>(dx + (size_t)m * lddx + j * 128 + lane * 4);
+                if (accumulate_dx) { const float4 o = *dst; d.x += o.x; d.y += o.y; d.z += o.z; d.w += o.w; }
+                *dst = d;
+            }
+        }
+    }
+    // fold the 8 warps (fixed order) -> part[chunk][N*K + N]
+    constexpr int STRIDE = N * K + N;
+    constexpr int SSTRIDE = (STRIDE + 3) & ~3;   // keeps every warp's float4 stores 16 B-aligned
+    float* mine = red + (size_t)warp * SSTRIDE;
+#pragma unroll
+    for (int n = 0; n < N; ++n) {
+#pragma unroll
+        for (int j = 0; j < KC; ++j) *reinterpret_cast<float4*>(mine + n * K + j * 128 + lane * 4) = acc[n][j];
+        if (lane == 0) mine[N * K + n] = accb[n];
+    }
+    __syncthreads();
+    for (int i = threadIdx.x; i < STRIDE; i += 256) {
+        float s = 0.f;
+#pragma unroll
+        for (int wv = 0; wv < 8; ++wv) s += red[(size_t)wv * SSTRIDE + i];
+        part[(size_t)blockIdx.x * STRIDE + i] = s;
+    }
+}
+
+// out_w[i] (i < cnt_w) and out_b[i - cnt_w] from partial rows of (cnt_w + cnt_b) floats
+__global__ void reduce_pair_kernel(const float* __restrict__ part_w, long long stride_w, const float* __restrict__ part_b, long long stride_b,
+                                   int splits, long long cnt_w, int cnt_b, float* __restrict__ out_w, float* __restrict__ out_b,
+                                   int accumulate) {
+    const long long i = (long long)blockIdx.x * blockDim.x + threadIdx.x;
+    if (i < cnt_w) {
+        float s = 0.f;
+        for (int k = 0; k < splits; ++k) s += part_w[(long long)k * stride_w + i];
+        out_w[i] = accumulate ? out_w[i] + s : s;
+    } else if (i < cnt_w + cnt_b && out_b) {
+        const long long j = i - cnt_w;
+        float s = 0.f;
+        for (int k = 0; k < splits; ++k) s += part_b[(long long)k * stride_b + j];
+        out_b[j] = accumulate ? out_b[j] + s : s;
+    }
+}
+
+void reduce_pair(const float* part_w, long long stride_w, const float* part_b, long long stride_b, int splits, long long cnt_w, int cnt_b,
+                 float* out_w, float* out_b, int accumulate, cudaStream_t s) {
+    const long long total = cnt_w + (out_b ? cnt_b : 0);
+    reduce_pair_kernel<<<(unsigned)ceil_div_ll(total, 256), 256, 0, s>>>(part_w, stride_w, part_b, stride_b, splits, cnt_w, cnt_b, out_w,
+                                                                          out_b, accumulate);
+    gymrl_count_launch();
+}
+
+bool skinny_bwd_fused_supported(const float* dy, const float* x, int ldx, const float* dx, int lddx, int N, int K) {
+    const bool shape = N >= 1 && N <= 8 && (K == 128 || K == 256 || K == 512) && N * (K / 128) <= 16;
+    const bool al = ((reinterpret_cast<uintptr_t>(x) & 15) == 0) && (ldx % 4 == 0) &&
+                    (!dx || (((reinterpret_cast<uintptr_t>(dx) & 15) == 0) && (lddx % 4 == 0)));
+    return shape && al;
+}
+int skinny_bwd_fused_chunks(int M) { return ceil_div(M, 64) < 512 ? ceil_div(M, 64) : 512; }
+
+template <int N, int KC>
+static int launch_fused(const float* dy, int lddy, const float* x, int ldx, const float* w, float* part, float* dx, int lddx, int M,
+                        int act_in, int acc_dx, int chunks, cudaStream_t s) {
+    constexpr size_t SMEM = (size_t)8 * ((N * 128 * KC + N + 3) & ~3) * sizeof(float);
+    static bool configured = false;
+    if (!configured) {
+        if (SMEM > 48 * 1024) {
+            cudaError_t e = cudaFuncSetAttribute(skinny_bwd_fused_kernel<N, KC>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)SMEM);
+            if (e != cudaSuccess) GYMRL_FAIL(GYMRL_ECUDA, "cudaFuncSetAttribute(smem=%zu) failed: %s", SMEM, cudaGetErrorString(e));
+        }
+        configured = true;
+    }
+    skinny_bwd_fused_kernel<N, KC><<<chunks, 256, SMEM, s>>>(dy, lddy, x, ldx, w, part, dx, lddx, M, act_in, acc_dx, ceil_div(M, chunks));
+    gymrl_count_launch();
+    return GYMRL_OK;
+}
+
+// part: chunks * (N*K + N) floats
+int skinny_bwd_fused(const float* dy, int lddy, const float* x, int ldx, const float* w, float* part, float* dx, int lddx, int M, int N,
+                     int K, int act_in, int acc_dx, int chunks, cudaStream_t s) {
+    const int KC = K / 128;
+#define SKF(NN, KK) if (N == NN && KC == KK) return launch_fused<NN, KK>(dy, lddy, x, ldx, w, part, dx, lddx, M, act_in, acc_dx, chunks, s)
+    SKF(1, 1); SKF(2, 1); SKF(3, 1); SKF(4, 1); SKF(5, 1); SKF(6, 1); SKF(7, 1); SKF(8, 1);
+    SKF(1, 2); SKF(2, 2); SKF(3, 2); SKF(4, 2); SKF(5, 2); SKF(6, 2); SKF(7, 2); SKF(8, 2);
+    SKF(1, 4); SKF(2, 4); SKF(3, 4); SKF(4, 4);
+#undef SKF
+    GYMRL_FAIL(GYMRL_EINVAL, "skinny_bwd_fused: unsupported N=%d K=%d", N, K);
 }

@@ -215,6 +215,8 @@ __global__ void __launch_bounds__(TC_THREADS, 1) gemm_tf32x3_kernel(const TcGemm
     float4 va0[Stager<BM, A_KMAJOR>::PASSES], vb0[Stager<BN, B_KMAJOR>::PASSES];
     float4 va1[Stager<BM, A_KMAJOR>::PASSES], vb1[Stager<BN, B_KMAJOR>::PASSES];
 
+    const bool do_colsum = !A_KMAJOR && p.colsum != nullptr && blockIdx.x == 0;
+    float4 csum = make_float4(0.f, 0.f, 0.f, 0.f);
     // convert one slab from registers into stage kb & 1 and hand it to the tensor core
     auto consume = [&](int kb, const float4 (&va)[Stager<BM, A_KMAJOR>::PASSES], const float4 (&vb)[Stager<BN, B_KMAJOR>::PASSES]) {
         const int s = kb & 1, use = kb >> 1;
@@ -223,6 +225,12 @@ __global__ void __launch_bounds__(TC_THREADS, 1) gemm_tf32x3_kernel(const TcGemm
         uint8_t *a_hi = st, *a_lo = st + A_BYTES, *b_hi = st + 2 * A_BYTES, *b_lo = st + 2 * A_BYTES + B_BYTES;
         sa.store(a_hi, a_lo, va);
         sb.store(b_hi, b_lo, vb);
+        if (!A_KMAJOR && do_colsum) {   // db rides along with dW: the dY slab is already in registers
+#pragma unroll
+            for (int i = 0; i < Stager<BM, A_KMAJOR>::PASSES; ++i) {
+                csum.x += va[i].x; csum.y += va[i].y; csum.z += va[i].z; csum.w += va[i].w;
+            }
+        }
         asm volatile("fence.proxy.async.shared::cta;" ::: "memory");   // generic-proxy smem writes -> visible to the tensor core
         __syncthreads();
         if (t == 0) {
@@ -258,6 +266,19 @@ __global__ void __launch_bounds__(TC_THREADS, 1) gemm_tf32x3_kernel(const TcGemm
     // ---- epilogue: TMEM -> registers -> global ----
     if (nslab > 0) mbar_wait(&bar_acc, 0);
     asm volatile("tcgen05.fence::after_thread_sync;" ::: "memory");
+    if (!A_KMAJOR && do_colsum) {
+        // thread t summed columns 4*(t%32).. of the k-rows congruent to t/32 (mod 8): fold the 8 warps in fixed order.
+        // (all MMAs have retired, so the operand stages are free to reuse as scratch)
+        float* red = reinterpret_cast<float*>(smem);
+        *reinterpret_cast<float4*>(red + warp * BM + (t & 31) * 4) = csum;
+        __syncthreads();
+        if (t < BM && m0 + t < p.M) {
+            float sum = 0.f;
+#pragma unroll
+            for (int wv = 0; wv < TC_THREADS / 32; ++wv) sum += red[wv * BM + t];
+            p.colsum[(long long)blockIdx.z * p.M + m0 + t] = sum;
+        }
+    }
     const int lane_q = warp & 3, col_half = warp >> 2;    // a warp may only touch TMEM lanes 32*(warp%4) .. +31
     const int m = m0 + lane_q * 32 + (t & 31);            // accumulator row = TMEM lane
     float* Cbase = p.C + (long long)blockIdx.z * p.c_split_stride;

@@ -11,6 +11,7 @@ struct TcGemmParams {
     const float* H; int ldh; int act_in;
     int k_chunk;                 // reduction elements per blockIdx.z (multiple of 32)
     long long c_split_stride;
+    float* colsum;               // MN-major A only (dW): colsum[blockIdx.z][M] = sum over this split's k of A[k][m] (nullable)
 };
 
 bool tc_gemm_supported(const TcGemmParams& p, bool a_kmajor, bool b_kmajor);

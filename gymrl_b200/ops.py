@@ -239,6 +239,20 @@ def linear_backward_weight(dy, x, dw, db=None, *, row_index=None, workspace=None
     return dw, db
 
 
+def linear_backward(dy, x, w, dw, db=None, *, dx=None, act_in=_ffi.ACT_NONE, row_index=None, workspace=None, accumulate=False, M=None):
+    """Whole layer backward: dw = dy.T @ x[row_index], db = dy.sum(0), dx = (dy @ w) * act'(x) (when dx is given)."""
+    N, K = dw.shape
+    M = dy.shape[0] if M is None else M
+    need = backward_weight_workspace(M, N, K)
+    if workspace is None:
+        workspace = torch.empty(need, device=dy.device, dtype=torch.uint8)
+    assert workspace.numel() * workspace.element_size() >= need, "workspace too small"
+    check(load().gymrl_linear_backward(ptr(dy, f32), _ld(dy), ptr(x, f32), _ld(x), ptr(row_index, i32), ptr(w, f32), ptr(dw, f32),
+                                       ptr(db, f32), ptr(dx, f32), _ld(dx) if dx is not None else 0, M, N, K, int(act_in),
+                                       int(accumulate), workspace.data_ptr(), workspace.numel() * workspace.element_size(), stream_ptr()))
+    return dw, db, dx
+
+
 # ------------------------------------------------------------------------------------------------
 # optimiser / target sync / permutation
 # ------------------------------------------------------------------------------------------------

@@ -207,6 +207,16 @@ int gymrl_linear_backward_weight(const float* d_dy, int lddy, const float* d_x, 
                                  int K, int accumulate, void* d_workspace, size_t workspace_bytes,
                                  void* stream);
 
+/* Whole backward of one dense layer in one call (what autograd does for nn.Linear, ppo_lunarlander.py:312
+ * loss.backward()): dW, db and, when d_dx != NULL, dX = (dY W) * act'(x) where x — the layer input — is the
+ * previous layer's activation output.  Policy / value / Q heads (N <= 8, K in {128, 256, 512}) run as ONE
+ * bandwidth-bound sweep over x; other shapes are gymrl_linear_backward_weight + gymrl_linear_backward_input.
+ * d_row_index (gathered input rows) requires d_dx == NULL.  Same workspace contract as backward_weight. */
+int gymrl_linear_backward(const float* d_dy, int lddy, const float* d_x, int ldx,
+                          const int32_t* d_row_index, const float* d_w, float* d_dw, float* d_db,
+                          float* d_dx, int lddx, int M, int N, int K, int act_in, int accumulate,
+                          void* d_workspace, size_t workspace_bytes, void* stream);
+
 /* ------------------------------------------------------------------------------------------------
  * Optimiser, clipping, target sync
  * ---------------------------------------------------------------------------------------------- */

@@ -265,6 +265,36 @@ def test_linear_backward_vs_torch_autograd(ops, M, N, K, act):
     assert torch.equal(dw, dw2)
 
 
+@pytest.mark.parametrize("M,N,K,act", [(16384, 4, 256, 1), (16384, 1, 256, 1), (256, 2, 128, 2), (4096, 3, 512, 1), (1000, 8, 256, 0),
+                                       (4096, 256, 256, 1), (300, 5, 64, 1)])
+def test_linear_backward_whole_layer(ops, M, N, K, act):
+    """gymrl_linear_backward (dW, db, dX in one call) == torch autograd of y = x @ w.T + b with x = act(pre); the
+    heads read / write strided halves of wider buffers exactly like ActorCriticEngine.backward."""
+    g = torch.Generator().manual_seed(M + 7 * N + K)
+    pre = torch.randn(M, 2 * K, generator=g)
+    x_full = torch.tanh(pre) if act == 1 else (torch.relu(pre) if act == 2 else pre)
+    w = torch.randn(N, K, generator=g) / K ** 0.5
+    dy_full = torch.randn(M, max(8, N), generator=g) / M
+    x, dy = x_full[:, K:], dy_full[:, :N]
+    dx_ref = dy @ w
+    if act == 1:
+        dx_ref = dx_ref * (1 - x ** 2)
+    elif act == 2:
+        dx_ref = dx_ref * (x > 0)
+    dw = torch.zeros(N, K, device="cuda"); db = torch.zeros(N, device="cuda")
+    dx_full = torch.full((M, 2 * K), 7.0, device="cuda")
+    xc, dyc = x_full.cuda(), dy_full.cuda()
+    ops.linear_backward(dyc[:, :N], xc[:, K:], w.cuda(), dw, db, dx=dx_full[:, K:], act_in=act)
+    torch.testing.assert_close(dx_full[:, K:].cpu(), dx_ref, rtol=1e-4, atol=1e-6 / M ** 0.5 + 1e-8)
+    assert (dx_full[:, :K] == 7.0).all()
+    torch.testing.assert_close(dw.cpu(), dy.T @ x, rtol=1e-4, atol=2e-6)
+    torch.testing.assert_close(db.cpu(), dy.sum(0), rtol=1e-4, atol=2e-6)
+    # deterministic, and dX optional
+    dw2 = torch.zeros(N, K, device="cuda")
+    ops.linear_backward(dyc[:, :N], xc[:, K:], w.cuda(), dw2, None)
+    assert torch.equal(dw, dw2)
+
+
 def test_linear_backward_weight_gather(ops):
     g = torch.Generator().manual_seed(5)
     X = torch.randn(9000, 8, generator=g)
