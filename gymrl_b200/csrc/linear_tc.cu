@@ -26,6 +26,13 @@ void gymrl_count_launch(int n = 1);
 
 #include "linear_tc.cuh"
 
+// developer timeline probe (tools/tc_timeline.py): CTA 0 / thread 0 and thread 255 stamp clock64() per pipeline phase
+__device__ long long* g_tc_dbg = nullptr;
+extern "C" int gymrl_debug_tc_timeline(long long* d_buf) {
+    return cudaMemcpyToSymbol(g_tc_dbg, &d_buf, sizeof(d_buf)) == cudaSuccess ? 0 : -1;
+}
+#define TC_STAMP(slot) do { if (dbg) dbg[(slot)] = clock64(); } while (0)
+
 __device__ __forceinline__ uint32_t smem_u32(const void* p) { return (uint32_t)__cvta_generic_to_shared(p); }
 
 __device__ __forceinline__ void mbar_init(uint64_t* bar, uint32_t count) {
@@ -64,11 +71,9 @@ template <int ROWS>
 __device__ __forceinline__ uint64_t make_desc_mn(uint32_t base, int j) {
     return make_desc(base + (uint32_t)(2 * j * (ROWS / 32)) * 512u, 512u, (uint32_t)(ROWS / 32) * 512u, 1u);
 }
-__device__ __forceinline__ uint32_t to_tf32(float x) {
-    uint32_t r;
-    asm("cvt.rna.tf32.f32 %0, %1;" : "=r"(r) : "f"(x));
-    return r;
-}
+// fp32 -> tf32, round to nearest (ties away), for finite inputs bit-identical to cvt.rna.tf32.f32; two integer ops
+// instead of the four ptxas emits for the cvt (its Inf/NaN guard; non-finite inputs stay non-finite here too).
+__device__ __forceinline__ uint32_t to_tf32(float x) { return (__float_as_uint(x) + 0x1000u) & 0xffffe000u; }
 __device__ __forceinline__ void split4(const float4 v, uint4& hi, uint4& lo) {
     hi.x = to_tf32(v.x); hi.y = to_tf32(v.y); hi.z = to_tf32(v.z); hi.w = to_tf32(v.w);
     lo.x = to_tf32(v.x - __uint_as_float(hi.x)); lo.y = to_tf32(v.y - __uint_as_float(hi.y));
@@ -83,18 +88,29 @@ __device__ __forceinline__ void split4(const float4 v, uint4& hi, uint4& lo) {
 
 // tanh with fp32-grade accuracy (|rel err| < ~5e-7) in ~10 instructions: odd polynomial near 0, 1 - 2/(e^{2|x|}+1) elsewhere.
 // (libdevice tanhf costs ~40 dependent instructions per element, which made the 4-warp epilogue the bottleneck.)
+__device__ __forceinline__ float exp2f_approx(float x) {
+    float r;
+    asm("ex2.approx.ftz.f32 %0, %1;" : "=f"(r) : "f"(x));
+    return r;
+}
+__device__ __forceinline__ float rcp_approx(float x) {
+    float r;
+    asm("rcp.approx.ftz.f32 %0, %1;" : "=f"(r) : "f"(x));
+    return r;
+}
 __device__ __forceinline__ float tanh_fast(float x) {
+    // branch-free: both forms are evaluated and selected (a per-element branch diverges inside almost every warp and
+    // its BSSY/BSYNC overhead cost more than the ~7 extra instructions)
     const float ax = fabsf(x);
-    if (ax < 0.25f) {
-        const float x2 = x * x;
-        float p = 62.0f / 2835.0f;
-        p = fmaf(p, x2, -17.0f / 315.0f);
-        p = fmaf(p, x2, 2.0f / 15.0f);
-        p = fmaf(p, x2, -1.0f / 3.0f);
-        return fmaf(x * x2, p, x);
-    }
-    const float e = __expf(2.0f * ax);
-    return copysignf(1.0f - __fdividef(2.0f, e + 1.0f), x);
+    const float x2 = x * x;
+    float p = 62.0f / 2835.0f;
+    p = fmaf(p, x2, -17.0f / 315.0f);
+    p = fmaf(p, x2, 2.0f / 15.0f);
+    p = fmaf(p, x2, -1.0f / 3.0f);
+    const float small = fmaf(x * x2, p, x);
+    const float e = exp2f_approx(ax * 2.885390081777927f);   // e^{2|x|}
+    const float big = copysignf(fmaf(-2.0f, rcp_approx(e + 1.0f), 1.0f), x);
+    return ax < 0.25f ? small : big;
 }
 
 // One operand's [ROWS x 32 k] slab pipeline: global -> registers (load) and registers -> hi/lo tf32 images in the
@@ -172,24 +188,34 @@ struct Stager {
     }
 };
 
+#define TC_LAUNCH_THREADS (TC_THREADS + 32)   // 8 producer / epilogue warps + 1 MMA-issue warp
+
+__device__ __forceinline__ void mbar_arrive(uint64_t* bar) {
+    asm volatile("mbarrier.arrive.shared::cta.b64 _, [%0];" ::"r"(smem_u32(bar)) : "memory");
+}
+__device__ __forceinline__ void producers_sync() { asm volatile("bar.sync 1, %0;" ::"n"(TC_THREADS) : "memory"); }
+
 template <int BN, bool A_KMAJOR, bool B_KMAJOR>
-__global__ void __launch_bounds__(TC_THREADS, 1) gemm_tf32x3_kernel(const TcGemmParams p) {
+__global__ void __launch_bounds__(TC_LAUNCH_THREADS, 1) gemm_tf32x3_kernel(const TcGemmParams p) {
     constexpr int BM = 128;
     constexpr uint32_t A_BYTES = BM * 128, B_BYTES = BN * 128;           // one image (hi or lo) of one 32-k slab
     constexpr uint32_t STAGE_BYTES = 2 * A_BYTES + 2 * B_BYTES;
     extern __shared__ __align__(1024) uint8_t smem_raw[];
     uint8_t* smem = reinterpret_cast<uint8_t*>((reinterpret_cast<uintptr_t>(smem_raw) + 1023) & ~(uintptr_t)1023);
-    __shared__ __align__(8) uint64_t bar_free[2];
-    __shared__ __align__(8) uint64_t bar_acc;
+    __shared__ __align__(8) uint64_t bar_full[2];   // producers -> MMA warp: stage converted (TC_THREADS arrivals)
+    __shared__ __align__(8) uint64_t bar_free[2];   // tensor core -> producers: the MMAs reading the stage retired (tcgen05.commit)
+    __shared__ __align__(8) uint64_t bar_acc;       // tensor core -> epilogue: accumulator complete
     __shared__ uint32_t tmem_base_s;
 
-    const int t = threadIdx.x, warp = t >> 5;
+    const int t = threadIdx.x, warp = t >> 5, lane = t & 31;
     const int m0 = blockIdx.y * BM, n0 = blockIdx.x * BN;
     const int kbeg = blockIdx.z * p.k_chunk;
     const int kend = min(p.K, kbeg + p.k_chunk);
     const int nslab = (kend - kbeg + 31) / 32;
 
     if (t == 0) {
+        mbar_init(&bar_full[0], TC_THREADS);
+        mbar_init(&bar_full[1], TC_THREADS);
         mbar_init(&bar_free[0], 1);
         mbar_init(&bar_free[1], 1);
         mbar_init(&bar_acc, 1);
@@ -204,118 +230,170 @@ __global__ void __launch_bounds__(TC_THREADS, 1) gemm_tf32x3_kernel(const TcGemm
     asm volatile("tcgen05.fence::after_thread_sync;" ::: "memory");
     const uint32_t tmem_d = tmem_base_s;
 
-    // instruction descriptor (cute::UMMA::InstrDescriptor): D=F32, A=B=TF32, majors, N>>3, M>>4
-    constexpr uint32_t IDESC = (1u << 4) | (2u << 7) | (2u << 10) | ((A_KMAJOR ? 0u : 1u) << 15) | ((B_KMAJOR ? 0u : 1u) << 16) |
-                               ((uint32_t)(BN >> 3) << 17) | ((uint32_t)(BM >> 4) << 24);
+    long long* dbg = (g_tc_dbg && blockIdx.x == 0 && blockIdx.y == 0 && blockIdx.z == 0 && (t == 0 || t == TC_THREADS)) ? g_tc_dbg + (t ? 512 : 0) : nullptr;
+    TC_STAMP(0);
 
-    Stager<BM, A_KMAJOR> sa;
-    Stager<BN, B_KMAJOR> sb;
-    sa.init(p.A, p.lda, p.a_rows, m0, p.M, kbeg);
-    sb.init(p.B, p.ldb, p.b_rows, n0, p.N, kbeg);
-    float4 va0[Stager<BM, A_KMAJOR>::PASSES], vb0[Stager<BN, B_KMAJOR>::PASSES];
-    float4 va1[Stager<BM, A_KMAJOR>::PASSES], vb1[Stager<BN, B_KMAJOR>::PASSES];
-
-    const bool do_colsum = !A_KMAJOR && p.colsum != nullptr && blockIdx.x == 0;
-    float4 csum = make_float4(0.f, 0.f, 0.f, 0.f);
-    // convert one slab from registers into stage kb & 1 and hand it to the tensor core
-    auto consume = [&](int kb, const float4 (&va)[Stager<BM, A_KMAJOR>::PASSES], const float4 (&vb)[Stager<BN, B_KMAJOR>::PASSES]) {
-        const int s = kb & 1, use = kb >> 1;
-        if (use >= 1) mbar_wait(&bar_free[s], (uint32_t)((use - 1) & 1));   // MMAs that read this stage have retired
-        uint8_t* st = smem + (size_t)s * STAGE_BYTES;
-        uint8_t *a_hi = st, *a_lo = st + A_BYTES, *b_hi = st + 2 * A_BYTES, *b_lo = st + 2 * A_BYTES + B_BYTES;
-        sa.store(a_hi, a_lo, va);
-        sb.store(b_hi, b_lo, vb);
-        if (!A_KMAJOR && do_colsum) {   // db rides along with dW: the dY slab is already in registers
+    if (warp == TC_THREADS / 32) {
+        // ===== MMA-issue warp: one elected lane feeds the tensor core; issuing blocks for about the duration of the
+        // MMAs (measured: 1.4k cycles per 12-MMA slab), which is why it must not share a thread with the converters =====
+        if (lane == 0) {
+            // instruction descriptor (cute::UMMA::InstrDescriptor): D=F32, A=B=TF32, majors, N>>3, M>>4
+            constexpr uint32_t IDESC = (1u << 4) | (2u << 7) | (2u << 10) | ((A_KMAJOR ? 0u : 1u) << 15) | ((B_KMAJOR ? 0u : 1u) << 16) |
+                                       ((uint32_t)(BN >> 3) << 17) | ((uint32_t)(BM >> 4) << 24);
+            for (int kb = 0; kb < nslab; ++kb) {
+                const int s = kb & 1, use = kb >> 1;
+                TC_STAMP(8 + kb * 8 + 0);
+                mbar_wait(&bar_full[s], (uint32_t)(use & 1));
+                TC_STAMP(8 + kb * 8 + 1);
+                asm volatile("tcgen05.fence::after_thread_sync;" ::: "memory");
+                const uint32_t st = smem_u32(smem + (size_t)s * STAGE_BYTES);
+                const uint32_t ah = st, al = st + A_BYTES, bh = st + 2 * A_BYTES, bl = st + 2 * A_BYTES + B_BYTES;
 #pragma unroll
-            for (int i = 0; i < Stager<BM, A_KMAJOR>::PASSES; ++i) {
-                csum.x += va[i].x; csum.y += va[i].y; csum.z += va[i].z; csum.w += va[i].w;
+                for (int j = 0; j < 4; ++j) {   // 4 k-steps of 8
+                    // K-major: +32 B inside the 128 B swizzle span (LBO = 16 B unused, SBO = 1024 B between 8-row atoms)
+                    // MN-major: k-atom pair j; LBO = 512 B between MN atoms, SBO = k-atom stride
+                    const uint64_t dah = A_KMAJOR ? make_desc(ah + j * 32, 16, 1024) : make_desc_mn<BM>(ah, j);
+                    const uint64_t dal = A_KMAJOR ? make_desc(al + j * 32, 16, 1024) : make_desc_mn<BM>(al, j);
+                    const uint64_t dbh = B_KMAJOR ? make_desc(bh + j * 32, 16, 1024) : make_desc_mn<BN>(bh, j);
+                    const uint64_t dbl = B_KMAJOR ? make_desc(bl + j * 32, 16, 1024) : make_desc_mn<BN>(bl, j);
+                    umma_tf32(tmem_d, dal, dbh, IDESC, (kb | j) ? 1u : 0u);
+                    umma_tf32(tmem_d, dah, dbl, IDESC, 1u);
+                    umma_tf32(tmem_d, dah, dbh, IDESC, 1u);
+                }
+                umma_commit(&bar_free[s]);
+                if (kb == nslab - 1) umma_commit(&bar_acc);
+                TC_STAMP(8 + kb * 8 + 2);
             }
         }
-        asm volatile("fence.proxy.async.shared::cta;" ::: "memory");   // generic-proxy smem writes -> visible to the tensor core
-        __syncthreads();
-        if (t == 0) {
-            asm volatile("tcgen05.fence::after_thread_sync;" ::: "memory");
-            const uint32_t ah = smem_u32(a_hi), al = smem_u32(a_lo), bh = smem_u32(b_hi), bl = smem_u32(b_lo);
+    } else {
+        // ===== producer warps: global -> registers -> hi/lo tf32 images in the stage ring; then the epilogue =====
+        Stager<BM, A_KMAJOR> sa;
+        Stager<BN, B_KMAJOR> sb;
+        sa.init(p.A, p.lda, p.a_rows, m0, p.M, kbeg);
+        sb.init(p.B, p.ldb, p.b_rows, n0, p.N, kbeg);
+        float4 va0[Stager<BM, A_KMAJOR>::PASSES], vb0[Stager<BN, B_KMAJOR>::PASSES];
+        float4 va1[Stager<BM, A_KMAJOR>::PASSES], vb1[Stager<BN, B_KMAJOR>::PASSES];
+        float4 va2[Stager<BM, A_KMAJOR>::PASSES], vb2[Stager<BN, B_KMAJOR>::PASSES];
+        const bool do_colsum = !A_KMAJOR && p.colsum != nullptr && blockIdx.x == 0;
+        float4 csum = make_float4(0.f, 0.f, 0.f, 0.f);
+
+        auto consume = [&](int kb, const float4 (&va)[Stager<BM, A_KMAJOR>::PASSES], const float4 (&vb)[Stager<BN, B_KMAJOR>::PASSES]) {
+            const int s = kb & 1, use = kb >> 1;
+            TC_STAMP(8 + kb * 8 + 0);
+            if (use >= 1) mbar_wait(&bar_free[s], (uint32_t)((use - 1) & 1));   // MMAs that read this stage have retired
+            TC_STAMP(8 + kb * 8 + 1);
+            uint8_t* st = smem + (size_t)s * STAGE_BYTES;
+            sa.store(st, st + A_BYTES, va);
+            sb.store(st + 2 * A_BYTES, st + 2 * A_BYTES + B_BYTES, vb);
+            if (!A_KMAJOR && do_colsum) {   // db rides along with dW: the dY slab is already in registers
 #pragma unroll
-            for (int j = 0; j < 4; ++j) {   // 4 k-steps of 8
-                // K-major: +32 B inside the 128 B swizzle span (LBO = 16 B unused, SBO = 1024 B between 8-row atoms)
-                // MN-major: k-atom pair j; LBO = 512 B between MN atoms, SBO = k-atom stride
-                const uint64_t dah = A_KMAJOR ? make_desc(ah + j * 32, 16, 1024) : make_desc_mn<BM>(ah, j);
-                const uint64_t dal = A_KMAJOR ? make_desc(al + j * 32, 16, 1024) : make_desc_mn<BM>(al, j);
-                const uint64_t dbh = B_KMAJOR ? make_desc(bh + j * 32, 16, 1024) : make_desc_mn<BN>(bh, j);
-                const uint64_t dbl = B_KMAJOR ? make_desc(bl + j * 32, 16, 1024) : make_desc_mn<BN>(bl, j);
-                umma_tf32(tmem_d, dal, dbh, IDESC, (kb | j) ? 1u : 0u);
-                umma_tf32(tmem_d, dah, dbl, IDESC, 1u);
-                umma_tf32(tmem_d, dah, dbh, IDESC, 1u);
+                for (int i = 0; i < Stager<BM, A_KMAJOR>::PASSES; ++i) {
+                    csum.x += va[i].x; csum.y += va[i].y; csum.z += va[i].z; csum.w += va[i].w;
+                }
             }
-            umma_commit(&bar_free[s]);
-            if (kb == nslab - 1) umma_commit(&bar_acc);
-        }
-    };
+            asm volatile("fence.proxy.async.shared::cta;" ::: "memory");   // generic-proxy smem writes -> visible to the tensor core
+            mbar_arrive(&bar_full[s]);
+            TC_STAMP(8 + kb * 8 + 2);
+        };
 
-    if (nslab > 0) { sa.load(va0); sb.load(vb0); }
-    for (int kb = 0; kb < nslab; kb += 2) {
-        if (kb + 1 < nslab) { sa.load(va1); sb.load(vb1); }
-        consume(kb, va0, vb0);
-        if (kb + 1 < nslab) {
-            if (kb + 2 < nslab) { sa.load(va0); sb.load(vb0); }
-            consume(kb + 1, va1, vb1);
+        // register sets: the loads of the next slab(s) are in flight while slab k is converted.  The launch is 9 warps,
+        // for which ptxas budgets 168 registers per thread: three sets fit for BN <= 128, two for BN = 256.
+        if (BN <= 128) {
+            if (nslab > 0) { sa.load(va0); sb.load(vb0); }
+            if (nslab > 1) { sa.load(va1); sb.load(vb1); }
+            for (int kb = 0; kb < nslab; kb += 3) {
+                if (kb + 2 < nslab) { sa.load(va2); sb.load(vb2); }
+                consume(kb, va0, vb0);
+                if (kb + 1 < nslab) {
+                    if (kb + 3 < nslab) { sa.load(va0); sb.load(vb0); }
+                    consume(kb + 1, va1, vb1);
+                }
+                if (kb + 2 < nslab) {
+                    if (kb + 4 < nslab) { sa.load(va1); sb.load(vb1); }
+                    consume(kb + 2, va2, vb2);
+                }
+            }
+        } else {
+            if (nslab > 0) { sa.load(va0); sb.load(vb0); }
+            for (int kb = 0; kb < nslab; kb += 2) {
+                if (kb + 1 < nslab) { sa.load(va1); sb.load(vb1); }
+                consume(kb, va0, vb0);
+                if (kb + 1 < nslab) {
+                    if (kb + 2 < nslab) { sa.load(va0); sb.load(vb0); }
+                    consume(kb + 1, va1, vb1);
+                }
+            }
         }
-    }
 
-    // ---- epilogue: TMEM -> registers -> global ----
-    if (nslab > 0) mbar_wait(&bar_acc, 0);
-    asm volatile("tcgen05.fence::after_thread_sync;" ::: "memory");
-    if (!A_KMAJOR && do_colsum) {
-        // thread t summed columns 4*(t%32).. of the k-rows congruent to t/32 (mod 8): fold the 8 warps in fixed order.
-        // (all MMAs have retired, so the operand stages are free to reuse as scratch)
-        float* red = reinterpret_cast<float*>(smem);
-        *reinterpret_cast<float4*>(red + warp * BM + (t & 31) * 4) = csum;
-        __syncthreads();
-        if (t < BM && m0 + t < p.M) {
-            float sum = 0.f;
+        // ---- epilogue: TMEM -> registers -> smem transpose -> coalesced global ----
+        TC_STAMP(1);
+        if (nslab > 0) mbar_wait(&bar_acc, 0);
+        TC_STAMP(2);
+        asm volatile("tcgen05.fence::after_thread_sync;" ::: "memory");
+        // all MMAs have retired: the operand stages are free to reuse as scratch
+        if (!A_KMAJOR && do_colsum) {
+            // thread t summed columns 4*(t%32).. of the k-rows congruent to t/32 (mod 8): fold the 8 warps in fixed order
+            float* red = reinterpret_cast<float*>(smem + 64 * 1024);
+            *reinterpret_cast<float4*>(red + warp * BM + lane * 4) = csum;
+            producers_sync();
+            if (t < BM && m0 + t < p.M) {
+                float sum = 0.f;
 #pragma unroll
-            for (int wv = 0; wv < TC_THREADS / 32; ++wv) sum += red[wv * BM + t];
-            p.colsum[(long long)blockIdx.z * p.M + m0 + t] = sum;
+                for (int wv = 0; wv < TC_THREADS / 32; ++wv) sum += red[wv * BM + t];
+                p.colsum[(long long)blockIdx.z * p.M + m0 + t] = sum;
+            }
         }
-    }
-    const int lane_q = warp & 3, col_half = warp >> 2;    // a warp may only touch TMEM lanes 32*(warp%4) .. +31
-    const int m = m0 + lane_q * 32 + (t & 31);            // accumulator row = TMEM lane
-    float* Cbase = p.C + (long long)blockIdx.z * p.c_split_stride;
+        const int lane_q = warp & 3, col_half = warp >> 2;    // a warp may only touch TMEM lanes 32*(warp%4) .. +31
+        float* Cbase = p.C + (long long)blockIdx.z * p.c_split_stride;
+        // A thread owns one accumulator row (32 contiguous columns per tcgen05.ld): storing that directly makes every
+        // STG touch 32 different lines (measured: 12k cycles of epilogue per tile).  Each warp transposes its 32x32 block
+        // through a private, XOR-swizzled 4 KB scratch so that 8 lanes cover one 128 B row segment -> 4 lines per STG.
+        uint8_t* scr = smem + (size_t)warp * 4096;
+        const int cq = lane & 7, rsub = lane >> 3;
 #pragma unroll 1
-    for (int c0 = col_half * (BN / 2); c0 < (col_half + 1) * (BN / 2); c0 += 32) {
-        uint32_t r[32];
-        const uint32_t taddr = tmem_d + ((uint32_t)(lane_q * 32) << 16) + (uint32_t)c0;
-        asm volatile(
-            "tcgen05.ld.sync.aligned.32x32b.x32.b32 "
-            "{%0, %1, %2, %3, %4, %5, %6, %7, %8, %9, %10, %11, %12, %13, %14, %15, "
-            "%16, %17, %18, %19, %20, %21, %22, %23, %24, %25, %26, %27, %28, %29, %30, %31}, [%32];"
-            : "=r"(r[0]), "=r"(r[1]), "=r"(r[2]), "=r"(r[3]), "=r"(r[4]), "=r"(r[5]), "=r"(r[6]), "=r"(r[7]), "=r"(r[8]), "=r"(r[9]),
-              "=r"(r[10]), "=r"(r[11]), "=r"(r[12]), "=r"(r[13]), "=r"(r[14]), "=r"(r[15]), "=r"(r[16]), "=r"(r[17]), "=r"(r[18]),
-              "=r"(r[19]), "=r"(r[20]), "=r"(r[21]), "=r"(r[22]), "=r"(r[23]), "=r"(r[24]), "=r"(r[25]), "=r"(r[26]), "=r"(r[27]),
-              "=r"(r[28]), "=r"(r[29]), "=r"(r[30]), "=r"(r[31])
-            : "r"(taddr));
-        asm volatile("tcgen05.wait::ld.sync.aligned;" ::: "memory");
-        if (m < p.M) {
-            // bias / h loads first: they are independent of the accumulator, so their latency overlaps the math
-            float4 b4[8], h4[8];
+        for (int c0 = col_half * (BN / 2); c0 < (col_half + 1) * (BN / 2); c0 += 32) {
+            uint32_t r[32];
+            const uint32_t taddr = tmem_d + ((uint32_t)(lane_q * 32) << 16) + (uint32_t)c0;
+            asm volatile(
+                "tcgen05.ld.sync.aligned.32x32b.x32.b32 "
+                "{%0, %1, %2, %3, %4, %5, %6, %7, %8, %9, %10, %11, %12, %13, %14, %15, "
+                "%16, %17, %18, %19, %20, %21, %22, %23, %24, %25, %26, %27, %28, %29, %30, %31}, [%32];"
+                : "=r"(r[0]), "=r"(r[1]), "=r"(r[2]), "=r"(r[3]), "=r"(r[4]), "=r"(r[5]), "=r"(r[6]), "=r"(r[7]), "=r"(r[8]), "=r"(r[9]),
+                  "=r"(r[10]), "=r"(r[11]), "=r"(r[12]), "=r"(r[13]), "=r"(r[14]), "=r"(r[15]), "=r"(r[16]), "=r"(r[17]), "=r"(r[18]),
+                  "=r"(r[19]), "=r"(r[20]), "=r"(r[21]), "=r"(r[22]), "=r"(r[23]), "=r"(r[24]), "=r"(r[25]), "=r"(r[26]), "=r"(r[27]),
+                  "=r"(r[28]), "=r"(r[29]), "=r"(r[30]), "=r"(r[31])
+                : "r"(taddr));
+            // this lane's output columns after the transpose (same for all 8 row groups): bias loaded once per chunk
+            const int n = n0 + c0 + cq * 4;
+            const bool n_ok = n < p.N;
+            const float4 b4 = (p.bias && n_ok) ? __ldg(reinterpret_cast<const float4*>(p.bias + n)) : make_float4(0.f, 0.f, 0.f, 0.f);
+            asm volatile("tcgen05.wait::ld.sync.aligned;" ::: "memory");
 #pragma unroll
-            for (int q = 0; q < 8; ++q) {
-                const int n = min(n0 + c0 + q * 4, p.N - 4);
-                b4[q] = p.bias ? __ldg(reinterpret_cast<const float4*>(p.bias + n)) : make_float4(0.f, 0.f, 0.f, 0.f);
-                if (p.H) h4[q] = __ldg(reinterpret_cast<const float4*>(p.H + (long long)m * p.ldh + n));
+            for (int q = 0; q < 8; ++q)
+                *reinterpret_cast<uint4*>(scr + lane * 128 + ((q ^ (lane & 7)) << 4)) =
+                    nslab > 0 ? make_uint4(r[q * 4], r[q * 4 + 1], r[q * 4 + 2], r[q * 4 + 3]) : make_uint4(0u, 0u, 0u, 0u);
+            __syncwarp();
+            float4 h4[8];
+            if (p.H) {
+#pragma unroll
+                for (int j = 0; j < 8; ++j) {
+                    const int m = m0 + lane_q * 32 + j * 4 + rsub;
+                    if (m < p.M && n_ok) h4[j] = __ldg(reinterpret_cast<const float4*>(p.H + (long long)m * p.ldh + n));
+                }
             }
 #pragma unroll
-            for (int q = 0; q < 8; ++q) {
-                const int n = n0 + c0 + q * 4;
-                if (n >= p.N) continue;
-                const float bq[4] = {b4[q].x, b4[q].y, b4[q].z, b4[q].w};
-                const float hq[4] = {h4[q].x, h4[q].y, h4[q].z, h4[q].w};
+            for (int j = 0; j < 8; ++j) {
+                const int row = j * 4 + rsub;
+                const int m = m0 + lane_q * 32 + row;
+                const float4 a4 = *reinterpret_cast<const float4*>(scr + row * 128 + ((cq ^ (row & 7)) << 4));
+                if (m >= p.M || !n_ok) continue;
+                const float acc[4] = {a4.x, a4.y, a4.z, a4.w};
+                const float bq[4] = {b4.x, b4.y, b4.z, b4.w};
+                const float hq[4] = {h4[j].x, h4[j].y, h4[j].z, h4[j].w};
                 float o[4];
 #pragma unroll
                 for (int e = 0; e < 4; ++e) {
-                    float v = nslab > 0 ? __uint_as_float(r[q * 4 + e]) : 0.f;
-                    v += bq[e];
+                    float v = acc[e] + bq[e];
                     if (p.act == GYMRL_ACT_TANH) v = tanh_fast(v);
                     else if (p.act == GYMRL_ACT_RELU) v = fmaxf(v, 0.f);
                     if (p.H) {
@@ -327,7 +405,9 @@ __global__ void __launch_bounds__(TC_THREADS, 1) gemm_tf32x3_kernel(const TcGemm
                 }
                 *reinterpret_cast<float4*>(Cbase + (long long)m * p.ldc + n) = make_float4(o[0], o[1], o[2], o[3]);
             }
+            __syncwarp();   // the scratch is rewritten by the next chunk
         }
+        TC_STAMP(3);
     }
     asm volatile("tcgen05.fence::before_thread_sync;" ::: "memory");
     __syncthreads();
@@ -347,7 +427,7 @@ static int launch_tc(const TcGemmParams& p, int splits, cudaStream_t s) {
         configured = true;
     }
     dim3 grid(p.N / BN, ceil_div(p.M, 128), splits);
-    gemm_tf32x3_kernel<BN, AK, BKM><<<grid, TC_THREADS, SMEM, s>>>(p);
+    gemm_tf32x3_kernel<BN, AK, BKM><<<grid, TC_LAUNCH_THREADS, SMEM, s>>>(p);
     gymrl_count_launch();
     return GYMRL_OK;
 }
