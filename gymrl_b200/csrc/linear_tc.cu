@@ -86,33 +86,6 @@ __device__ __forceinline__ void split4(const float4 v, uint4& hi, uint4& lo) {
 //           (32 MN elements), at ((j * ROWS/32) + i) * 1024.
 #define TC_THREADS 256   // 8 warps: two warps per TMEM lane quarter, so staging and the epilogue have latency-hiding partners
 
-// tanh with fp32-grade accuracy (|rel err| < ~5e-7) in ~10 instructions: odd polynomial near 0, 1 - 2/(e^{2|x|}+1) elsewhere.
-// (libdevice tanhf costs ~40 dependent instructions per element, which made the 4-warp epilogue the bottleneck.)
-__device__ __forceinline__ float exp2f_approx(float x) {
-    float r;
-    asm("ex2.approx.ftz.f32 %0, %1;" : "=f"(r) : "f"(x));
-    return r;
-}
-__device__ __forceinline__ float rcp_approx(float x) {
-    float r;
-    asm("rcp.approx.ftz.f32 %0, %1;" : "=f"(r) : "f"(x));
-    return r;
-}
-__device__ __forceinline__ float tanh_fast(float x) {
-    // branch-free: both forms are evaluated and selected (a per-element branch diverges inside almost every warp and
-    // its BSSY/BSYNC overhead cost more than the ~7 extra instructions)
-    const float ax = fabsf(x);
-    const float x2 = x * x;
-    float p = 62.0f / 2835.0f;
-    p = fmaf(p, x2, -17.0f / 315.0f);
-    p = fmaf(p, x2, 2.0f / 15.0f);
-    p = fmaf(p, x2, -1.0f / 3.0f);
-    const float small = fmaf(x * x2, p, x);
-    const float e = exp2f_approx(ax * 2.885390081777927f);   // e^{2|x|}
-    const float big = copysignf(fmaf(-2.0f, rcp_approx(e + 1.0f), 1.0f), x);
-    return ax < 0.25f ? small : big;
-}
-
 // One operand's [ROWS x 32 k] slab pipeline: global -> registers (load) and registers -> hi/lo tf32 images in the
 // canonical UMMA smem layout (store).  Loads are unconditional (out-of-range MN rows are clamped onto valid ones:
 // they only feed output rows/columns the epilogue never writes) and addressed through per-thread pointers set up
@@ -348,6 +321,8 @@ __global__ void __launch_bounds__(TC_LAUNCH_THREADS, 1) gemm_tf32x3_kernel(const
         // A thread owns one accumulator row (32 contiguous columns per tcgen05.ld): storing that directly makes every
         // STG touch 32 different lines (measured: 12k cycles of epilogue per tile).  Each warp transposes its 32x32 block
         // through a private, XOR-swizzled 4 KB scratch so that 8 lanes cover one 128 B row segment -> 4 lines per STG.
+        // (Prefetching the next chunk's tcgen05.ld while the current one is stored was tried and measured 8-20 % slower
+        // on the same box, so the chunks stay strictly sequential.)
         uint8_t* scr = smem + (size_t)warp * 4096;
         const int cq = lane & 7, rsub = lane >> 3;
 #pragma unroll 1
@@ -445,7 +420,12 @@ bool tc_gemm_supported(const TcGemmParams& p, bool a_kmajor, bool b_kmajor) {
 }
 
 int tc_gemm_launch(const TcGemmParams& p, bool a_kmajor, bool b_kmajor, int splits, cudaStream_t s) {
-    const int bn = (p.N % 256 == 0) ? 256 : (p.N % 128 == 0 ? 128 : 64);
+    // widest tile that still gives (nearly) every SM a CTA: the rollout's M = 4096 forward would otherwise run 32 CTAs
+    // on 148 SMs.  (tc_gemm_supported guarantees N % 64 == 0.)
+    const long long mt = (long long)ceil_div(p.M, 128) * splits;
+    int bn = 64;
+    if (p.N % 256 == 0 && mt * (p.N / 256) >= 120) bn = 256;
+    else if (p.N % 128 == 0 && mt * (p.N / 128) >= 120) bn = 128;
 #define TC_DISPATCH(AK, BKM)                                             \
     switch (bn) {                                                        \
         case 256: return launch_tc<256, AK, BKM>(p, splits, s);          \
