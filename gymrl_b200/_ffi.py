@@ -46,6 +46,7 @@ SIGNATURES = {
     "gymrl_env_step": (c_int, [_P] * 9),
     "gymrl_env_get_state": (c_int, [_P, _P, _P]),
     "gymrl_env_set_state": (c_int, [_P, _P, _P]),
+    "gymrl_env_set_profile": (c_int, [_P, _P]),
     "gymrl_env_episode_stats": (c_int, [_P, c_int, _P, _P, _P, _P]),
     "gymrl_sample_categorical": (c_int, [_P, c_int, _P, _P, _P, _P, _P, c_int, _P, c_int, c_int, c_u64, c_u64, c_u32, _P, c_int, _P]),
     "gymrl_select_eps_greedy": (c_int, [_P, c_int, _P, c_int, c_int, c_float, c_u64, c_u64, c_u32, _P, _P]),

@@ -350,6 +350,13 @@ extern "C" int gymrl_env_set_state(gymrl_env* e, const double* d_state, void* st
     return GYMRL_OK;
 }
 
+extern "C" int gymrl_env_set_profile(gymrl_env* e, long long* d_prof) {
+    GYMRL_REQUIRE(e != nullptr, "env is NULL");
+    GYMRL_REQUIRE(e->kind == GYMRL_ENV_LUNARLANDER || d_prof == nullptr, "profile counters exist for LunarLander only");
+    e->prof = d_prof;
+    return GYMRL_OK;
+}
+
 extern "C" int gymrl_env_episode_stats(gymrl_env* e, int last_k, double* mean_return, double* mean_length,
                                        uint64_t* total_episodes, void* stream) {
     GYMRL_REQUIRE(e != nullptr, "env is NULL");

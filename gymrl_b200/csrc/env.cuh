@@ -25,6 +25,13 @@ struct gymrl_env {
     int32_t* refill_list;    // [3][N]
     int32_t* refill_count;   // [3] (+ tick at [3])
     int32_t* tick;           // step counter mod-3 addressing of the refill queues
+    // LunarLander work scheduling: a step's solver chain is 4-8x longer for an env with ground contacts than for one
+    // in free flight, so the step kernel runs the few heavy envs first and alone in their warps and packs the light
+    // ones densely (results do not depend on the mapping).  cost = touching manifolds in the env's last step.
+    int32_t* cost;           // [N]
+    int32_t* order;          // [N] env ids, heavy first
+    int32_t* order_cnt;      // [2] = {heavy count, heavy envs per warp}
+    long long* prof;         // nullable diagnostic buffer [N][8], see gymrl_env_set_profile
     // shared bookkeeping, all [N]
     int32_t* elapsed;     // TimeLimit counter
     uint32_t* episode;    // episodes started so far (keys the reset draws)

@@ -93,6 +93,11 @@ class VecEnv:
         assert s.shape == (self.num_envs, self.state_doubles)
         check(load().gymrl_env_set_state(self._h, ptr(s, f64), stream_ptr()))
 
+    def set_profile(self, buf: Optional[torch.Tensor]) -> None:
+        """Diagnostic: int64 [N, 8] device buffer the LunarLander step kernel fills with per-env cycle counters."""
+        self._prof = buf
+        check(load().gymrl_env_set_profile(self._h, ptr(buf, torch.int64) if buf is not None else None))
+
     def episode_stats(self, last_k: int = 100) -> Tuple[float, float, int]:
         mr, ml, te = C.c_double(), C.c_double(), C.c_uint64()
         check(load().gymrl_env_episode_stats(self._h, int(last_k), C.byref(mr), C.byref(ml), C.byref(te), stream_ptr()))

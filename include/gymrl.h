@@ -76,6 +76,10 @@ int gymrl_env_step(gymrl_env* env, const void* d_actions, float* d_obs, float* d
  * teacher-force the device env from the oracle (and vice versa). */
 int gymrl_env_get_state(gymrl_env* env, double* d_state, void* stream);
 int gymrl_env_set_state(gymrl_env* env, const double* d_state, void* stream);
+/* Diagnostic (LunarLander only; no reference counterpart): d_prof = device int64 [N][8], overwritten by every
+ * subsequent step with {step cycles, collide, constraint setup, velocity iterations, position iterations (cycles),
+ * touching manifolds, position iterations run, work slot}.  NULL switches it off (the default). */
+int gymrl_env_set_profile(gymrl_env* env, long long* d_prof);
 /* Mean return/length over the last `last_k` finished episodes (all envs).  SYNCHRONOUS (one small
  * D2H) — call at log time only.  Replaces the deque(maxlen=100) bookkeeping at
  * algorithms/ppo_lunarlander.py:172,219-221. */
