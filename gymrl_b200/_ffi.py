@@ -25,7 +25,7 @@ class PPOCfg(C.Structure):
     """struct gymrl_ppo_cfg"""
     _fields_ = [("mode", c_int), ("clip_eps_min", c_float), ("clip_eps_max", c_float), ("dual_clip", c_float),
                 ("value_coef", c_float), ("entropy_coef", c_float), ("erc_low", c_float), ("erc_high", c_float),
-                ("vclip_eps_min", c_float), ("vclip_eps_max", c_float)]
+                ("vclip_eps_min", c_float), ("vclip_eps_max", c_float), ("d_entropy_coef", c_void_p)]
 
 
 PPO_DUALCLIP, PPO_FULL, PPO_VALUE_CLIP = 0, 1, 4
@@ -68,6 +68,14 @@ SIGNATURES = {
     "gymrl_adam_step": (c_int, [_P, _P, _P, _P, c_ll, _P, c_float, c_float, c_float, _P, _P, c_float, c_float, c_float, _P]),
     "gymrl_polyak": (c_int, [_P, _P, c_ll, c_float, _P]),
     "gymrl_random_permutation": (c_int, [_P, c_int, c_u64, c_u32, _P, _P]),
+    "gymrl_mhc_workspace_bytes": (c_size_t, [c_int, c_int, c_int]),
+    "gymrl_mhc_stage_forward": (c_int, [_P, c_int, c_int, _P, _P, _P, _P, _P, _P, _P, _P, _P, _P, _P, c_int, c_int, c_int, c_float, _P]),
+    "gymrl_mhc_stage_backward_a": (c_int, [_P, c_int, c_int, _P, _P, _P, _P, _P, _P, _P, _P, _P, c_int, c_int, c_int, _P]),
+    "gymrl_mhc_stage_backward_b": (c_int, [_P, c_int, c_int, _P, _P, _P, _P, _P, _P, _P, _P, _P, _P, _P, _P, _P, c_size_t, c_int,
+                                           c_int, c_int, _P]),
+    "gymrl_rmsnorm_forward": (c_int, [_P, c_int, c_int, c_int, _P, _P, c_int, c_int, c_int, c_int, c_float, _P]),
+    "gymrl_rmsnorm_backward": (c_int, [_P, c_int, c_int, c_int, _P, _P, c_int, _P, c_int, _P, _P, c_size_t, c_int, c_int, c_int,
+                                       c_int, c_float, _P]),
     "gymrl_counter_add": (c_int, [_P, c_u32, _P]),
     "gymrl_slice_i32": (c_int, [_P, _P, c_int, _P, _P]),
     "gymrl_replay_sample_indices": (c_int, [_P, c_int, _P, c_u64, c_u32, _P, _P]),

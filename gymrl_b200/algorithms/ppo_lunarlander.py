@@ -214,13 +214,13 @@ class PPOTrainer:
 
         self.env = ops.VecEnv(cfg.env_name, N, seed=self.seed, first_env_id=gdist.shard(N, self.rank)[0])
         state_dim, action_dim = self.env.obs_dim, self.env.n_actions
-        self.model = ActorCritic(state_dim, action_dim, cfg.hidden_dim)
+        self.model = self._make_model(state_dim, action_dim)
         gdist.broadcast_module_(self.model, self.device)   # identical replicas: rank 0's initialisation everywhere
         self.net = self.model.to_engine(self.device)
         self.optimizer = FusedAdam(self.net.fp, lr=cfg.lr, eps=1e-5)
         self.buffer = RolloutBuffer(T, N, state_dim, self.device)
-        self.acts_roll = _Acts(N, cfg.hidden_dim, action_dim, self.device, backward=False)
-        self.acts_mb = _Acts(self.mb, cfg.hidden_dim, action_dim, self.device, backward=True)
+        self.acts_roll = self._make_acts(N, backward=False)
+        self.acts_mb = self._make_acts(self.mb, backward=True)
         self.net.alloc_workspace(self.mb)
         self.perm = torch.zeros(N * T, device=self.device, dtype=i32)
         self.idx_mb = torch.zeros(self.mb, device=self.device, dtype=i32)
@@ -231,8 +231,7 @@ class PPOTrainer:
         self.ctr_mb = torch.zeros(1, device=self.device, dtype=i32)       # minibatch window within the epoch
         self.term = torch.zeros(N, device=self.device, dtype=u8)
         self.trunc = torch.zeros(N, device=self.device, dtype=u8)
-        self.loss_cfg = _ffi.PPOCfg(mode=_ffi.PPO_DUALCLIP, clip_eps_min=cfg.clip_eps, clip_eps_max=cfg.clip_eps,
-                                    dual_clip=cfg.dual_clip, value_coef=cfg.value_coef, entropy_coef=cfg.entropy_coef)
+        self.loss_cfg = self._make_loss_cfg()
         self.step_count = 0
         self.episode_rewards = deque(maxlen=100)
         self._episodes_seen = 0
@@ -248,15 +247,37 @@ class PPOTrainer:
             print(f"Model parameters: {sum(p.numel() for p in self.model.parameters()):,}")
             print(f"Envs: {N} x {self.world} GPU(s), rollout {T} steps, {self.n_mb} minibatches of {self.mb}")
 
+    # ---------------------------------------------------------------- construction hooks (ppo_full overrides them)
+    def _make_model(self, state_dim: int, action_dim: int) -> nn.Module:
+        return ActorCritic(state_dim, action_dim, self.cfg.hidden_dim)
+
+    def _make_acts(self, M: int, backward: bool, n_actions: Optional[int] = None):
+        return _Acts(M, self.cfg.hidden_dim, n_actions or self.env.n_actions, self.device, backward)
+
+    def _make_loss_cfg(self):
+        cfg = self.cfg
+        return _ffi.PPOCfg(mode=_ffi.PPO_DUALCLIP, clip_eps_min=cfg.clip_eps, clip_eps_max=cfg.clip_eps,
+                           dual_clip=cfg.dual_clip, value_coef=cfg.value_coef, entropy_coef=cfg.entropy_coef)
+
+    def _sample_step(self, acts, t: int):
+        buf, N, A = self.buffer, self.N, self.env.n_actions
+        ops.sample_categorical(acts.lv[:, :A], seed=self.seed, first_id=self.rank * N, draw_base=self.ctr_action,
+                               action=buf.action[t], logp=buf.log_prob[t], value_in=acts.lv[:, A:A + 1],
+                               value_out=buf.value[t])
+
+    def _loss_step(self, acts):
+        buf, A = self.buffer, self.env.n_actions
+        ops.ppo_loss(acts.lv[:, :A], acts.lv[:, A:A + 1], buf.action.view(-1), buf.log_prob.view(-1), buf.adv.view(-1),
+                     buf.ret.view(-1), self.loss_cfg, row_index=self.idx_mb, dlogits=acts.dlv[:, :A],
+                     dvalue=acts.dlv[:, A:A + 1], metrics=self.metrics)
+
     # ---------------------------------------------------------------- rollout
     def _rollout_body(self):
         buf, env, net, acts = self.buffer, self.env, self.net, self.acts_roll
         N, A = self.N, self.env.n_actions
         for t in range(self.T):
             net.forward(buf.obs[t], acts, N)
-            ops.sample_categorical(acts.lv[:, :A], seed=self.seed, first_id=self.rank * N, draw_base=self.ctr_action,
-                                   action=buf.action[t], logp=buf.log_prob[t], value_in=acts.lv[:, A:A + 1],
-                                   value_out=buf.value[t])
+            self._sample_step(acts, t)
             ops.counter_add(self.ctr_action, 1)
             env.step(buf.action[t], obs=buf.obs[t + 1], reward=buf.reward[t], terminated=self.term, truncated=self.trunc,
                      want_next_obs=False, done=buf.done[t])
@@ -305,9 +326,7 @@ class PPOTrainer:
         ops.slice_i32(self.idx_mb, self.perm, self.ctr_mb)
         ops.counter_add(self.ctr_mb, 1)
         net.forward(obs_flat, acts, M, row_index=self.idx_mb)
-        ops.ppo_loss(acts.lv[:, :A], acts.lv[:, A:A + 1], buf.action.view(-1), buf.log_prob.view(-1), buf.adv.view(-1),
-                     buf.ret.view(-1), self.loss_cfg, row_index=self.idx_mb, dlogits=acts.dlv[:, :A],
-                     dvalue=acts.dlv[:, A:A + 1], metrics=self.metrics)
+        self._loss_step(acts)
         net.backward(obs_flat, acts, M, row_index=self.idx_mb)
 
     def _opt_body(self):
@@ -454,7 +473,7 @@ class PPOTrainer:
         x = torch.as_tensor(np.asarray(state, dtype=np.float32), device=self.device).reshape(1, -1)
         acts = getattr(self, "_acts_one", None)
         if acts is None:
-            acts = self._acts_one = _Acts(1, self.cfg.hidden_dim, self.env.n_actions, self.device, backward=False)
+            acts = self._acts_one = self._make_acts(1, backward=False)
         A = self.env.n_actions
         self.net.forward(x, acts, 1)
         a, lp, _ = ops.sample_categorical(acts.lv[:, :A], seed=self.seed, first_id=1 << 40, draw_base=self.ctr_action,
@@ -466,7 +485,7 @@ class PPOTrainer:
         """Deterministic (argmax) episodes, one env copy per episode, stepped in lockstep (ref eval :368-399)."""
         print(f"\nEvaluating for {num_episodes} episodes...")
         env = ops.VecEnv(self.cfg.env_name, num_episodes, seed=self.seed + 12345, first_env_id=1 << 32)
-        acts = _Acts(num_episodes, self.cfg.hidden_dim, env.n_actions, self.device, backward=False)
+        acts = self._make_acts(num_episodes, backward=False, n_actions=env.n_actions)
         A = env.n_actions
         obs = env.reset()
         action = torch.zeros(num_episodes, device=self.device, dtype=i32)

@@ -40,6 +40,7 @@ SOURCES = {
     "optim.cu": [],
     "replay.cu": [],
     "qlearn.cu": [],
+    "mhc.cu": [],
 }
 
 

@@ -30,6 +30,7 @@ __global__ void ppo_loss_kernel(const float* __restrict__ logits, int ldl, const
     __shared__ float scratch[32];
     const int i = blockIdx.x * blockDim.x + threadIdx.x;
     const float invB = 1.0f / (float)B;
+    const float ent_coef = cfg.d_entropy_coef ? *cfg.d_entropy_coef : cfg.entropy_coef;
     float m_pol = 0.f, m_val = 0.f, m_ent = 0.f, m_clip = 0.f, m_kl = 0.f, m_erc = 0.f;
     if (i < B) {
         const int r = row_index ? row_index[i] : i;
@@ -93,7 +94,7 @@ __global__ void ppo_loss_kernel(const float* __restrict__ logits, int ldl, const
         }
         // gradients: L = -obj*mask/B + vc*mask*vterm/B - ec*mask*H/B
         const float dL_dlp = -(g * ratio) * mask * invB;
-        const float dL_dH = -cfg.entropy_coef * mask * invB;
+        const float dL_dH = -ent_coef * mask * invB;
         for (int j = 0; j < A; ++j) {
             const float dlp = (j == a ? 1.0f : 0.0f) - p[j];
             const float dH = -p[j] * (ln[j] + H);
@@ -120,7 +121,7 @@ __global__ void ppo_loss_kernel(const float* __restrict__ logits, int ldl, const
         atomicAdd(&metrics[3], m_clip);
         atomicAdd(&metrics[4], m_kl);
         atomicAdd(&metrics[5], m_erc);
-        atomicAdd(&metrics[6], m_pol + m_val - cfg.entropy_coef * m_ent);
+        atomicAdd(&metrics[6], m_pol + m_val - ent_coef * m_ent);
         if (blockIdx.x == 0) atomicAdd(&metrics[7], 1.0f);
     }
 }

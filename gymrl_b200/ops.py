@@ -293,3 +293,53 @@ def slice_i32(dst, src, block_index):
     """dst[:] = src[block*n:(block+1)*n] with `block` a device int32 scalar."""
     check(load().gymrl_slice_i32(ptr(dst, i32), ptr(src, i32), dst.numel(), ptr(block_index, i32), stream_ptr()))
     return dst
+
+
+# ------------------------------------------------------------------------------------------------
+# ppo_full network glue: mHC stages, RMSNorm (+SiLU)   (csrc/mhc.cu)
+# ------------------------------------------------------------------------------------------------
+def mhc_workspace_bytes(D, head_width=256, head_groups=2) -> int:
+    return int(load().gymrl_mhc_workspace_bytes(int(D), int(head_width), int(head_groups)))
+
+
+def mhc_stage_forward(h_prev, *, D, row_stride, branch_stride, M, z_prev=None, coef_prev=None, h_cur=None, params=None,
+                      coef_cur=None, h_pre=None, final_weight=None, feat=None, sk_iters=10, eps=1e-6):
+    """params = (g [2D], w [2D, 8], alpha [3], beta [8]) of the NEXT stage (None: no next stage)."""
+    g = w = al = be = None
+    if params is not None:
+        g, w, al, be = params
+    check(load().gymrl_mhc_stage_forward(ptr(h_prev, f32), int(row_stride), int(branch_stride), ptr(z_prev, f32), ptr(coef_prev, f32),
+                                         ptr(h_cur, f32), ptr(g, f32), ptr(w, f32), ptr(al, f32), ptr(be, f32), ptr(coef_cur, f32),
+                                         ptr(h_pre, f32), ptr(final_weight, f32), ptr(feat, f32), int(M), int(D), int(sk_iters),
+                                         float(eps), stream_ptr()))
+
+
+def mhc_stage_backward_a(h, z, dh_next, params, *, D, row_stride, branch_stride, M, dz, dh_partial, scratch, sk_iters=10):
+    g, w, al, be = params
+    check(load().gymrl_mhc_stage_backward_a(ptr(h, f32), int(row_stride), int(branch_stride), ptr(z, f32), ptr(dh_next, f32),
+                                            ptr(g, f32), ptr(w, f32), ptr(al, f32), ptr(be, f32), ptr(dz, f32), ptr(dh_partial, f32),
+                                            ptr(scratch, f32), int(M), int(D), int(sk_iters), stream_ptr()))
+
+
+def mhc_stage_backward_b(h, dh_pre, scratch, dh_partial, params, grads, *, D, row_stride, branch_stride, M, workspace, dh=None,
+                         dx0=None, accumulate=False):
+    """grads = (dg, dw, dalpha, dbeta) views into the flat gradient buffer."""
+    g, w, al, _ = params
+    dg, dw, dal, dbe = grads
+    check(load().gymrl_mhc_stage_backward_b(ptr(h, f32), int(row_stride), int(branch_stride), ptr(dh_pre, f32), ptr(scratch, f32),
+                                            ptr(dh_partial, f32), ptr(dh, f32), ptr(dx0, f32), ptr(g, f32), ptr(w, f32), ptr(al, f32),
+                                            ptr(dg, f32), ptr(dw, f32), ptr(dal, f32), ptr(dbe, f32), workspace.data_ptr(),
+                                            workspace.numel() * workspace.element_size(), int(accumulate), int(M), int(D), stream_ptr()))
+
+
+def rmsnorm_forward(x, weight, y, *, M, W, groups=1, sum2=False, silu=False, eps=1e-6):
+    check(load().gymrl_rmsnorm_forward(ptr(x, f32), _ld(x), int(sum2), int(silu), ptr(weight, f32), ptr(y, f32), _ld(y), int(M), int(W),
+                                       int(groups), float(eps), stream_ptr()))
+    return y
+
+
+def rmsnorm_backward(x, weight, dy, dx, dweight, *, M, W, workspace, groups=1, sum2=False, silu=False, eps=1e-6, accumulate=False):
+    check(load().gymrl_rmsnorm_backward(ptr(x, f32), _ld(x), int(sum2), int(silu), ptr(weight, f32), ptr(dy, f32), _ld(dy), ptr(dx, f32),
+                                        _ld(dx), ptr(dweight, f32), workspace.data_ptr(), workspace.numel() * workspace.element_size(),
+                                        int(accumulate), int(M), int(W), int(groups), float(eps), stream_ptr()))
+    return dx, dweight

@@ -165,6 +165,8 @@ typedef struct gymrl_ppo_cfg {
     float erc_high;
     float vclip_eps_min; /* value-clip window (VALUE_CLIP flag)                        */
     float vclip_eps_max;
+    const float* d_entropy_coef; /* nullable device scalar overriding entropy_coef: lets a captured CUDA graph
+                                  * follow ppo_full's per-update entropy anneal (:664-666)      */
 } gymrl_ppo_cfg;
 
 /* metrics (device float[8], accumulated with += so zero before the first minibatch):
@@ -354,6 +356,44 @@ int gymrl_noisy_compose(const float* d_w_mu, const float* d_w_sigma, const float
 int gymrl_noisy_backward(const float* d_dw, const float* d_db, const float* d_eps_in, const float* d_eps_out,
                          float* d_dw_mu, float* d_dw_sigma, float* d_db_mu, float* d_db_sigma, int N, int K,
                          int accumulate, void* stream);
+
+/* ------------------------------------------------------------------------------------------------
+ * ppo_full network glue: manifold hyper-connection stages, RMSNorm, SiLU.
+ * algorithms/ppo_full_lunarlander.py: sinkhorn_knopp_batched :76-103, ManifoldHyperConnectionFuse :106-194,
+ * MHCBlock :197-229, MHCBackbone :232-267, RMSNorm :273-284, MLP :287-318.  mhc_rate n = 2, mhc_dim D in {128, 256}.
+ * Rows are [2][D] float32 (row stride / branch stride given for inputs so that the backbone input x0 [M][D] can be
+ * read as both branches: stride D / 0).  The Linear layers between the stages are gymrl_linear_* with ACT_NONE.
+ * ---------------------------------------------------------------------------------------------- */
+/* Bytes of workspace the *_backward* calls below need (per-block parameter-gradient partials). */
+size_t gymrl_mhc_workspace_bytes(int D, int head_width, int head_groups);
+/* One fused row-wise pass between two GEMMs of the backbone forward:
+ *   (z_prev != NULL)  h_cur = depth_connection(prev stage) = post_i silu(z_prev) + sum_j P_ij h_prev_j, stored [M][2][D];
+ *                     otherwise the row is h_prev itself (not stored);
+ *   (g != NULL)       mapping() of the next stage on that row: coef_cur [M][8] = {pre0 pre1 post0 post1 P00 P01 P10 P11},
+ *                     h_pre [M][D] = sum_i pre_i h_i (the next GEMM's input);
+ *   (final_weight)    feat [M][D] = RMSNorm(h_0 + h_1) * final_weight  (MHCBackbone.forward :263-267). */
+int gymrl_mhc_stage_forward(const float* d_h_prev, int prev_row_stride, int prev_branch_stride, const float* d_z_prev,
+                            const float* d_coef_prev, float* d_h_cur, const float* d_g, const float* d_w, const float* d_alpha,
+                            const float* d_beta, float* d_coef_cur, float* d_h_pre, const float* d_final_weight, float* d_feat,
+                            int M, int D, int sk_iters, float eps, void* stream);
+/* Backward of one stage, split around its GEMM backward.  A: from d_dh_next = dL/d(stage output) [M][2][D] and the saved
+ * stage input h and GEMM output z: dz [M][D] (the GEMM's upstream gradient), dh_partial [M][2][D], scratch [M][24]. */
+int gymrl_mhc_stage_backward_a(const float* d_h, int row_stride, int branch_stride, const float* d_z, const float* d_dh_next,
+                               const float* d_g, const float* d_w, const float* d_alpha, const float* d_beta, float* d_dz,
+                               float* d_dh_partial, float* d_scratch, int M, int D, int sk_iters, void* stream);
+/* B: with d_dh_pre = dz @ W [M][D]: the full input gradient (d_dh [M][2][D], or its branch sum d_dx0 [M][D] when that is
+ * non-NULL) and the parameter gradients of mhc.norm.weight (dg [2D]), mhc.w (dw [2D][8]), alpha [3], beta [8]. */
+int gymrl_mhc_stage_backward_b(const float* d_h, int row_stride, int branch_stride, const float* d_dh_pre, const float* d_scratch,
+                               const float* d_dh_partial, float* d_dh, float* d_dx0, const float* d_g, const float* d_w,
+                               const float* d_alpha, float* d_dg, float* d_dw, float* d_dalpha, float* d_dbeta, void* d_workspace,
+                               size_t workspace_bytes, int accumulate, int M, int D, void* stream);
+/* y = a * rsqrt(mean(a^2) + eps) * weight per group of width W (128 | 256), `groups` groups per row;
+ * a = silu(x) (silu = 1: the MLP heads' Linear -> SiLU -> RMSNorm, :305-308) | x | x[0:W] + x[W:2W] (sum2 = 1). */
+int gymrl_rmsnorm_forward(const float* d_x, int ldx, int sum2, int silu, const float* d_weight, float* d_y, int ldy, int M, int W,
+                          int groups, float eps, void* stream);
+int gymrl_rmsnorm_backward(const float* d_x, int ldx, int sum2, int silu, const float* d_weight, const float* d_dy, int lddy,
+                           float* d_dx, int lddx, float* d_dweight, void* d_workspace, size_t workspace_bytes, int accumulate,
+                           int M, int W, int groups, float eps, void* stream);
 
 #ifdef __cplusplus
 }

@@ -85,3 +85,20 @@ def test_ppo_update_gradients_via_oracle_forward(golden):
     r = A.ppo_loss_grad(logits, value, g["action"], g["logp_old"], adv, ret)
     for k in ("policy_loss", "value_loss", "entropy", "clip_frac", "approx_kl"):
         np.testing.assert_allclose(r[k], g["m1_" + k], rtol=2e-4, atol=2e-6)
+
+
+def test_mhc_oracle_matches_reference_module(golden):
+    """oracle/mhc_np.py (float64) vs the reference ActorCritic's own forward and torch-autograd gradients
+    (algorithms/ppo_full_lunarlander.py:76-412, fixture from oracle/make_golden_mhc.py)."""
+    from oracle.mhc_np import ActorCriticMHC
+    g = golden("mhc_actor_critic.npz")
+    sd = {k[2:]: g[k] for k in g.files if k.startswith("p:")}
+    assert sum(v.size for v in sd.values()) == 144433        # SURVEY §8 a17: ppo_full parameter count
+    net = ActorCriticMHC(sd, int(g["rate"]), int(g["layers"]), int(g["sk_it"]))
+    logits, value = net.forward(g["x"])
+    np.testing.assert_allclose(logits, g["logits"], rtol=0, atol=2e-6)
+    np.testing.assert_allclose(value, g["value"], rtol=0, atol=2e-6)
+    grads = net.backward(g["Gl"], g["Gv"])
+    for k in sd:
+        ref = g["g:" + k]
+        assert np.abs(grads[k].reshape(ref.shape) - ref).max() <= 2e-5 * max(np.abs(ref).max(), 1e-6), k
