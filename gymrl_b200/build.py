@@ -41,6 +41,7 @@ SOURCES = {
     "replay.cu": [],
     "qlearn.cu": [],
     "mhc.cu": [],
+    "normalize.cu": ["-fmad=false"],
 }
 
 

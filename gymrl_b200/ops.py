@@ -343,3 +343,29 @@ def rmsnorm_backward(x, weight, dy, dx, dweight, *, M, W, workspace, groups=1, s
                                         _ld(dx), ptr(dweight, f32), workspace.data_ptr(), workspace.numel() * workspace.element_size(),
                                         int(accumulate), int(M), int(W), int(groups), float(eps), stream_ptr()))
     return dx, dweight
+
+
+# ------------------------------------------------------------------------------------------------
+# running normalisation (utils path, csrc/normalize.cu)
+# ------------------------------------------------------------------------------------------------
+def running_stats_update(x, state):
+    """x [N, D] float32, state float64 [1 + 3 D]."""
+    assert x.is_contiguous()
+    N, D = x.shape
+    check(load().gymrl_running_stats_update(ptr(x, f32), N, D, ptr(state, f64), stream_ptr()))
+
+
+def running_normalize(x, state, center=True, out=None):
+    assert x.is_contiguous()
+    N, D = x.shape
+    out = torch.empty_like(x) if out is None else out
+    check(load().gymrl_running_normalize(ptr(x, f32), ptr(out, f32), N, D, ptr(state, f64), int(center), stream_ptr()))
+    return out
+
+
+def reward_scaling(r, R, state, gamma, reset=None, out=None):
+    N = r.numel()
+    out = torch.empty_like(r) if out is None else out
+    check(load().gymrl_reward_scaling(ptr(r, f32), ptr(out, f32), ptr(R, f64), ptr(reset, u8), float(gamma), ptr(state, f64), N,
+                                      stream_ptr()))
+    return out

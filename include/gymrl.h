@@ -395,6 +395,21 @@ int gymrl_rmsnorm_backward(const float* d_x, int ldx, int sum2, int silu, const 
                            float* d_dx, int lddx, float* d_dweight, void* d_workspace, size_t workspace_bytes, int accumulate,
                            int M, int W, int groups, float eps, void* stream);
 
+/* ------------------------------------------------------------------------------------------------
+ * Running normalisation of the utils path: utils/normalization.py RunningMeanStd :4-22,
+ * Normalization :25-35, RewardScaling :38-52 (applied per env step by utils/runner.py:112,125-126).
+ * d_state = float64 [1 + 3 D] {n, mean[D], S[D], std[D]} (zero-initialised).  A call feeds the N rows of x in env
+ * order: for N <= 32 with the reference's exact rule and precisions (first-sample quirk mean = std = x included),
+ * so N = 1 is the reference; for larger N the batch moments are merged in float64.
+ * ---------------------------------------------------------------------------------------------- */
+int gymrl_running_stats_update(const float* d_x, int N, int D, double* d_state, void* stream);
+/* y = (x - mean) / (std + 1e-8)  (center = 1, Normalization.__call__) or x / (std + 1e-8) (center = 0). */
+int gymrl_running_normalize(const float* d_x, float* d_y, int N, int D, const double* d_state, int center, void* stream);
+/* RewardScaling.__call__: R_i = gamma R_i + r_i (R_i zeroed first where d_reset[i], = RewardScaling.reset at an
+ * episode start), statistic (d_state float64[4], D = 1) updated with the N values of R, out_i = r_i / (std + 1e-8). */
+int gymrl_reward_scaling(const float* d_r, float* d_out, double* d_R, const uint8_t* d_reset, double gamma, double* d_state,
+                         int N, void* stream);
+
 #ifdef __cplusplus
 }
 #endif

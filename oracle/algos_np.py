@@ -151,3 +151,43 @@ def mlp_actor_critic_forward(sd, x):
     a = np.tanh(h @ sd["actor.0.weight"].T.astype(np.float64) + sd["actor.0.bias"])
     c = np.tanh(h @ sd["critic.0.weight"].T.astype(np.float64) + sd["critic.0.bias"])
     return a @ sd["actor.2.weight"].T.astype(np.float64) + sd["actor.2.bias"], (c @ sd["critic.2.weight"].T.astype(np.float64) + sd["critic.2.bias"])[:, 0]
+
+
+# ---- running normalisation (utils/normalization.py:4-52) -------------------------------------------------------------
+class RunningMeanStdNP:
+    """Same update rule and precisions as the reference: mean float32, S float64, std float64 (float32 = x at n == 1)."""
+
+    def __init__(self, D):
+        self.n, self.mean, self.S, self.std = 0, np.zeros(D), np.zeros(D), np.zeros(D)
+
+    def update(self, x):
+        x = np.array(x, dtype=np.float32)
+        self.n += 1
+        if self.n == 1:
+            self.mean, self.std = x, x
+        else:
+            old = self.mean.copy()
+            self.mean = (old + (x - old) / np.float32(self.n)).astype(np.float32)
+            self.S = self.S + ((x - old) * (x - self.mean)).astype(np.float64)
+            self.std = np.sqrt(self.S / self.n)
+
+
+def normalize_stream(x):
+    """Normalization.__call__(x_t) for t = 0.. (update=True) -> float32 rows."""
+    rm = RunningMeanStdNP(x.shape[1])
+    out = np.zeros_like(x, dtype=np.float32)
+    for t in range(len(x)):
+        rm.update(x[t])
+        out[t] = ((x[t] - rm.mean).astype(np.float64) / (np.asarray(rm.std, np.float64) + 1e-8)).astype(np.float32)
+    return out, rm
+
+
+def reward_scaling_stream(r, reset_at, gamma):
+    rm, R, out = RunningMeanStdNP(1), np.zeros(1), np.zeros(len(r), np.float32)
+    for t in range(len(r)):
+        if reset_at[t]:
+            R = np.zeros(1)
+        R = gamma * R + r[t]
+        rm.update(R)
+        out[t] = np.float32(r[t] / (float(np.asarray(rm.std, np.float64)[0]) + 1e-8))
+    return out

@@ -1,0 +1,183 @@
+"""GPU parity of the utils path: device Normalization / RewardScaling vs the
+reference classes' outputs (tests/golden/normalization.npz), utils.buffer vs the reference's compute_advantage golden,
+the Gymnasium-shaped env view vs the CPU oracle env, and the reference's runner loop driving an agent end to end.
+"""
+import types
+
+import numpy as np
+import pytest
+import torch
+
+pytestmark = pytest.mark.gpu
+from oracle import algos_np as A  # noqa: E402
+from oracle import envs_np  # noqa: E402
+
+
+def test_normalization_matches_reference_stream(golden):
+    from gymrl_b200.utils.normalization import Normalization
+    g = golden("normalization.npz")
+    norm = Normalization(shape=(8,))
+    ys = np.stack([norm(g["x"][t]) for t in range(len(g["x"]))])          # one observation per call, like utils/runner.py:112
+    np.testing.assert_array_equal(ys, g["y"].astype(np.float32))          # same operations, same precisions: bit-exact
+    np.testing.assert_array_equal(norm.running_ms.mean.astype(np.float64), g["mean"])
+    np.testing.assert_allclose(norm.running_ms.std, g["std"], rtol=1e-15)
+    np.testing.assert_allclose(norm.running_ms.S, g["S"], rtol=1e-15)
+    assert norm.running_ms.n == int(g["n"])
+    np.testing.assert_array_equal(norm(g["x"][0], update=False), g["y_eval"].astype(np.float32))
+    assert norm.running_ms.n == int(g["n"])                               # update=False leaves the statistic alone
+
+
+def test_reward_scaling_matches_reference_stream(golden):
+    from gymrl_b200.utils.normalization import RewardScaling
+    g = golden("normalization.npz")
+    rs = RewardScaling(shape=1, gamma=float(g["gamma"]))
+    out = []
+    for t in range(len(g["r"])):
+        if g["reset_at"][t]:
+            rs.reset()
+        out.append(rs(float(g["r"][t]))[0])
+    np.testing.assert_allclose(np.array(out), g["r_scaled"], rtol=2e-6)   # reward is float64 in the reference, float32 on the device
+
+
+def test_normalization_batched_merge():
+    """N > 32 rows per call: merged batch moments equal the float64 moments of everything seen so far."""
+    from gymrl_b200.utils.normalization import Normalization
+    rng = np.random.default_rng(1)
+    x = (rng.standard_normal((5, 4096, 8)) * 3 + 1).astype(np.float32)
+    norm = Normalization(shape=(8,))
+    for t in range(5):
+        y = norm(torch.as_tensor(x[t]).cuda())
+    allx = x.reshape(-1, 8).astype(np.float64)
+    np.testing.assert_allclose(norm.running_ms.mean, allx.mean(0), rtol=1e-6)
+    np.testing.assert_allclose(norm.running_ms.std, allx.std(0), rtol=1e-9)
+    np.testing.assert_allclose(y.cpu().numpy(), (x[4] - allx.mean(0)) / (allx.std(0) + 1e-8), rtol=1e-4, atol=1e-5)
+
+
+def _cfg(**kw):
+    c = types.SimpleNamespace(gamma=0.99, lamda=0.95, device=torch.device("cuda"), batch_size=64, memory_capacity=1000, seed=3)
+    c.__dict__.update(kw)
+    return c
+
+
+def test_on_policy_buffer_matches_reference(golden):
+    """store() the reference's 8-tuples one env step at a time, sample(): normalised advantage (ddof = 1) and v_target equal the
+    reference ReplayBuffer_on_policy.compute_advantage outputs (utils/buffer.py:21-35)."""
+    from gymrl_b200.utils.buffer import ReplayBuffer_on_policy
+    g = golden("gae_utils.npz")
+    T = len(g["reward"])
+    buf = ReplayBuffer_on_policy(_cfg(gamma=float(g["gamma"]), lamda=float(g["lamda"])))
+    rng = np.random.default_rng(0)
+    states = rng.standard_normal((T, 8)).astype(np.float32)
+    for t in range(T):
+        buf.store((states[t], int(t % 4), float(g["reward"][t, 0]), bool(g["done"][t, 0]), bool(g["dw"][t, 0]), -0.5,
+                   float(g["value"][t, 0]), float(g["next_value"][t, 0])))
+    assert buf.size() == T
+    s, a, logp, adv, v_target = buf.sample()
+    assert s.shape == (T, 8) and a.shape == (T, 1) and a.dtype == torch.long and adv.shape == (T, 1)
+    np.testing.assert_array_equal(v_target.cpu().numpy(), g["v_target"])                 # float32 recurrence: bit-exact
+    np.testing.assert_allclose(adv.cpu().numpy(), g["adv_normalized"], rtol=2e-5, atol=2e-6)
+    with pytest.raises(AssertionError):
+        buf.store((states[0], 0, 0.0, False, False, 0.0, 0.0, 0.0))                      # store after sample (ref :11)
+    buf.clear()
+    assert buf.size() == 0
+
+
+def test_off_policy_buffer_semantics():
+    from gymrl_b200.utils.buffer import ReplayBuffer_off_policy
+    buf = ReplayBuffer_off_policy(_cfg(memory_capacity=50, batch_size=16))
+    for i in range(10):
+        buf.store((np.full(4, i, np.float32), i % 2, float(i), np.full(4, i + 1, np.float32), i == 9))
+    assert buf.size() == 10
+    s, a, r, s2, d = buf.sample()
+    assert s.shape == (10, 4) and r.shape == (10,)                      # min(batch_size, size) (ref :122)
+    assert sorted(r.cpu().tolist()) == list(map(float, range(10)))      # without replacement (ref :124)
+    np.testing.assert_array_equal(s2.cpu().numpy()[:, 0], r.cpu().numpy() + 1)
+    for i in range(10, 120):
+        buf.store((np.full(4, i, np.float32), 0, float(i), np.full(4, i + 1, np.float32), False))
+    assert buf.size() == 50 and buf.is_full
+    s, a, r, s2, d = buf.sample()
+    rr = r.cpu().numpy()
+    assert len(rr) == 16 and len(set(rr.tolist())) == 16 and rr.min() >= 70   # the ring kept the newest 50
+
+
+def test_gym_view_matches_oracle_env():
+    from gymrl_b200.utils import env as E
+    env = E.make("CartPole-v1")
+    obs, info = env.reset(seed=123)
+    ora = envs_np.CartPoleVec(1, seed=123)
+    o0 = ora.reset()
+    np.testing.assert_allclose(obs, o0[0], rtol=1e-6, atol=1e-7)
+    assert env.observation_space.shape == (4,) and env.action_space.n == 2 and env.spec.max_episode_steps == 500
+    rng = np.random.default_rng(0)
+    steps = 0
+    for _ in range(200):
+        a = int(rng.integers(2))
+        obs, r, term, trunc, _ = env.step(a)
+        cur, nobs, rr, te, tr = ora.step(np.array([a]))
+        np.testing.assert_allclose(obs, nobs[0], rtol=1e-5, atol=1e-6)     # gymnasium returns the terminal observation itself
+        assert r == float(rr[0]) and term == bool(te[0]) and trunc == bool(tr[0])
+        steps += 1
+        if term or trunc:
+            obs, _ = env.reset()                                             # unseeded: the next episode of the same stream
+            np.testing.assert_allclose(obs, cur[0], rtol=1e-5, atol=1e-6)
+    env.close()
+    p = E.make("Pendulum-v1")
+    o, _ = p.reset(seed=1)
+    assert o.shape == (3,) and p.action_space.shape == (1,) and float(p.action_space.high[0]) == 2.0
+    o, r, te, tr, _ = p.step(np.array([0.5], np.float32))
+    assert o.shape == (3,) and r <= 0.0 and not te
+    p.close()
+
+
+def test_runner_train_loop_drives_an_agent(tmp_path, monkeypatch):
+    """utils.runner.BenchMark.train with a minimal on-policy agent (the agent protocol of SURVEY §1): the loop attaches
+    the device normalisers, infers on_policy from the buffer class (q17), calls update() whenever the buffer holds
+    batch_size transitions, evaluates and saves a checkpoint in the reference's layout."""
+    monkeypatch.chdir(tmp_path)
+    from gymrl_b200.utils import runner as R
+    from gymrl_b200.utils.buffer import ReplayBuffer_on_policy
+    from gymrl_b200.utils.model import MLP, ModelLoader
+
+    class Config(R.BasicConfig):
+        def __init__(self):
+            super().__init__()
+            self.env_name, self.algo_name = "CartPole-v1", "TestPPO"
+            self.train_eps, self.eval_freq, self.save_freq, self.batch_size = 6, 3, 3, 32
+
+    class Agent(ModelLoader):
+        def __init__(self, cfg):
+            super().__init__(cfg)
+            self.net = MLP([cfg.n_states, 16, cfg.n_actions + 1]).to(cfg.device)
+            self.memory = ReplayBuffer_on_policy(cfg)
+            self.learn_step, self.updates = 0, []
+
+        @torch.no_grad()
+        def choose_action(self, state):
+            out = self.net(torch.as_tensor(state, dtype=torch.float32, device=self.cfg.device).unsqueeze(0))[0]
+            dist = torch.distributions.Categorical(logits=out[:-1])
+            a = dist.sample()
+            return int(a), float(dist.log_prob(a)), float(out[-1])
+
+        @torch.no_grad()
+        def evaluate(self, state):
+            out = self.net(torch.as_tensor(state, dtype=torch.float32, device=self.cfg.device).unsqueeze(0))[0]
+            return int(out[:-1].argmax())
+
+        def update(self):
+            s, a, logp, adv, v_target = self.memory.sample()
+            assert s.shape[0] == a.shape[0] == adv.shape[0] >= self.cfg.batch_size and torch.isfinite(adv).all()
+            self.updates.append(s.shape[0])
+            self.memory.clear()
+            self.learn_step += 1
+            return {"adv_mean": float(adv.mean()), "nan_metric": float("nan")}
+
+    agents = []
+    R.BenchMark.train(lambda cfg: agents.append(Agent(cfg)) or agents[-1], Config)
+    ag = agents[0]
+    assert ag.cfg.on_policy is True and ag.cfg.use_rnn is False and ag.cfg.n_states == 4 and ag.cfg.n_actions == 2
+    assert len(ag.updates) >= 1 and ag.state_norm.running_ms.n > 32
+    ckpt = torch.load(ag.cfg.save_path, weights_only=False)
+    assert "net_state_dict" in ckpt and "state_norm_state_dict" in ckpt and ckpt["learn_step"] == ag.learn_step
+    ag.learn_step = -1
+    ag.load_model()
+    assert ag.learn_step == ckpt["learn_step"]

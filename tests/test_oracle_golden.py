@@ -102,3 +102,14 @@ def test_mhc_oracle_matches_reference_module(golden):
     for k in sd:
         ref = g["g:" + k]
         assert np.abs(grads[k].reshape(ref.shape) - ref).max() <= 2e-5 * max(np.abs(ref).max(), 1e-6), k
+
+
+def test_normalization_oracle_matches_reference(golden):
+    """oracle restatement of utils/normalization.py vs the reference classes' own outputs (oracle/make_golden_utils.py)."""
+    g = golden("normalization.npz")
+    y, rm = A.normalize_stream(g["x"])
+    np.testing.assert_allclose(y, g["y"].astype(np.float32), rtol=1e-6, atol=1e-7)
+    np.testing.assert_allclose(rm.mean, g["mean"], rtol=0, atol=0)
+    np.testing.assert_allclose(rm.std, g["std"], rtol=1e-15)
+    rs = A.reward_scaling_stream(g["r"], g["reset_at"], float(g["gamma"]))
+    np.testing.assert_allclose(rs, g["r_scaled"].astype(np.float32), rtol=2e-6)
