@@ -251,6 +251,38 @@ def gen_td3():
     np.savez(OUT / "td3_update.npz", **out)
 
 
+def gen_ddpg():
+    """DDPGTrainer.update (algorithms/ddpg_pendulum.py:154-195) x2."""
+    rl.install_gymnasium_stub(make=lambda name, **k: rl.FakeEnv(3, act_dim=1, bound=2.0, max_steps=200))
+    m = rl.load("algorithms/ddpg_pendulum.py")
+    torch.manual_seed(18)
+    cfg = m.Config(); cfg.device = "cpu"; cfg.batch_size = 256; cfg.hidden_dim = 64
+    import io, contextlib
+    with contextlib.redirect_stdout(io.StringIO()):
+        t = m.DDPGTrainer(cfg)
+    with torch.no_grad():
+        for p in list(t.critic_target.parameters()) + list(t.actor_target.parameters()):
+            p.add_(0.02 * torch.randn_like(p))
+    rng = np.random.default_rng(19)
+    B = cfg.batch_size
+    out = dict(gamma=cfg.gamma, tau=cfg.tau)
+    out.update(_sd(t.actor, "a0_")); out.update(_sd(t.actor_target, "at0_")); out.update(_sd(t.critic, "c0_")); out.update(_sd(t.critic_target, "ct0_"))
+    batches = []
+    for k in range(2):
+        s = rng.standard_normal((B, 3)).astype(np.float32); s2 = rng.standard_normal((B, 3)).astype(np.float32)
+        a = rng.uniform(-2, 2, (B, 1)).astype(np.float32)
+        r = (-rng.random(B) * 16).astype(np.float64); d = rng.random(B) < 0.05
+        batches.append((s, a, r, s2, d))
+        out.update({f"b{k}_s": s, f"b{k}_a": a, f"b{k}_r": r.astype(np.float32), f"b{k}_s2": s2, f"b{k}_d": d.astype(np.uint8)})
+    bi = iter(batches)
+    t.memory.sample = lambda bs: next(bi)
+    t.memory.buffer = deque([0] * B)
+    l0 = t.update(); l1 = t.update()
+    out.update(_sd(t.actor, "a2_")); out.update(_sd(t.actor_target, "at2_")); out.update(_sd(t.critic, "c2_")); out.update(_sd(t.critic_target, "ct2_"))
+    out.update(losses=np.array([l0[0], l0[1], l1[0], l1[1]], dtype=np.float64))
+    np.savez(OUT / "ddpg_update.npz", **out)
+
+
 def main():
     torch.set_num_threads(1)
     gen_sumtree()
@@ -259,3 +291,4 @@ def main():
     gen_rainbow()
     gen_sac()
     gen_td3()
+    gen_ddpg()

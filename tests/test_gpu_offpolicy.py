@@ -217,11 +217,33 @@ def test_td3_update_matches_reference(golden):
     _cmp(t.actor_target, g, "at2_", rtol=3e-5, atol=3e-7)
 
 
+# ------------------------------------------------------------------------------------------------ DDPG
+def test_ddpg_update_matches_reference(golden):
+    """Two DDPGTrainer.update() calls of the reference (algorithms/ddpg_pendulum.py:154-195) on the same batches."""
+    from gymrl_b200.algorithms import ddpg_pendulum as Dm
+    g = golden("ddpg_update.npz")
+    cfg = Dm.Config(); cfg.batch_size, cfg.hidden_dim, cfg.seed, cfg.memory_capacity = 256, 64, 0, 1024
+    t = Dm.DDPGTrainer(cfg)
+    for mod, fp, pre in ((t.actor, t.fp_a, "a0_"), (t.actor_target, t.fp_at, "at0_"), (t.critic, t.fp_c, "c0_"), (t.critic_target, t.fp_ct, "ct0_")):
+        _load(mod, g, pre); fp.refresh_views()
+    out = []
+    for k in range(2):
+        _fill_ring(t.memory, g[f"b{k}_s"], g[f"b{k}_a"], g[f"b{k}_r"], g[f"b{k}_s2"], g[f"b{k}_d"])
+        idx = torch.arange(256 * k, 256 * (k + 1), device="cuda", dtype=i32)
+        al, cl = t.update(idx)
+        out += [float(al[0]), 0.5 * float(cl[0])]
+    np.testing.assert_allclose(out, g["losses"], rtol=5e-4, atol=5e-5)
+    _cmp(t.critic, g, "c2_", rtol=3e-4, atol=3e-6)
+    _cmp(t.actor, g, "a2_", rtol=3e-4, atol=3e-6)
+    _cmp(t.critic_target, g, "ct2_", rtol=3e-5, atol=3e-7)
+    _cmp(t.actor_target, g, "at2_", rtol=3e-5, atol=3e-7)
+
+
 # ------------------------------------------------------------------------------------------------ smoke at BASELINE sizes
-@pytest.mark.parametrize("algo", ["dqn", "rainbow", "sac", "td3"])
+@pytest.mark.parametrize("algo", ["dqn", "rainbow", "sac", "td3", "ddpg"])
 def test_offpolicy_trainers_run_vectorised(algo):
     import importlib
-    name = {"dqn": "dqn_cartpole", "rainbow": "rainbow_dqn_cartpole", "sac": "sac_pendulum", "td3": "td3_pendulum"}[algo]
+    name = {"dqn": "dqn_cartpole", "rainbow": "rainbow_dqn_cartpole", "sac": "sac_pendulum", "td3": "td3_pendulum", "ddpg": "ddpg_pendulum"}[algo]
     M = importlib.import_module(f"gymrl_b200.algorithms.{name}")
     cfg = M.Config()
     cfg.num_envs, cfg.seed, cfg.max_locksteps = 1024, 3, 30
