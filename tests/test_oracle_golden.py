@@ -113,3 +113,15 @@ def test_normalization_oracle_matches_reference(golden):
     np.testing.assert_allclose(rm.std, g["std"], rtol=1e-15)
     rs = A.reward_scaling_stream(g["r"], g["reset_at"], float(g["gamma"]))
     np.testing.assert_allclose(rs, g["r_scaled"].astype(np.float32), rtol=2e-6)
+
+
+def test_sqrt_threshold():
+    """csrc/env_lunar.cu replaces `sqrtf(x) <= B2_LINEAR_SLOP` in the joint position solve by `x <= 0x1.a36e3p-16f`:
+    exact for every float32 x (checked on the 2^17 floats around the boundary and on random magnitudes)."""
+    slop, T = np.float32(0.005), np.float32(float.fromhex("0x1.a36e3p-16"))
+    base = T.view(np.uint32)
+    xs = np.arange(int(base) - 65536, int(base) + 65536, dtype=np.uint32).view(np.float32)
+    assert np.array_equal(np.sqrt(xs) <= slop, xs <= T)
+    rng = np.random.default_rng(0)
+    xr = np.exp(rng.uniform(-30, 5, 200000)).astype(np.float32)
+    assert np.array_equal(np.sqrt(xr) <= slop, xr <= T)
