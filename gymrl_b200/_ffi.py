@@ -68,6 +68,9 @@ SIGNATURES = {
     "gymrl_adam_step": (c_int, [_P, _P, _P, _P, c_ll, _P, c_float, c_float, c_float, _P, _P, c_float, c_float, c_float, _P]),
     "gymrl_polyak": (c_int, [_P, _P, c_ll, c_float, _P]),
     "gymrl_random_permutation": (c_int, [_P, c_int, c_u64, c_u32, _P, _P]),
+    "gymrl_ppo_heads_workspace_bytes": (c_size_t, [c_int, c_int]),
+    "gymrl_ppo_heads_fused": (c_int, [_P, c_int, _P, _P, _P, _P, _P, _P, _P, _P, _P, _P, _P, _P, c_int, c_int, _P, _P, _P, _P, _P, _P, _P,
+                                      c_size_t, c_int, c_int, c_int, c_int, _P, _P]),
     "gymrl_running_stats_update": (c_int, [_P, c_int, c_int, _P, _P]),
     "gymrl_running_normalize": (c_int, [_P, _P, c_int, c_int, _P, c_int, _P]),
     "gymrl_reward_scaling": (c_int, [_P, _P, _P, _P, c_double, _P, c_int, _P]),

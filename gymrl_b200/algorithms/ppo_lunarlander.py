@@ -67,6 +67,7 @@ class Config:
         self.num_minibatches = None
         self.reset_each_rollout = None
         self.use_cuda_graph = True
+        self.fused_heads = True   # heads + loss + heads backward as one kernel where the shape allows (H in {128,256}, 4 actions)
 
 
 class ActorCritic(nn.Module):
@@ -132,18 +133,27 @@ class ActorCriticEngine:
         self.gWa2, self.gba2 = fp.g("actor.2.weight"), fp.g("actor.2.bias")
         self.gWc2, self.gbc2 = fp.g("critic.2.weight"), fp.g("critic.2.bias")
         self.workspace = None
+        # heads + loss + heads backward as one sweep (gymrl_ppo_heads_fused) where the kernel is built for the shape
+        self.can_fuse_heads = self.A == 4 and self.H in (128, 256)
 
     def alloc_workspace(self, M: int):
         need = max(ops.backward_weight_workspace(M, 2 * self.H, self.H), ops.backward_weight_workspace(M, self.H, self.H),
                    ops.backward_weight_workspace(M, self.H, self.D), ops.backward_weight_workspace(M, self.A, self.H))
+        if self.can_fuse_heads:
+            need = max(need, ops.ppo_heads_workspace_bytes(self.H, self.A))
         self.workspace = torch.empty(need, device=self.fp.flat.device, dtype=torch.uint8)
 
-    def forward(self, x: torch.Tensor, acts: _Acts, M: int, row_index: Optional[torch.Tensor] = None):
-        """logits = acts.lv[:M, :A], value = acts.lv[:M, A]."""
-        T, H, A = _ffi.ACT_TANH, self.H, self.A
+    def forward_trunk(self, x: torch.Tensor, acts: _Acts, M: int, row_index: Optional[torch.Tensor] = None):
+        """acts.ac[:M] = (actor | critic) head-trunk activations."""
+        T = _ffi.ACT_TANH
         ops.linear_forward(x, self.W1, self.b1, T, row_index=row_index, out=acts.h1, M=M)
         ops.linear_forward(acts.h1, self.W2, self.b2, T, out=acts.h2, M=M)
         ops.linear_forward(acts.h2, self.Wac, self.bac, T, out=acts.ac, M=M)
+
+    def forward(self, x: torch.Tensor, acts: _Acts, M: int, row_index: Optional[torch.Tensor] = None):
+        """logits = acts.lv[:M, :A], value = acts.lv[:M, A]."""
+        H, A = self.H, self.A
+        self.forward_trunk(x, acts, M, row_index)
         ops.linear_forward(acts.ac[:, :H], self.Wa2, self.ba2, _ffi.ACT_NONE, out=acts.lv[:, :A], M=M)
         ops.linear_forward(acts.ac[:, H:], self.Wc2, self.bc2, _ffi.ACT_NONE, out=acts.lv[:, A:A + 1], M=M)
         return acts.lv
@@ -154,9 +164,22 @@ class ActorCriticEngine:
         dl, dv = acts.dlv[:, :A], acts.dlv[:, A:A + 1]
         ops.linear_backward(dl, acts.ac[:, :H], self.Wa2, self.gWa2, self.gba2, dx=acts.dac[:, :H], act_in=T, workspace=ws, M=M)
         ops.linear_backward(dv, acts.ac[:, H:], self.Wc2, self.gWc2, self.gbc2, dx=acts.dac[:, H:], act_in=T, workspace=ws, M=M)
+        self.backward_trunk(x, acts, M, row_index)
+
+    def backward_trunk(self, x: torch.Tensor, acts: _Acts, M: int, row_index: Optional[torch.Tensor] = None):
+        """Given acts.dac[:M] = dL/d(pre-activation of the head trunks), fill the gradients of the three trunk layers."""
+        T, ws = _ffi.ACT_TANH, self.workspace
         ops.linear_backward(acts.dac, acts.h2, self.Wac, self.gWac, self.gbac, dx=acts.dh2, act_in=T, workspace=ws, M=M)
         ops.linear_backward(acts.dh2, acts.h1, self.W2, self.gW2, self.gb2, dx=acts.dh1, act_in=T, workspace=ws, M=M)
         ops.linear_backward(acts.dh1, x, self.W1, self.gW1, self.gb1, row_index=row_index, workspace=ws, M=M)
+
+    def heads_loss_backward(self, acts: _Acts, M: int, action, logp_old, adv, ret, loss_cfg, *, row_index=None, metrics=None,
+                            lv_out=None):
+        """Output heads, PPO loss and heads backward in one sweep over acts.ac: fills acts.dac and the head gradients."""
+        ops.ppo_heads_fused(acts.ac, self.Wa2, self.ba2, self.Wc2, self.bc2, action, logp_old, adv, ret, loss_cfg,
+                            dh=acts.dac, dWa=self.gWa2, dba=self.gba2, dWc=self.gWc2, dbc=self.gbc2, workspace=self.workspace,
+                            M=M, row_index=row_index, act_in=_ffi.ACT_TANH, lv_out=lv_out, metrics=metrics)
+
 
 class RolloutBuffer:
     """Device-resident [T][N] SoA rollout store (ref RolloutBuffer :120-154 keeps Python lists).
@@ -325,9 +348,15 @@ class PPOTrainer:
         obs_flat = buf.obs[:self.T].view(self.T * self.N, -1)
         ops.slice_i32(self.idx_mb, self.perm, self.ctr_mb)
         ops.counter_add(self.ctr_mb, 1)
-        net.forward(obs_flat, acts, M, row_index=self.idx_mb)
-        self._loss_step(acts)
-        net.backward(obs_flat, acts, M, row_index=self.idx_mb)
+        if getattr(self.cfg, "fused_heads", True) and getattr(net, "can_fuse_heads", False):
+            net.forward_trunk(obs_flat, acts, M, row_index=self.idx_mb)
+            net.heads_loss_backward(acts, M, buf.action.view(-1), buf.log_prob.view(-1), buf.adv.view(-1), buf.ret.view(-1),
+                                    self.loss_cfg, row_index=self.idx_mb, metrics=self.metrics)
+            net.backward_trunk(obs_flat, acts, M, row_index=self.idx_mb)
+        else:
+            net.forward(obs_flat, acts, M, row_index=self.idx_mb)
+            self._loss_step(acts)
+            net.backward(obs_flat, acts, M, row_index=self.idx_mb)
 
     def _opt_body(self):
         self.optimizer.launch(max_norm=self.cfg.max_grad_norm, grad_scale=1.0 / self.world)

@@ -23,6 +23,7 @@
 // owns, reduced across the block in shared memory, written as per-block partials and summed by a second kernel in a
 // fixed order (deterministic; no float atomics).
 #include "common.cuh"
+#include "rowwise.cuh"
 
 void gymrl_count_launch(int n = 1);
 
@@ -37,16 +38,6 @@ __device__ __forceinline__ float silu_gradf_(float x) {
     const float s = sigmoidf_(x);
     return s * (1.0f + x * (1.0f - s));
 }
-__device__ __forceinline__ float4 ld4(const float* p) { return *reinterpret_cast<const float4*>(p); }
-__device__ __forceinline__ void st4(float* p, float4 v) { *reinterpret_cast<float4*>(p) = v; }
-__device__ __forceinline__ float dot4(float4 a, float4 b) { return a.x * b.x + a.y * b.y + a.z * b.z + a.w * b.w; }
-__device__ __forceinline__ float4 axpy4(float a, float4 x, float4 y) {
-    return make_float4(fmaf(a, x.x, y.x), fmaf(a, x.y, y.y), fmaf(a, x.z, y.z), fmaf(a, x.w, y.w));
-}
-__device__ __forceinline__ float4 scale4(float a, float4 x) { return make_float4(a * x.x, a * x.y, a * x.z, a * x.w); }
-__device__ __forceinline__ float4 add4(float4 a, float4 b) { return make_float4(a.x + b.x, a.y + b.y, a.z + b.z, a.w + b.w); }
-__device__ __forceinline__ float4 mul4(float4 a, float4 b) { return make_float4(a.x * b.x, a.y * b.y, a.z * b.z, a.w * b.w); }
-
 // Per-lane copy of the stage parameters touching this lane's elements.
 template <int NCH>
 struct StageParams {
@@ -394,24 +385,6 @@ mhc_stage_bwd_b_kernel(const float* __restrict__ h_in, int row_stride, int branc
     for (int i = threadIdx.x; i < P; i += blockDim.x) out[i] = s_acc[i];
 }
 
-// out[p] (+)= sum_b partials[b][p], fixed order
-__global__ void reduce_blocks_kernel(const float* __restrict__ partials, int nblk, int P, float* __restrict__ o0, int n0,
-                                     float* __restrict__ o1, int n1, float* __restrict__ o2, int n2, float* __restrict__ o3,
-                                     int n3, int accumulate) {
-    const int p = blockIdx.x * blockDim.x + threadIdx.x;
-    if (p >= P) return;
-    float s = 0.f;
-    for (int b = 0; b < nblk; ++b) s += partials[(size_t)b * P + p];
-    float* dst;
-    int q = p;
-    if (q < n0) dst = o0 + q;
-    else if ((q -= n0) < n1) dst = o1 + q;
-    else if ((q -= n1) < n2) dst = o2 + q;
-    else { q -= n2; dst = o3 + q; }
-    (void)n3;
-    *dst = accumulate ? *dst + s : s;
-}
-
 // ---------------------------------------------------------------------------------------------------------------
 // RMSNorm (+ optional SiLU in front, + optional "sum of two branches" in front), row-wise, `groups` groups of width W
 //   y = a * rsqrt(mean(a^2) + eps) * weight,  a = silu(x) | x | x_0 + x_1
@@ -599,8 +572,8 @@ extern "C" int gymrl_mhc_stage_backward_b(const float* h, int row_stride, int br
         mhc_stage_bwd_b_kernel<2><<<grid, kWarpsPerBlock * 32, smem, s>>>(h, row_stride, branch_stride, dh_pre, scratch, dh_partial, dh, dx0,
                                                                           g, w, alpha, (float*)workspace, M);
     }
-    reduce_blocks_kernel<<<ceil_div(P, 256), 256, 0, s>>>((const float*)workspace, grid, P, dw, 2 * D * 8, dg, 2 * D, dalpha, 3, dbeta, 8,
-                                                         accumulate);
+    launch_reduce_blocks((const float*)workspace, grid, P, dw, 2 * D * 8, dg, 2 * D, dalpha, 3, dbeta, 8,
+                                                         accumulate, s);
     gymrl_count_launch(2);
     GYMRL_LAUNCH_CHECK("mhc_stage_backward_b");
     return GYMRL_OK;
@@ -654,7 +627,7 @@ extern "C" int gymrl_rmsnorm_backward(const float* x, int ldx, int sum2, int sil
     if (sum2) launch_rms_bwd<false, true>(x, ldx, weight, dy, lddy, dx, lddx, partials, grid, M, W, groups, eps, s);
     else if (silu) launch_rms_bwd<true, false>(x, ldx, weight, dy, lddy, dx, lddx, partials, grid, M, W, groups, eps, s);
     else launch_rms_bwd<false, false>(x, ldx, weight, dy, lddy, dx, lddx, partials, grid, M, W, groups, eps, s);
-    reduce_blocks_kernel<<<ceil_div(P, 256), 256, 0, s>>>(partials, grid, P, dweight, P, nullptr, 0, nullptr, 0, nullptr, 0, accumulate);
+    launch_reduce_blocks(partials, grid, P, dweight, P, nullptr, 0, nullptr, 0, nullptr, 0, accumulate, s);
     gymrl_count_launch(2);
     GYMRL_LAUNCH_CHECK("rmsnorm_backward");
     return GYMRL_OK;

@@ -15,10 +15,104 @@
 // only by chance, so this kernel is gather-latency bound, not bandwidth bound).  The five metric
 // sums are block-reduced and added with one atomic per block.
 #include "common.cuh"
+#include "rowwise.cuh"
 
 void gymrl_count_launch(int n = 1);
 
 #define MAX_A 16
+
+struct PpoSample {
+    float dlogits[MAX_A];
+    float dvalue;
+    float m_pol, m_val, m_ent, m_clip, m_kl, m_erc;
+};
+
+// One sample of the loss and its gradient wrt (logits, V).  `A` may be a compile-time constant at the call site.
+__device__ __forceinline__ void ppo_sample(const float* z, float V, int a, float lpo, float Adv, float R, float ent_old_r,
+                                           float val_old_r, const gymrl_ppo_cfg& cfg, float ent_coef, float invB, int A,
+                                           PpoSample& o) {
+    // loops run to MAX_A with a guard so that every array index is a compile-time constant (arrays stay in registers)
+    float ln[MAX_A], p[MAX_A];
+    float mx = z[0];
+#pragma unroll
+    for (int j = 1; j < MAX_A; ++j)
+        if (j < A) mx = fmaxf(mx, z[j]);
+    float s = 0.f;
+#pragma unroll
+    for (int j = 0; j < MAX_A; ++j)
+        if (j < A) s += expf(z[j] - mx);
+    const float lse = logf(s) + mx;
+    float H = 0.f;
+    float lp = 0.f;
+#pragma unroll
+    for (int j = 0; j < MAX_A; ++j)
+        if (j < A) {
+            ln[j] = z[j] - lse;
+            p[j] = expf(ln[j]);
+            H -= p[j] * ln[j];
+            lp = j == a ? ln[j] : lp;
+        }
+    const float ratio = expf(lp - lpo);
+    const float lo = 1.0f - cfg.clip_eps_min, hi = 1.0f + cfg.clip_eps_max;
+    const bool in_range = ratio >= lo && ratio <= hi;
+    const float surr2 = fminf(fmaxf(ratio, lo), hi) * Adv;
+    const int mode = cfg.mode & 3;
+    float mask = 1.0f;
+    float obj, g;  // objective (to maximise) and d obj / d ratio
+    if (mode == GYMRL_PPO_FULL) {
+        const float er = H / (ent_old_r + 1e-8f);
+        mask = (er > 1.0f - cfg.erc_low && er < 1.0f + cfg.erc_high) ? 1.0f : 0.0f;
+        const float cr = fminf(fmaxf(ratio, 0.0f), cfg.dual_clip);
+        const float surr1 = cr * Adv;
+        const float g1 = (ratio >= 0.0f && ratio <= cfg.dual_clip) ? Adv : 0.0f;
+        const float g2 = in_range ? Adv : 0.0f;
+        obj = fminf(surr1, surr2);
+        g = surr1 < surr2 ? g1 : (surr1 == surr2 ? 0.5f * (g1 + g2) : g2);
+    } else {
+        const float surr1 = ratio * Adv;
+        const float g2 = in_range ? Adv : 0.0f;
+        const float min_surr = fminf(surr1, surr2);
+        float gm = surr1 < surr2 ? Adv : (surr1 == surr2 ? 0.5f * (Adv + g2) : g2);
+        obj = min_surr;
+        g = gm;
+        if (Adv < 0.0f) {
+            const float dc = cfg.dual_clip * Adv;
+            obj = fmaxf(min_surr, dc);
+            g = min_surr > dc ? gm : (min_surr == dc ? 0.5f * gm : 0.0f);
+        }
+    }
+    // value term
+    const float e1 = V - R;
+    float vterm = e1 * e1, dv = 2.0f * e1;
+    if (cfg.mode & GYMRL_PPO_VALUE_CLIP) {
+        const float vo = val_old_r;
+        const float dlt = V - vo;
+        const float vcl = vo + fminf(fmaxf(dlt, -cfg.vclip_eps_min), cfg.vclip_eps_max);
+        const float e2 = vcl - R;
+        const float l2 = e2 * e2;
+        const float pass = (dlt >= -cfg.vclip_eps_min && dlt <= cfg.vclip_eps_max) ? 1.0f : 0.0f;
+        const float d2 = 2.0f * e2 * pass;
+        if (l2 > vterm) { vterm = l2; dv = d2; }
+        else if (l2 == vterm) { dv = 0.5f * (dv + d2); }
+    }
+    // gradients: L = -obj*mask/B + vc*mask*vterm/B - ec*mask*H/B
+    const float dL_dlp = -(g * ratio) * mask * invB;
+    const float dL_dH = -ent_coef * mask * invB;
+#pragma unroll
+    for (int j = 0; j < MAX_A; ++j)
+        if (j < A) {
+            const float dlp = (j == a ? 1.0f : 0.0f) - p[j];
+            const float dH = -p[j] * (ln[j] + H);
+            o.dlogits[j] = dL_dlp * dlp + dL_dH * dH;
+        }
+    o.dvalue = cfg.value_coef * mask * dv * invB;
+    o.m_pol = -obj * mask * invB;
+    o.m_val = cfg.value_coef * mask * vterm * invB;
+    o.m_ent = H * mask * invB;
+    o.m_clip = ((ratio < lo || ratio > hi) ? 1.0f : 0.0f) * mask * invB;
+    o.m_kl = (lpo - lp) * invB;
+    o.m_erc = (1.0f - mask) * invB;
+}
 
 __global__ void ppo_loss_kernel(const float* __restrict__ logits, int ldl, const float* __restrict__ value, int ldv,
                                 const int32_t* __restrict__ row_index, const int32_t* __restrict__ action,
@@ -34,79 +128,18 @@ __global__ void ppo_loss_kernel(const float* __restrict__ logits, int ldl, const
     float m_pol = 0.f, m_val = 0.f, m_ent = 0.f, m_clip = 0.f, m_kl = 0.f, m_erc = 0.f;
     if (i < B) {
         const int r = row_index ? row_index[i] : i;
-        float z[MAX_A], ln[MAX_A], p[MAX_A];
-        for (int j = 0; j < A; ++j) z[j] = logits[(size_t)i * ldl + j];
-        float mx = z[0];
-        for (int j = 1; j < A; ++j) mx = fmaxf(mx, z[j]);
-        float s = 0.f;
-        for (int j = 0; j < A; ++j) s += expf(z[j] - mx);
-        const float lse = logf(s) + mx;
-        float H = 0.f;
-        for (int j = 0; j < A; ++j) {
-            ln[j] = z[j] - lse;
-            p[j] = expf(ln[j]);
-            H -= p[j] * ln[j];
-        }
-        const int a = action[r];
-        const float lp = ln[a], lpo = logp_old[r], Adv = adv[r], R = ret[r], V = value[(size_t)i * ldv];
-        const float ratio = expf(lp - lpo);
-        const float lo = 1.0f - cfg.clip_eps_min, hi = 1.0f + cfg.clip_eps_max;
-        const bool in_range = ratio >= lo && ratio <= hi;
-        const float surr2 = fminf(fmaxf(ratio, lo), hi) * Adv;
-        const int mode = cfg.mode & 3;
-        float mask = 1.0f;
-        float obj, g;  // objective (to maximise) and d obj / d ratio
-        if (mode == GYMRL_PPO_FULL) {
-            const float er = H / (ent_old[r] + 1e-8f);
-            mask = (er > 1.0f - cfg.erc_low && er < 1.0f + cfg.erc_high) ? 1.0f : 0.0f;
-            const float cr = fminf(fmaxf(ratio, 0.0f), cfg.dual_clip);
-            const float surr1 = cr * Adv;
-            const float g1 = (ratio >= 0.0f && ratio <= cfg.dual_clip) ? Adv : 0.0f;
-            const float g2 = in_range ? Adv : 0.0f;
-            obj = fminf(surr1, surr2);
-            g = surr1 < surr2 ? g1 : (surr1 == surr2 ? 0.5f * (g1 + g2) : g2);
-        } else {
-            const float surr1 = ratio * Adv;
-            const float g2 = in_range ? Adv : 0.0f;
-            const float min_surr = fminf(surr1, surr2);
-            float gm = surr1 < surr2 ? Adv : (surr1 == surr2 ? 0.5f * (Adv + g2) : g2);
-            obj = min_surr;
-            g = gm;
-            if (Adv < 0.0f) {
-                const float dc = cfg.dual_clip * Adv;
-                obj = fmaxf(min_surr, dc);
-                g = min_surr > dc ? gm : (min_surr == dc ? 0.5f * gm : 0.0f);
-            }
-        }
-        // value term
-        const float e1 = V - R;
-        float vterm = e1 * e1, dv = 2.0f * e1;
-        if (cfg.mode & GYMRL_PPO_VALUE_CLIP) {
-            const float vo = val_old[r];
-            const float dlt = V - vo;
-            const float vcl = vo + fminf(fmaxf(dlt, -cfg.vclip_eps_min), cfg.vclip_eps_max);
-            const float e2 = vcl - R;
-            const float l2 = e2 * e2;
-            const float pass = (dlt >= -cfg.vclip_eps_min && dlt <= cfg.vclip_eps_max) ? 1.0f : 0.0f;
-            const float d2 = 2.0f * e2 * pass;
-            if (l2 > vterm) { vterm = l2; dv = d2; }
-            else if (l2 == vterm) { dv = 0.5f * (dv + d2); }
-        }
-        // gradients: L = -obj*mask/B + vc*mask*vterm/B - ec*mask*H/B
-        const float dL_dlp = -(g * ratio) * mask * invB;
-        const float dL_dH = -ent_coef * mask * invB;
-        for (int j = 0; j < A; ++j) {
-            const float dlp = (j == a ? 1.0f : 0.0f) - p[j];
-            const float dH = -p[j] * (ln[j] + H);
-            dlogits[(size_t)i * lddl + j] = dL_dlp * dlp + dL_dH * dH;
-        }
-        dvalue[(size_t)i * lddv] = cfg.value_coef * mask * dv * invB;
-        m_pol = -obj * mask * invB;
-        m_val = cfg.value_coef * mask * vterm * invB;
-        m_ent = H * mask * invB;
-        m_clip = ((ratio < lo || ratio > hi) ? 1.0f : 0.0f) * mask * invB;
-        m_kl = (lpo - lp) * invB;
-        m_erc = (1.0f - mask) * invB;
+        float z[MAX_A];
+#pragma unroll
+        for (int j = 0; j < MAX_A; ++j)
+            if (j < A) z[j] = logits[(size_t)i * ldl + j];
+        PpoSample o;
+        ppo_sample(z, value[(size_t)i * ldv], action[r], logp_old[r], adv[r], ret[r], ent_old ? ent_old[r] : 0.f,
+                   val_old ? val_old[r] : 0.f, cfg, ent_coef, invB, A, o);
+#pragma unroll
+        for (int j = 0; j < MAX_A; ++j)
+            if (j < A) dlogits[(size_t)i * lddl + j] = o.dlogits[j];
+        dvalue[(size_t)i * lddv] = o.dvalue;
+        m_pol = o.m_pol; m_val = o.m_val; m_ent = o.m_ent; m_clip = o.m_clip; m_kl = o.m_kl; m_erc = o.m_erc;
     }
     m_pol = block_sum(m_pol, scratch);
     m_val = block_sum(m_val, scratch);
@@ -124,6 +157,185 @@ __global__ void ppo_loss_kernel(const float* __restrict__ logits, int ldl, const
         atomicAdd(&metrics[6], m_pol + m_val - ent_coef * m_ent);
         if (blockIdx.x == 0) atomicAdd(&metrics[7], 1.0f);
     }
+}
+
+// ---------------------------------------------------------------------------------------------------------------
+// Fused output heads + loss + heads backward (one sweep over the [M][2H] head-trunk activations).
+//   h = (h_a | h_c): logits = Wa h_a + ba (A x H), V = Wc h_c + bc;  loss as above;
+//   dh_a = (Wa^T dlogits) act'(h_a), dh_c = dV Wc act'(h_c);  dWa += dlogits (x) h_a, dba += dlogits, dWc += dV h_c, dbc += dV.
+// Replaces skinny_fwd<A> + skinny_fwd<1> + ppo_loss + 2 x skinny_bwd_fused (+ their reductions): those five launches each
+// re-read (half of) the [M][2H] activation and are latency-bound at ~10 us each; this reads it once and writes dh once.
+// One warp per row, lane l owns elements {128 j + 4 l ..+3} of each half; the A + 1 dot products are warp reductions, the
+// per-sample loss runs redundantly on every lane (registers only), weight-gradient sums stay in registers over the rows
+// a warp owns and leave through per-block partials + a fixed-order reduction (deterministic).
+// ---------------------------------------------------------------------------------------------------------------
+constexpr int kHeadsWarps = 8;
+constexpr int kHeadsMaxBlocks = 4 * GYMRL_NUM_SMS;
+
+template <int NCH, int A>
+__global__ void __launch_bounds__(kHeadsWarps * 32, 2)
+ppo_heads_fused_kernel(const float* __restrict__ h, int ldh, const float* __restrict__ Wa, const float* __restrict__ ba,
+                       const float* __restrict__ Wc, const float* __restrict__ bc, const int32_t* __restrict__ row_index,
+                       const int32_t* __restrict__ action, const float* __restrict__ logp_old, const float* __restrict__ adv,
+                       const float* __restrict__ ret, const float* __restrict__ ent_old, const float* __restrict__ val_old,
+                       float* __restrict__ dh, int lddh, int act_tanh, float* __restrict__ lv_out, float* __restrict__ partials,
+                       float* __restrict__ metrics, int M, gymrl_ppo_cfg cfg) {
+    constexpr int H = 128 * NCH;
+    constexpr int P = A * H + A + H + 1;     // [dWa | dba | dWc | dbc]
+    extern __shared__ float s_acc[];
+    __shared__ float s_met[kHeadsWarps][6];
+    const int lane = threadIdx.x & 31, wid = threadIdx.x >> 5;
+    const int warp = blockIdx.x * kHeadsWarps + wid, nwarps = gridDim.x * kHeadsWarps;
+    for (int i = threadIdx.x; i < P; i += blockDim.x) s_acc[i] = 0.f;
+    float4 wa[A][NCH], wc[NCH], gwa[A][NCH], gwc[NCH];
+    float bav[A], gb[A + 1];
+#pragma unroll
+    for (int j = 0; j < NCH; ++j) {
+#pragma unroll
+        for (int a = 0; a < A; ++a) {
+            wa[a][j] = ld4(Wa + (size_t)a * H + 128 * j + 4 * lane);
+            gwa[a][j] = make_float4(0.f, 0.f, 0.f, 0.f);
+        }
+        wc[j] = ld4(Wc + 128 * j + 4 * lane);
+        gwc[j] = make_float4(0.f, 0.f, 0.f, 0.f);
+    }
+#pragma unroll
+    for (int a = 0; a < A; ++a) { bav[a] = ba[a]; gb[a] = 0.f; }
+    gb[A] = 0.f;
+    const float bcv = bc[0];
+    const float invB = 1.0f / (float)M;
+    const float ent_coef = cfg.d_entropy_coef ? *cfg.d_entropy_coef : cfg.entropy_coef;
+    float met[6] = {0.f, 0.f, 0.f, 0.f, 0.f, 0.f};
+    for (int row = warp; row < M; row += nwarps) {
+        const float* hp = h + (size_t)row * ldh;
+        float4 ha[NCH], hc[NCH];
+        float z[A + 1];
+#pragma unroll
+        for (int a = 0; a <= A; ++a) z[a] = 0.f;
+#pragma unroll
+        for (int j = 0; j < NCH; ++j) {
+            ha[j] = ld4(hp + 128 * j + 4 * lane);
+            hc[j] = ld4(hp + H + 128 * j + 4 * lane);
+#pragma unroll
+            for (int a = 0; a < A; ++a) z[a] += dot4(ha[j], wa[a][j]);
+            z[A] += dot4(hc[j], wc[j]);
+        }
+        const int r = row_index ? row_index[row] : row;
+        const int act = action[r];
+        const float lpo = logp_old[r], Adv = adv[r], R = ret[r];
+        const float eo = ent_old ? ent_old[r] : 0.f, vo = val_old ? val_old[r] : 0.f;
+#pragma unroll
+        for (int a = 0; a <= A; ++a) z[a] = warp_sum(z[a]);
+#pragma unroll
+        for (int a = 0; a < A; ++a) z[a] += bav[a];
+        const float V = z[A] + bcv;
+        PpoSample o;
+        ppo_sample(z, V, act, lpo, Adv, R, eo, vo, cfg, ent_coef, invB, A, o);
+        if (lv_out && lane == 0) {
+#pragma unroll
+            for (int a = 0; a < A; ++a) lv_out[(size_t)row * 8 + a] = z[a];
+            lv_out[(size_t)row * 8 + A] = V;
+        }
+        met[0] += o.m_pol; met[1] += o.m_val; met[2] += o.m_ent; met[3] += o.m_clip; met[4] += o.m_kl; met[5] += o.m_erc;
+#pragma unroll
+        for (int a = 0; a < A; ++a) gb[a] += o.dlogits[a];
+        gb[A] += o.dvalue;
+        float* dp = dh + (size_t)row * lddh;
+#pragma unroll
+        for (int j = 0; j < NCH; ++j) {
+            float4 da = make_float4(0.f, 0.f, 0.f, 0.f);
+#pragma unroll
+            for (int a = 0; a < A; ++a) {
+                da = axpy4(o.dlogits[a], wa[a][j], da);
+                gwa[a][j] = axpy4(o.dlogits[a], ha[j], gwa[a][j]);
+            }
+            float4 dc = scale4(o.dvalue, wc[j]);
+            gwc[j] = axpy4(o.dvalue, hc[j], gwc[j]);
+            if (act_tanh) {
+                da = mul4(da, make_float4(1.f - ha[j].x * ha[j].x, 1.f - ha[j].y * ha[j].y, 1.f - ha[j].z * ha[j].z, 1.f - ha[j].w * ha[j].w));
+                dc = mul4(dc, make_float4(1.f - hc[j].x * hc[j].x, 1.f - hc[j].y * hc[j].y, 1.f - hc[j].z * hc[j].z, 1.f - hc[j].w * hc[j].w));
+            }
+            st4(dp + 128 * j + 4 * lane, da);
+            st4(dp + H + 128 * j + 4 * lane, dc);
+        }
+    }
+    __syncthreads();
+    for (int wsel = 0; wsel < kHeadsWarps; ++wsel) {
+        if (wid == wsel) {
+#pragma unroll
+            for (int j = 0; j < NCH; ++j) {
+#pragma unroll
+                for (int a = 0; a < A; ++a) {
+                    float* q = s_acc + (size_t)a * H + 128 * j + 4 * lane;
+                    q[0] += gwa[a][j].x; q[1] += gwa[a][j].y; q[2] += gwa[a][j].z; q[3] += gwa[a][j].w;
+                }
+                float* q = s_acc + A * H + A + 128 * j + 4 * lane;
+                q[0] += gwc[j].x; q[1] += gwc[j].y; q[2] += gwc[j].z; q[3] += gwc[j].w;
+            }
+            if (lane == 0) {
+#pragma unroll
+                for (int a = 0; a < A; ++a) s_acc[A * H + a] += gb[a];
+                s_acc[A * H + A + H] += gb[A];
+#pragma unroll
+                for (int k = 0; k < 6; ++k) s_met[wid][k] = met[k];
+            }
+        }
+        __syncthreads();
+    }
+    float* out = partials + (size_t)blockIdx.x * P;
+    for (int i = threadIdx.x; i < P; i += blockDim.x) out[i] = s_acc[i];
+    if (threadIdx.x == 0 && metrics) {
+        float m[6] = {0.f, 0.f, 0.f, 0.f, 0.f, 0.f};
+        for (int w = 0; w < kHeadsWarps; ++w)
+            for (int k = 0; k < 6; ++k) m[k] += s_met[w][k];
+        for (int k = 0; k < 6; ++k) atomicAdd(&metrics[k], m[k]);
+        atomicAdd(&metrics[6], m[0] + m[1] - ent_coef * m[2]);
+        if (blockIdx.x == 0) atomicAdd(&metrics[7], 1.0f);
+    }
+}
+
+extern "C" size_t gymrl_ppo_heads_workspace_bytes(int H, int A) {
+    return (size_t)kHeadsMaxBlocks * (size_t)(A * H + A + H + 1) * sizeof(float);
+}
+
+extern "C" int gymrl_ppo_heads_fused(const float* d_h, int ldh, const float* d_Wa, const float* d_ba, const float* d_Wc,
+                                     const float* d_bc, const int32_t* d_row_index, const int32_t* d_action,
+                                     const float* d_logp_old, const float* d_adv, const float* d_ret, const float* d_entropy_old,
+                                     const float* d_value_old, float* d_dh, int lddh, int act_in, float* d_dWa, float* d_dba,
+                                     float* d_dWc, float* d_dbc, float* d_lv_out, float* d_metrics, void* d_workspace,
+                                     size_t workspace_bytes, int accumulate, int batch, int H, int n_actions,
+                                     const gymrl_ppo_cfg* cfg, void* stream) {
+    GYMRL_REQUIRE(cfg != nullptr, "cfg is NULL");
+    GYMRL_REQUIRE(d_h && d_Wa && d_ba && d_Wc && d_bc && d_action && d_logp_old && d_adv && d_ret && d_dh && d_dWa && d_dba && d_dWc &&
+                  d_dbc && d_workspace, "NULL pointer");
+    GYMRL_REQUIRE(batch > 0 && (H == 128 || H == 256) && n_actions == 4, "fused heads are built for H in {128, 256} and 4 actions "
+                  "(got H=%d, A=%d): use gymrl_linear_* + gymrl_ppo_loss otherwise", H, n_actions);
+    GYMRL_REQUIRE(act_in == 0 || act_in == 1, "act_in must be GYMRL_ACT_NONE or GYMRL_ACT_TANH");
+    GYMRL_REQUIRE(ldh % 4 == 0 && lddh % 4 == 0, "leading dimensions must be multiples of 4 floats");
+    GYMRL_REQUIRE((cfg->mode & 3) <= GYMRL_PPO_FULL, "unknown PPO mode %d", cfg->mode);
+    GYMRL_REQUIRE((cfg->mode & 3) != GYMRL_PPO_FULL || d_entropy_old, "GYMRL_PPO_FULL needs d_entropy_old");
+    GYMRL_REQUIRE(!(cfg->mode & GYMRL_PPO_VALUE_CLIP) || d_value_old, "VALUE_CLIP needs d_value_old");
+    const int A = 4;
+    const int P = A * H + A + H + 1;
+    int grid = ceil_div(batch, kHeadsWarps * 8);           // >= 8 rows per warp so the per-warp set-up amortises
+    if (grid > kHeadsMaxBlocks) grid = kHeadsMaxBlocks;
+    if (grid < 1) grid = 1;
+    GYMRL_REQUIRE(workspace_bytes >= (size_t)grid * P * sizeof(float), "workspace too small: need %zu bytes", (size_t)grid * P * sizeof(float));
+    cudaStream_t s = as_stream(stream);
+    const size_t smem = (size_t)P * sizeof(float);
+    float* partials = (float*)d_workspace;
+    if (H == 256)
+        ppo_heads_fused_kernel<2, 4><<<grid, kHeadsWarps * 32, smem, s>>>(d_h, ldh, d_Wa, d_ba, d_Wc, d_bc, d_row_index, d_action, d_logp_old, d_adv,
+                                                                           d_ret, d_entropy_old, d_value_old, d_dh, lddh, act_in, d_lv_out, partials,
+                                                                           d_metrics, batch, *cfg);
+    else
+        ppo_heads_fused_kernel<1, 4><<<grid, kHeadsWarps * 32, smem, s>>>(d_h, ldh, d_Wa, d_ba, d_Wc, d_bc, d_row_index, d_action, d_logp_old, d_adv,
+                                                                           d_ret, d_entropy_old, d_value_old, d_dh, lddh, act_in, d_lv_out, partials,
+                                                                           d_metrics, batch, *cfg);
+    launch_reduce_blocks(partials, grid, P, d_dWa, A * H, d_dba, A, d_dWc, H, d_dbc, 1, accumulate, s);
+    gymrl_count_launch(2);
+    GYMRL_LAUNCH_CHECK("ppo_heads_fused");
+    return GYMRL_OK;
 }
 
 extern "C" int gymrl_ppo_loss(const float* d_logits, int ld_logits, const float* d_value, int ld_value,

@@ -202,6 +202,27 @@ def ppo_loss(logits, value, action, logp_old, adv, ret, cfg: _ffi.PPOCfg, *, row
     return dlogits, dvalue, metrics
 
 
+def ppo_heads_workspace_bytes(H, A=4) -> int:
+    return int(load().gymrl_ppo_heads_workspace_bytes(int(H), int(A)))
+
+
+def ppo_heads_workspace(H, A=4, device="cuda"):
+    return torch.empty(ppo_heads_workspace_bytes(H, A), device=device, dtype=torch.uint8)
+
+
+def ppo_heads_fused(h, Wa, ba, Wc, bc, action, logp_old, adv, ret, cfg: _ffi.PPOCfg, *, dh, dWa, dba, dWc, dbc, workspace, M,
+                    row_index=None, entropy_old=None, value_old=None, act_in=_ffi.ACT_TANH, lv_out=None, metrics=None,
+                    accumulate=False):
+    """Output heads + PPO loss + heads backward in one sweep over h [M, 2H] (csrc/ppo_loss.cu)."""
+    A, H = Wa.shape
+    check(load().gymrl_ppo_heads_fused(ptr(h, f32), _ld(h), ptr(Wa, f32), ptr(ba, f32), ptr(Wc, f32), ptr(bc, f32), ptr(row_index, i32),
+                                       ptr(action, i32), ptr(logp_old, f32), ptr(adv, f32), ptr(ret, f32), ptr(entropy_old, f32),
+                                       ptr(value_old, f32), ptr(dh, f32), _ld(dh), int(act_in), ptr(dWa, f32), ptr(dba, f32),
+                                       ptr(dWc, f32), ptr(dbc, f32), ptr(lv_out, f32), ptr(metrics, f32), workspace.data_ptr(),
+                                       workspace.numel() * workspace.element_size(), int(accumulate), int(M), int(H), int(A),
+                                       C.byref(cfg), stream_ptr()))
+
+
 # ------------------------------------------------------------------------------------------------
 # dense layers
 # ------------------------------------------------------------------------------------------------

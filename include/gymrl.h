@@ -357,6 +357,20 @@ int gymrl_noisy_backward(const float* d_dw, const float* d_db, const float* d_ep
                          float* d_dw_mu, float* d_dw_sigma, float* d_db_mu, float* d_db_sigma, int N, int K,
                          int accumulate, void* stream);
 
+/* Fused output heads + PPO loss + heads backward over the head-trunk activations d_h [batch][2H] = (actor | critic):
+ *   logits = Wa h_a + ba (Wa [4][H]), V = Wc h_c + bc (Wc [1][H]); the loss of gymrl_ppo_loss (same cfg, same metrics);
+ *   d_dh [batch][2H] = dL/dh (times the tanh derivative 1 - h^2 when act_in = GYMRL_ACT_TANH);
+ *   dWa, dba, dWc, dbc (= or += with `accumulate`).  d_lv_out (nullable) [batch][8] receives logits | V.
+ * One launch instead of the last two Linear layers of ActorCritic (algorithms/ppo_lunarlander.py:83,86), the loss
+ * (:278-300) and their backward; H in {128, 256}, 4 actions.  Workspace: gymrl_ppo_heads_workspace_bytes(H, 4). */
+size_t gymrl_ppo_heads_workspace_bytes(int H, int n_actions);
+int gymrl_ppo_heads_fused(const float* d_h, int ldh, const float* d_Wa, const float* d_ba, const float* d_Wc, const float* d_bc,
+                          const int32_t* d_row_index, const int32_t* d_action, const float* d_logp_old, const float* d_adv,
+                          const float* d_ret, const float* d_entropy_old, const float* d_value_old, float* d_dh, int lddh,
+                          int act_in, float* d_dWa, float* d_dba, float* d_dWc, float* d_dbc, float* d_lv_out, float* d_metrics,
+                          void* d_workspace, size_t workspace_bytes, int accumulate, int batch, int H, int n_actions,
+                          const gymrl_ppo_cfg* cfg, void* stream);
+
 /* ------------------------------------------------------------------------------------------------
  * ppo_full network glue: manifold hyper-connection stages, RMSNorm, SiLU.
  * algorithms/ppo_full_lunarlander.py: sinkhorn_knopp_batched :76-103, ManifoldHyperConnectionFuse :106-194,

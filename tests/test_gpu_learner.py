@@ -213,6 +213,76 @@ def test_ppo_loss_vs_oracle_with_gather(ops, mode):
         np.testing.assert_allclose(m[i], r[k], rtol=2e-4, atol=2e-6)
 
 
+@pytest.mark.parametrize("mode,H,B", [("dualclip", 256, 16384), ("full", 256, 1777), ("dualclip+vclip", 128, 4096), ("dualclip", 128, 5),
+                                      ("full+vclip", 256, 40000)])
+def test_ppo_heads_fused_vs_oracle(ops, mode, H, B):
+    """gymrl_ppo_heads_fused = heads forward + loss + heads backward in one sweep: every output against the oracle loss
+    (float64 heads around it) on the same gathered samples, and the logits/value copy against the separate head kernels."""
+    from gymrl_b200 import _ffi
+    rng = np.random.default_rng(H + B)
+    Btot, A_ = B + 3000, 4
+    idx = rng.permutation(Btot)[:B].astype(np.int32)
+    h = np.tanh(rng.standard_normal((B, 2 * H))).astype(np.float32)
+    Wa, ba = (rng.standard_normal((A_, H)) * 0.2).astype(np.float32), (rng.standard_normal(A_) * 0.1).astype(np.float32)
+    Wc, bc = (rng.standard_normal((1, H)) * 0.1).astype(np.float32), (rng.standard_normal(1) * 0.1).astype(np.float32)
+    act = rng.integers(0, A_, Btot).astype(np.int32)
+    lpo = (-np.abs(rng.standard_normal(Btot)) - 0.5).astype(np.float32)
+    adv, ret = rng.standard_normal(Btot).astype(np.float32), rng.standard_normal(Btot).astype(np.float32)
+    ent_old = (rng.random(Btot) * 1.3 + 0.05).astype(np.float32)
+    v_old = rng.standard_normal(Btot).astype(np.float32)
+    full, vclip = mode.startswith("full"), mode.endswith("vclip")
+    cfg = _loss_cfg(mode=(_ffi.PPO_FULL if full else 0) | (_ffi.PPO_VALUE_CLIP if vclip else 0), clip_eps_max=0.28 if full else 0.2)
+    d_h = cu(h)
+    dh = torch.full((B, 2 * H), float("nan"), device="cuda")
+    dWa, dba = torch.full((A_, H), float("nan"), device="cuda"), torch.full((A_,), float("nan"), device="cuda")
+    dWc, dbc = torch.full((1, H), float("nan"), device="cuda"), torch.full((1,), float("nan"), device="cuda")
+    lv = torch.zeros(B, 8, device="cuda")
+    met = torch.zeros(8, device="cuda")
+    ws = ops.ppo_heads_workspace(H, A_)
+    ops.ppo_heads_fused(d_h, cu(Wa), cu(ba), cu(Wc), cu(bc), cu(act), cu(lpo), cu(adv), cu(ret), cfg, dh=dh, dWa=dWa, dba=dba,
+                        dWc=dWc, dbc=dbc, workspace=ws, M=B, row_index=cu(idx), entropy_old=cu(ent_old) if full else None,
+                        value_old=cu(v_old) if vclip else None, lv_out=lv, metrics=met)
+    # forward copy vs the separate head kernels (fp32 dot products in a different order)
+    lg = ops.linear_forward(d_h[:, :H], cu(Wa), cu(ba), _ffi.ACT_NONE)
+    vv = ops.linear_forward(d_h[:, H:], cu(Wc), cu(bc), _ffi.ACT_NONE)
+    torch.testing.assert_close(lv[:, :A_], lg, rtol=1e-5, atol=2e-6)
+    torch.testing.assert_close(lv[:, A_:A_ + 1], vv, rtol=1e-5, atol=2e-6)
+    # oracle loss on the kernel's own logits/value (so clip / tie decisions agree), float64 heads backward around it
+    logits, value = lv[:, :A_].cpu().numpy(), lv[:, A_].cpu().numpy()
+    r = A.ppo_loss_grad(logits, value, act[idx], lpo[idx], adv[idx], ret[idx], mode="full" if full else "dualclip",
+                        clip_eps_max=0.28 if full else 0.2, entropy_old=ent_old[idx] if full else None,
+                        value_old=v_old[idx] if vclip else None)
+    dl, dv = r["dlogits"].astype(np.float64), r["dvalue"].astype(np.float64).reshape(-1, 1)
+    ha, hc = h[:, :H].astype(np.float64), h[:, H:].astype(np.float64)
+    ref_dh = np.concatenate([(dl @ Wa) * (1 - ha * ha), (dv @ Wc) * (1 - hc * hc)], axis=1)
+    sc = 1.0 / B
+    np.testing.assert_allclose(dh.cpu().numpy(), ref_dh, rtol=1e-3, atol=2e-5 * sc)
+    np.testing.assert_allclose(dWa.cpu().numpy(), dl.T @ ha, rtol=1e-3, atol=1e-5)
+    np.testing.assert_allclose(dba.cpu().numpy(), dl.sum(0), rtol=1e-3, atol=1e-5)
+    np.testing.assert_allclose(dWc.cpu().numpy(), dv.T @ hc, rtol=1e-3, atol=1e-5)
+    np.testing.assert_allclose(dbc.cpu().numpy(), dv.sum(0), rtol=1e-3, atol=1e-5)
+    m = met.cpu().numpy()
+    for i, k in enumerate(("policy_loss", "value_loss", "entropy", "clip_frac", "approx_kl", "erc_frac")):
+        np.testing.assert_allclose(m[i], r[k], rtol=3e-4, atol=3e-6)
+    assert m[7] == 1.0
+    # accumulate = += on the parameter gradients, deterministic partial order (two runs are bit-identical)
+    g0 = dWa.clone()
+    ops.ppo_heads_fused(d_h, cu(Wa), cu(ba), cu(Wc), cu(bc), cu(act), cu(lpo), cu(adv), cu(ret), cfg, dh=dh, dWa=dWa, dba=dba,
+                        dWc=dWc, dbc=dbc, workspace=ws, M=B, row_index=cu(idx), entropy_old=cu(ent_old) if full else None,
+                        value_old=cu(v_old) if vclip else None, accumulate=True)
+    assert torch.equal(dWa, g0 + g0)
+
+
+def test_ppo_heads_fused_rejects_unsupported_shapes(ops):
+    from gymrl_b200 import _ffi
+    H, B = 64, 32
+    z = lambda *s: torch.zeros(*s, device="cuda")
+    zi = torch.zeros(B, device="cuda", dtype=torch.int32)
+    with pytest.raises(RuntimeError):
+        ops.ppo_heads_fused(z(B, 2 * H), z(4, H), z(4), z(1, H), z(1), zi, z(B), z(B), z(B), _loss_cfg(), dh=z(B, 2 * H), dWa=z(4, H),
+                            dba=z(4), dWc=z(1, H), dbc=z(1), workspace=ops.ppo_heads_workspace(256, 4), M=B)
+
+
 # ------------------------------------------------------------------------------------------------ dense layers
 @pytest.mark.parametrize("M,N,K,act", [(16384, 256, 256, 1), (4096, 512, 256, 1), (4096, 256, 8, 1), (333, 70, 19, 2),
                                        (4096, 4, 256, 0), (4096, 1, 256, 0), (128, 256, 3, 2), (64, 2, 256, 0), (1, 256, 8, 1)])
@@ -365,11 +435,13 @@ def test_random_permutation_is_bijection(ops, n):
 from conftest import trainer_from_golden as _trainer_from_golden  # noqa: E402
 
 
-def test_ppo_update_gradients_match_reference(golden):
+@pytest.mark.parametrize("fused_heads", [True, False])
+def test_ppo_update_gradients_match_reference(golden, fused_heads):
     """Forward + fused loss + backward of the whole ActorCritic against the reference's autograd gradients
-    (PPOTrainer.update with one full-batch minibatch, unclipped)."""
+    (PPOTrainer.update with one full-batch minibatch, unclipped), through the one-sweep heads kernel and the separate ones."""
     g = golden("ppo_update.npz")
     t = _trainer_from_golden(g, use_graph=False, n_mb=1)
+    t.cfg.fused_heads = fused_heads
     t.cfg.max_grad_norm = 1e9
     t.optimizer.param_groups[0]["lr"] = 0.0
     met = t.update(float(g["next_value"]))
