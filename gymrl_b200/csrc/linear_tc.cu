@@ -32,8 +32,31 @@ extern "C" int gymrl_debug_tc_timeline(long long* d_buf) {
     return cudaMemcpyToSymbol(g_tc_dbg, &d_buf, sizeof(d_buf)) == cudaSuccess ? 0 : -1;
 }
 #define TC_STAMP(slot) do { if (dbg) dbg[(slot)] = clock64(); } while (0)
+// per-CTA wall-clock probe: thread 0 of every CTA stamps %globaltimer (ns) at entry / TMEM ready / mainloop end /
+// accumulator ready / epilogue end / exit, plus its SM id -> 8 slots per CTA
+__device__ long long* g_tc_cta_dbg = nullptr;
+extern "C" int gymrl_debug_tc_cta_times(long long* d_buf) {
+    return cudaMemcpyToSymbol(g_tc_cta_dbg, &d_buf, sizeof(d_buf)) == cudaSuccess ? 0 : -1;
+}
+__device__ __forceinline__ long long globaltimer_ns() {
+    long long v;
+    asm volatile("mov.u64 %0, %%globaltimer;" : "=l"(v));
+    return v;
+}
+#define TC_GSTAMP(slot) do { if (cdbg) cdbg[(slot)] = globaltimer_ns(); } while (0)
 
 __device__ __forceinline__ uint32_t smem_u32(const void* p) { return (uint32_t)__cvta_generic_to_shared(p); }
+
+// Explicit shared-state-space accesses: the stage ring is reached through a pointer that was aligned by integer
+// arithmetic, so the compiler no longer knows its address space and emits generic ST.E / LD.E for plain dereferences.
+__device__ __forceinline__ void sts128(uint32_t addr, const uint4 v) {
+    asm volatile("st.shared.v4.b32 [%0], {%1, %2, %3, %4};" ::"r"(addr), "r"(v.x), "r"(v.y), "r"(v.z), "r"(v.w));
+}
+__device__ __forceinline__ float4 lds128(uint32_t addr) {
+    float4 v;
+    asm volatile("ld.shared.v4.f32 {%0, %1, %2, %3}, [%4];" : "=f"(v.x), "=f"(v.y), "=f"(v.z), "=f"(v.w) : "r"(addr));
+    return v;
+}
 
 __device__ __forceinline__ void mbar_init(uint64_t* bar, uint32_t count) {
     asm volatile("mbarrier.init.shared::cta.b64 [%0], %1;" ::"r"(smem_u32(bar)), "r"(count));
@@ -149,17 +172,110 @@ struct Stager {
             k += 32;
         }
     }
-    __device__ __forceinline__ void store(uint8_t* s_hi, uint8_t* s_lo, const float4 (&v)[PASSES]) const {
+    __device__ __forceinline__ void store(uint32_t s_hi, uint32_t s_lo, const float4 (&v)[PASSES]) const {
         constexpr uint32_t STRIDE = KMAJOR ? (uint32_t)(TC_THREADS / 64) * 1024u : (uint32_t)(KSTEP / 4) * (ROWS / 32) * 512u;
 #pragma unroll
         for (int i = 0; i < PASSES; ++i) {
             uint4 hi, lo;
             split4(v[i], hi, lo);
-            *reinterpret_cast<uint4*>(s_hi + soff + STRIDE * i) = hi;
-            *reinterpret_cast<uint4*>(s_lo + soff + STRIDE * i) = lo;
+            sts128(s_hi + soff + STRIDE * i, hi);
+            sts128(s_lo + soff + STRIDE * i, lo);
         }
     }
 };
+
+// ---- epilogue: TMEM -> registers -> per-warp smem transpose -> coalesced global -------------------------------------
+// A thread owns one accumulator row (32 contiguous columns per tcgen05.ld): storing that directly makes every STG touch
+// 32 different lines.  Each warp transposes its 32x32 block through a private, XOR-swizzled 4 KB scratch so that 8 lanes
+// cover one 128 B row segment -> 4 full lines per STG.128.  The activation variant is a template parameter: with it as a
+// run-time value the eight row groups of a chunk were separated by branches and ran strictly one after the other
+// (LD -> tanh chain -> STG, ~200 cycles each; 1.7-2.2k cycles per chunk measured); branch-free they are issued together.
+enum { EPI_PLAIN = 0, EPI_TANH, EPI_RELU, EPI_DTANH, EPI_DRELU, EPI_GENERIC };
+struct EpiArgs {
+    uint32_t scr, tmem_row;
+    int lane, c_begin, c_end, m_base, n0;
+    float* C;
+    bool have_acc;
+    long long* dbg;
+};
+template <int MODE>
+__device__ __forceinline__ float epi_apply(float v, float h, int act, int act_in, bool has_h) {
+    if (MODE == EPI_TANH) return tanh_fast(v);
+    if (MODE == EPI_RELU) return fmaxf(v, 0.f);
+    if (MODE == EPI_DTANH) return v * (1.0f - h * h);
+    if (MODE == EPI_DRELU) return h > 0.f ? v : 0.f;
+    if (MODE == EPI_GENERIC) {
+        if (act == GYMRL_ACT_TANH) v = tanh_fast(v);
+        else if (act == GYMRL_ACT_RELU) v = fmaxf(v, 0.f);
+        if (has_h) {
+            if (act_in == GYMRL_ACT_TANH) v *= (1.0f - h * h);
+            else if (act_in == GYMRL_ACT_RELU) v = h > 0.f ? v : 0.f;
+        }
+    }
+    return v;
+}
+template <int MODE>
+__device__ __forceinline__ void epilogue_chunks(const TcGemmParams& p, const EpiArgs& ea) {
+    constexpr bool USE_H = MODE == EPI_DTANH || MODE == EPI_DRELU || MODE == EPI_GENERIC;
+    long long* dbg = ea.dbg;
+    const int lane = ea.lane, cq = lane & 7, rsub = lane >> 3;
+    const bool has_h = USE_H && p.H != nullptr;
+#pragma unroll 1
+    for (int c0 = ea.c_begin; c0 < ea.c_end; c0 += 32) {
+        uint32_t r[32];
+        const uint32_t taddr = ea.tmem_row + (uint32_t)c0;
+        asm volatile(
+            "tcgen05.ld.sync.aligned.32x32b.x32.b32 "
+            "{%0, %1, %2, %3, %4, %5, %6, %7, %8, %9, %10, %11, %12, %13, %14, %15, "
+            "%16, %17, %18, %19, %20, %21, %22, %23, %24, %25, %26, %27, %28, %29, %30, %31}, [%32];"
+            : "=r"(r[0]), "=r"(r[1]), "=r"(r[2]), "=r"(r[3]), "=r"(r[4]), "=r"(r[5]), "=r"(r[6]), "=r"(r[7]), "=r"(r[8]), "=r"(r[9]),
+              "=r"(r[10]), "=r"(r[11]), "=r"(r[12]), "=r"(r[13]), "=r"(r[14]), "=r"(r[15]), "=r"(r[16]), "=r"(r[17]), "=r"(r[18]),
+              "=r"(r[19]), "=r"(r[20]), "=r"(r[21]), "=r"(r[22]), "=r"(r[23]), "=r"(r[24]), "=r"(r[25]), "=r"(r[26]), "=r"(r[27]),
+              "=r"(r[28]), "=r"(r[29]), "=r"(r[30]), "=r"(r[31])
+            : "r"(taddr));
+        // this lane's output columns after the transpose (same for all 8 row groups): bias loaded once per chunk
+        const int n = ea.n0 + c0 + cq * 4;
+        const bool n_ok = n < p.N;
+        const float4 b4 = (p.bias && n_ok) ? __ldg(reinterpret_cast<const float4*>(p.bias + n)) : make_float4(0.f, 0.f, 0.f, 0.f);
+        float4 h4[8];
+        if (has_h) {   // issued before the TMEM wait: the L2 latency of the h tile hides behind the transpose
+#pragma unroll
+            for (int j = 0; j < 8; ++j) {
+                const int m = min(ea.m_base + j * 4 + rsub, p.M - 1);
+                h4[j] = n_ok ? __ldg(reinterpret_cast<const float4*>(p.H + (long long)m * p.ldh + n)) : make_float4(0.f, 0.f, 0.f, 0.f);
+            }
+        }
+        asm volatile("tcgen05.wait::ld.sync.aligned;" ::: "memory");
+        TC_STAMP(300 + (c0 >> 5) * 4 + 0);
+#pragma unroll
+        for (int q = 0; q < 8; ++q)
+            sts128(ea.scr + lane * 128 + ((q ^ (lane & 7)) << 4),
+                   ea.have_acc ? make_uint4(r[q * 4], r[q * 4 + 1], r[q * 4 + 2], r[q * 4 + 3]) : make_uint4(0u, 0u, 0u, 0u));
+        __syncwarp();
+        TC_STAMP(300 + (c0 >> 5) * 4 + 1);
+        float4 a4[8];
+#pragma unroll
+        for (int j = 0; j < 8; ++j) {
+            const int row = j * 4 + rsub;
+            a4[j] = lds128(ea.scr + row * 128 + ((cq ^ (row & 7)) << 4));
+        }
+#pragma unroll
+        for (int j = 0; j < 8; ++j) {
+            const float4 hh = has_h ? h4[j] : make_float4(0.f, 0.f, 0.f, 0.f);
+            a4[j].x = epi_apply<MODE>(a4[j].x + b4.x, hh.x, p.act, p.act_in, has_h);
+            a4[j].y = epi_apply<MODE>(a4[j].y + b4.y, hh.y, p.act, p.act_in, has_h);
+            a4[j].z = epi_apply<MODE>(a4[j].z + b4.z, hh.z, p.act, p.act_in, has_h);
+            a4[j].w = epi_apply<MODE>(a4[j].w + b4.w, hh.w, p.act, p.act_in, has_h);
+        }
+#pragma unroll
+        for (int j = 0; j < 8; ++j) {
+            const int m = ea.m_base + j * 4 + rsub;
+            if (m < p.M && n_ok) *reinterpret_cast<float4*>(ea.C + (long long)m * p.ldc + n) = a4[j];
+        }
+        TC_STAMP(300 + (c0 >> 5) * 4 + 2);
+        __syncwarp();   // the scratch is rewritten by the next chunk
+    }
+}
 
 #define TC_LAUNCH_THREADS (TC_THREADS + 32)   // 8 producer / epilogue warps + 1 MMA-issue warp
 
@@ -182,6 +298,9 @@ __global__ void __launch_bounds__(TC_LAUNCH_THREADS, 1) gemm_tf32x3_kernel(const
 
     const int t = threadIdx.x, warp = t >> 5, lane = t & 31;
     const int m0 = blockIdx.y * BM, n0 = blockIdx.x * BN;
+    long long* cdbg = (g_tc_cta_dbg && t == 0) ? g_tc_cta_dbg + 8ll * (blockIdx.x + gridDim.x * (blockIdx.y + gridDim.y * blockIdx.z)) : nullptr;
+    TC_GSTAMP(0);
+    if (cdbg) { uint32_t smid; asm volatile("mov.u32 %0, %%smid;" : "=r"(smid)); cdbg[6] = smid; }
     const int kbeg = blockIdx.z * p.k_chunk;
     const int kend = min(p.K, kbeg + p.k_chunk);
     const int nslab = (kend - kbeg + 31) / 32;
@@ -205,6 +324,7 @@ __global__ void __launch_bounds__(TC_LAUNCH_THREADS, 1) gemm_tf32x3_kernel(const
 
     long long* dbg = (g_tc_dbg && blockIdx.x == 0 && blockIdx.y == 0 && blockIdx.z == 0 && (t == 0 || t == TC_THREADS)) ? g_tc_dbg + (t ? 512 : 0) : nullptr;
     TC_STAMP(0);
+    TC_GSTAMP(1);
 
     if (warp == TC_THREADS / 32) {
         // ===== MMA-issue warp: one elected lane feeds the tensor core; issuing blocks for about the duration of the
@@ -240,6 +360,7 @@ __global__ void __launch_bounds__(TC_LAUNCH_THREADS, 1) gemm_tf32x3_kernel(const
         }
     } else {
         // ===== producer warps: global -> registers -> hi/lo tf32 images in the stage ring; then the epilogue =====
+        const uint32_t smem_base = smem_u32(smem);
         Stager<BM, A_KMAJOR> sa;
         Stager<BN, B_KMAJOR> sb;
         sa.init(p.A, p.lda, p.a_rows, m0, p.M, kbeg);
@@ -255,7 +376,7 @@ __global__ void __launch_bounds__(TC_LAUNCH_THREADS, 1) gemm_tf32x3_kernel(const
             TC_STAMP(8 + kb * 8 + 0);
             if (use >= 1) mbar_wait(&bar_free[s], (uint32_t)((use - 1) & 1));   // MMAs that read this stage have retired
             TC_STAMP(8 + kb * 8 + 1);
-            uint8_t* st = smem + (size_t)s * STAGE_BYTES;
+            const uint32_t st = smem_base + (uint32_t)s * STAGE_BYTES;
             sa.store(st, st + A_BYTES, va);
             sb.store(st + 2 * A_BYTES, st + 2 * A_BYTES + B_BYTES, vb);
             if (!A_KMAJOR && do_colsum) {   // db rides along with dW: the dY slab is already in registers
@@ -300,8 +421,10 @@ __global__ void __launch_bounds__(TC_LAUNCH_THREADS, 1) gemm_tf32x3_kernel(const
 
         // ---- epilogue: TMEM -> registers -> smem transpose -> coalesced global ----
         TC_STAMP(1);
+        TC_GSTAMP(2);
         if (nslab > 0) mbar_wait(&bar_acc, 0);
         TC_STAMP(2);
+        TC_GSTAMP(3);
         asm volatile("tcgen05.fence::after_thread_sync;" ::: "memory");
         // all MMAs have retired: the operand stages are free to reuse as scratch
         if (!A_KMAJOR && do_colsum) {
@@ -323,69 +446,29 @@ __global__ void __launch_bounds__(TC_LAUNCH_THREADS, 1) gemm_tf32x3_kernel(const
         // through a private, XOR-swizzled 4 KB scratch so that 8 lanes cover one 128 B row segment -> 4 lines per STG.
         // (Prefetching the next chunk's tcgen05.ld while the current one is stored was tried and measured 8-20 % slower
         // on the same box, so the chunks stay strictly sequential.)
-        uint8_t* scr = smem + (size_t)warp * 4096;
-        const int cq = lane & 7, rsub = lane >> 3;
-#pragma unroll 1
-        for (int c0 = col_half * (BN / 2); c0 < (col_half + 1) * (BN / 2); c0 += 32) {
-            uint32_t r[32];
-            const uint32_t taddr = tmem_d + ((uint32_t)(lane_q * 32) << 16) + (uint32_t)c0;
-            asm volatile(
-                "tcgen05.ld.sync.aligned.32x32b.x32.b32 "
-                "{%0, %1, %2, %3, %4, %5, %6, %7, %8, %9, %10, %11, %12, %13, %14, %15, "
-                "%16, %17, %18, %19, %20, %21, %22, %23, %24, %25, %26, %27, %28, %29, %30, %31}, [%32];"
-                : "=r"(r[0]), "=r"(r[1]), "=r"(r[2]), "=r"(r[3]), "=r"(r[4]), "=r"(r[5]), "=r"(r[6]), "=r"(r[7]), "=r"(r[8]), "=r"(r[9]),
-                  "=r"(r[10]), "=r"(r[11]), "=r"(r[12]), "=r"(r[13]), "=r"(r[14]), "=r"(r[15]), "=r"(r[16]), "=r"(r[17]), "=r"(r[18]),
-                  "=r"(r[19]), "=r"(r[20]), "=r"(r[21]), "=r"(r[22]), "=r"(r[23]), "=r"(r[24]), "=r"(r[25]), "=r"(r[26]), "=r"(r[27]),
-                  "=r"(r[28]), "=r"(r[29]), "=r"(r[30]), "=r"(r[31])
-                : "r"(taddr));
-            // this lane's output columns after the transpose (same for all 8 row groups): bias loaded once per chunk
-            const int n = n0 + c0 + cq * 4;
-            const bool n_ok = n < p.N;
-            const float4 b4 = (p.bias && n_ok) ? __ldg(reinterpret_cast<const float4*>(p.bias + n)) : make_float4(0.f, 0.f, 0.f, 0.f);
-            asm volatile("tcgen05.wait::ld.sync.aligned;" ::: "memory");
-#pragma unroll
-            for (int q = 0; q < 8; ++q)
-                *reinterpret_cast<uint4*>(scr + lane * 128 + ((q ^ (lane & 7)) << 4)) =
-                    nslab > 0 ? make_uint4(r[q * 4], r[q * 4 + 1], r[q * 4 + 2], r[q * 4 + 3]) : make_uint4(0u, 0u, 0u, 0u);
-            __syncwarp();
-            float4 h4[8];
-            if (p.H) {
-#pragma unroll
-                for (int j = 0; j < 8; ++j) {
-                    const int m = m0 + lane_q * 32 + j * 4 + rsub;
-                    if (m < p.M && n_ok) h4[j] = __ldg(reinterpret_cast<const float4*>(p.H + (long long)m * p.ldh + n));
-                }
-            }
-#pragma unroll
-            for (int j = 0; j < 8; ++j) {
-                const int row = j * 4 + rsub;
-                const int m = m0 + lane_q * 32 + row;
-                const float4 a4 = *reinterpret_cast<const float4*>(scr + row * 128 + ((cq ^ (row & 7)) << 4));
-                if (m >= p.M || !n_ok) continue;
-                const float acc[4] = {a4.x, a4.y, a4.z, a4.w};
-                const float bq[4] = {b4.x, b4.y, b4.z, b4.w};
-                const float hq[4] = {h4[j].x, h4[j].y, h4[j].z, h4[j].w};
-                float o[4];
-#pragma unroll
-                for (int e = 0; e < 4; ++e) {
-                    float v = acc[e] + bq[e];
-                    if (p.act == GYMRL_ACT_TANH) v = tanh_fast(v);
-                    else if (p.act == GYMRL_ACT_RELU) v = fmaxf(v, 0.f);
-                    if (p.H) {
-                        const float h = hq[e];
-                        if (p.act_in == GYMRL_ACT_TANH) v *= (1.0f - h * h);
-                        else if (p.act_in == GYMRL_ACT_RELU) v = h > 0.f ? v : 0.f;
-                    }
-                    o[e] = v;
-                }
-                *reinterpret_cast<float4*>(Cbase + (long long)m * p.ldc + n) = make_float4(o[0], o[1], o[2], o[3]);
-            }
-            __syncwarp();   // the scratch is rewritten by the next chunk
+        const uint32_t scr = smem_base + (uint32_t)warp * 4096u;
+        EpiArgs ea;
+        ea.scr = scr; ea.tmem_row = tmem_d + ((uint32_t)(lane_q * 32) << 16); ea.lane = lane;
+        ea.c_begin = col_half * (BN / 2); ea.c_end = (col_half + 1) * (BN / 2);
+        ea.m_base = m0 + lane_q * 32; ea.n0 = n0; ea.C = Cbase; ea.have_acc = nslab > 0; ea.dbg = dbg;
+        // the activation / derivative variant is uniform over the launch: pick a branch-free instantiation once
+        if (p.H == nullptr) {
+            if (p.act == GYMRL_ACT_TANH) epilogue_chunks<EPI_TANH>(p, ea);
+            else if (p.act == GYMRL_ACT_RELU) epilogue_chunks<EPI_RELU>(p, ea);
+            else epilogue_chunks<EPI_PLAIN>(p, ea);
+        } else if (p.act == GYMRL_ACT_NONE && p.act_in == GYMRL_ACT_TANH) {
+            epilogue_chunks<EPI_DTANH>(p, ea);
+        } else if (p.act == GYMRL_ACT_NONE && p.act_in == GYMRL_ACT_RELU) {
+            epilogue_chunks<EPI_DRELU>(p, ea);
+        } else {
+            epilogue_chunks<EPI_GENERIC>(p, ea);
         }
         TC_STAMP(3);
+        TC_GSTAMP(4);
     }
     asm volatile("tcgen05.fence::before_thread_sync;" ::: "memory");
     __syncthreads();
+    TC_GSTAMP(5);
     if (warp == 0) {
         asm volatile("tcgen05.dealloc.cta_group::1.sync.aligned.b32 %0, %1;" ::"r"(tmem_d), "n"(BN) : "memory");
     }

@@ -38,6 +38,13 @@ def main():
             s = t[8 + kb * 8: 8 + kb * 8 + 3]
             d = [s[0] - t0] + [s[i] - s[i - 1] for i in range(1, 3)]
             print(f"  {kb:2d}: {d[0]:7d} {d[1]:7d} {d[2]:7d}")
+        if off == 0:
+            print(" epilogue chunk (thread 0): tcgen05.ld done (since acc ready / previous chunk end), +STS+syncwarp, +LDS/math/STG issue")
+            prev = t[2]
+            for c in range(4):
+                s = t[300 + c * 4: 300 + c * 4 + 3]
+                print(f"  chunk {c}: {s[0] - prev:7d} {s[1] - s[0]:7d} {s[2] - s[1]:7d}")
+                prev = s[2]
 
 
 if __name__ == "__main__":
