@@ -328,7 +328,7 @@ class PPOTrainer(base.PPOTrainer):
     def _loss_step(self, acts):
         buf, A = self.buffer, self.env.n_actions
         ops.ppo_loss(acts.lv[:, :A], acts.lv[:, A:A + 1], buf.action.view(-1), buf.log_prob.view(-1), buf.adv.view(-1),
-                     buf.ret.view(-1), self.loss_cfg, row_index=self.idx_mb, entropy_old=buf.entropy.view(-1),
+                     buf.ret.view(-1), self.loss_cfg, row_index=self._idx_cur, entropy_old=buf.entropy.view(-1),
                      dlogits=acts.dlv[:, :A], dvalue=acts.dlv[:, A:A + 1], metrics=self.metrics)
 
     # ---- the reference's method names
@@ -348,20 +348,7 @@ class PPOTrainer(base.PPOTrainer):
             buf.adv.copy_(torch.as_tensor(advantages, dtype=f32, device=self.device).view_as(buf.adv))
         if returns is not None and returns.data_ptr() != buf.ret.data_ptr():
             buf.ret.copy_(torch.as_tensor(returns, dtype=f32, device=self.device).view_as(buf.ret))
-        self.optimizer.sync_lr()
-        self._ensure_update_graphs()
-        self.metrics.zero_()
-        for _ in range(cfg.num_epochs):
-            ops.random_permutation(self.N * self.T, seed=self.seed + 7919 * self.rank, draw_base=self.ctr_perm, out=self.perm)
-            ops.counter_add(self.ctr_perm, 1)
-            self.ctr_mb.zero_()
-            for _ in range(self.n_mb):
-                if self.world == 1:
-                    self._replay(self._g_mb) if self._g_mb is not None else self._minibatch_body()
-                else:
-                    self._replay(self._g_mb_bwd) if self._g_mb_bwd is not None else self._fwd_bwd_body()
-                    gdist.allreduce_sum_(self.net.fp.grad)
-                    self._replay(self._g_opt) if self._g_opt is not None else self._opt_body()
+        self._run_epochs()
         if cfg.anneal:   # after the update, from the post-rollout step count
             frac = 1 - self.step_count / cfg.max_train_steps
             self.lr = cfg.lr * frac

@@ -133,6 +133,8 @@ class ActorCriticEngine:
         self.gWa2, self.gba2 = fp.g("actor.2.weight"), fp.g("actor.2.bias")
         self.gWc2, self.gbc2 = fp.g("critic.2.weight"), fp.g("critic.2.bias")
         self.workspace = None
+        self.ws_layers = None
+        self.deferred_reduce = True   # forward_trunk/backward may run inside an ops.reduce_defer_begin() scope
         # heads + loss + heads backward as one sweep (gymrl_ppo_heads_fused) where the kernel is built for the shape
         self.can_fuse_heads = self.A == 4 and self.H in (128, 256)
 
@@ -142,6 +144,13 @@ class ActorCriticEngine:
         if self.can_fuse_heads:
             need = max(need, ops.ppo_heads_workspace_bytes(self.H, self.A))
         self.workspace = torch.empty(need, device=self.fp.flat.device, dtype=torch.uint8)
+        # one workspace per backward call of a minibatch, so their partial sums can be folded together at the end
+        # (ops.reduce_defer_begin / reduce_flush): [heads (or actor head), critic head, head trunks, shared.2, shared.0]
+        dev = self.fp.flat.device
+        heads = max(ops.backward_weight_workspace(M, self.A, self.H), ops.ppo_heads_workspace_bytes(self.H, self.A) if self.can_fuse_heads else 0)
+        sizes = [heads, ops.backward_weight_workspace(M, 1, self.H), ops.backward_weight_workspace(M, 2 * self.H, self.H),
+                 ops.backward_weight_workspace(M, self.H, self.H), ops.backward_weight_workspace(M, self.H, self.D)]
+        self.ws_layers = [torch.empty(s, device=dev, dtype=torch.uint8) for s in sizes]
 
     def forward_trunk(self, x: torch.Tensor, acts: _Acts, M: int, row_index: Optional[torch.Tensor] = None):
         """acts.ac[:M] = (actor | critic) head-trunk activations."""
@@ -160,24 +169,24 @@ class ActorCriticEngine:
 
     def backward(self, x: torch.Tensor, acts: _Acts, M: int, row_index: Optional[torch.Tensor] = None):
         """Given acts.dlv[:M] = dL/d(logits, value), fill the flat gradient buffer."""
-        T, H, A, ws = _ffi.ACT_TANH, self.H, self.A, self.workspace
+        T, H, A, ws = _ffi.ACT_TANH, self.H, self.A, self.ws_layers
         dl, dv = acts.dlv[:, :A], acts.dlv[:, A:A + 1]
-        ops.linear_backward(dl, acts.ac[:, :H], self.Wa2, self.gWa2, self.gba2, dx=acts.dac[:, :H], act_in=T, workspace=ws, M=M)
-        ops.linear_backward(dv, acts.ac[:, H:], self.Wc2, self.gWc2, self.gbc2, dx=acts.dac[:, H:], act_in=T, workspace=ws, M=M)
+        ops.linear_backward(dl, acts.ac[:, :H], self.Wa2, self.gWa2, self.gba2, dx=acts.dac[:, :H], act_in=T, workspace=ws[0], M=M)
+        ops.linear_backward(dv, acts.ac[:, H:], self.Wc2, self.gWc2, self.gbc2, dx=acts.dac[:, H:], act_in=T, workspace=ws[1], M=M)
         self.backward_trunk(x, acts, M, row_index)
 
     def backward_trunk(self, x: torch.Tensor, acts: _Acts, M: int, row_index: Optional[torch.Tensor] = None):
         """Given acts.dac[:M] = dL/d(pre-activation of the head trunks), fill the gradients of the three trunk layers."""
-        T, ws = _ffi.ACT_TANH, self.workspace
-        ops.linear_backward(acts.dac, acts.h2, self.Wac, self.gWac, self.gbac, dx=acts.dh2, act_in=T, workspace=ws, M=M)
-        ops.linear_backward(acts.dh2, acts.h1, self.W2, self.gW2, self.gb2, dx=acts.dh1, act_in=T, workspace=ws, M=M)
-        ops.linear_backward(acts.dh1, x, self.W1, self.gW1, self.gb1, row_index=row_index, workspace=ws, M=M)
+        T, ws = _ffi.ACT_TANH, self.ws_layers
+        ops.linear_backward(acts.dac, acts.h2, self.Wac, self.gWac, self.gbac, dx=acts.dh2, act_in=T, workspace=ws[2], M=M)
+        ops.linear_backward(acts.dh2, acts.h1, self.W2, self.gW2, self.gb2, dx=acts.dh1, act_in=T, workspace=ws[3], M=M)
+        ops.linear_backward(acts.dh1, x, self.W1, self.gW1, self.gb1, row_index=row_index, workspace=ws[4], M=M)
 
     def heads_loss_backward(self, acts: _Acts, M: int, action, logp_old, adv, ret, loss_cfg, *, row_index=None, metrics=None,
                             lv_out=None):
         """Output heads, PPO loss and heads backward in one sweep over acts.ac: fills acts.dac and the head gradients."""
         ops.ppo_heads_fused(acts.ac, self.Wa2, self.ba2, self.Wc2, self.bc2, action, logp_old, adv, ret, loss_cfg,
-                            dh=acts.dac, dWa=self.gWa2, dba=self.gba2, dWc=self.gWc2, dbc=self.gbc2, workspace=self.workspace,
+                            dh=acts.dac, dWa=self.gWa2, dba=self.gba2, dWc=self.gWc2, dbc=self.gbc2, workspace=self.ws_layers[0],
                             M=M, row_index=row_index, act_in=_ffi.ACT_TANH, lv_out=lv_out, metrics=metrics)
 
 
@@ -221,6 +230,8 @@ class RolloutBuffer:
 
 
 class PPOTrainer:
+    MAX_EPOCH_GRAPH_MINIBATCHES = 64   # beyond this one minibatch graph is replayed with a device-side window counter
+
     def __init__(self, config: Config):
         _ffi.require_cuda()
         self.cfg = cfg = config
@@ -260,6 +271,9 @@ class PPOTrainer:
         self._episodes_seen = 0
         self._g_roll = None
         self._g_mb = None
+        self._g_epoch = None
+        self._n_sumsq = 0
+        self._idx_cur = self.idx_mb
         self._g_mb_bwd = None
         self._g_opt = None
         self._started = False
@@ -291,7 +305,7 @@ class PPOTrainer:
     def _loss_step(self, acts):
         buf, A = self.buffer, self.env.n_actions
         ops.ppo_loss(acts.lv[:, :A], acts.lv[:, A:A + 1], buf.action.view(-1), buf.log_prob.view(-1), buf.adv.view(-1),
-                     buf.ret.view(-1), self.loss_cfg, row_index=self.idx_mb, dlogits=acts.dlv[:, :A],
+                     buf.ret.view(-1), self.loss_cfg, row_index=self._idx_cur, dlogits=acts.dlv[:, :A],
                      dvalue=acts.dlv[:, A:A + 1], metrics=self.metrics)
 
     # ---------------------------------------------------------------- rollout
@@ -342,28 +356,56 @@ class PPOTrainer:
         return buf.adv, buf.ret
 
     # ---------------------------------------------------------------- update
-    def _fwd_bwd_body(self):
+    def _fwd_bwd_body(self, window: Optional[int] = None):
+        """Forward + loss + backward of one minibatch.  `window` = static index of the minibatch inside the epoch's
+        permutation (the row indices are then a view of self.perm); None = the window the device counter ctr_mb points
+        at, copied into idx_mb (lets ONE captured graph walk through the epoch)."""
         buf, net, acts = self.buffer, self.net, self.acts_mb
         A, M = self.env.n_actions, self.mb
         obs_flat = buf.obs[:self.T].view(self.T * self.N, -1)
-        ops.slice_i32(self.idx_mb, self.perm, self.ctr_mb)
-        ops.counter_add(self.ctr_mb, 1)
-        if getattr(self.cfg, "fused_heads", True) and getattr(net, "can_fuse_heads", False):
-            net.forward_trunk(obs_flat, acts, M, row_index=self.idx_mb)
-            net.heads_loss_backward(acts, M, buf.action.view(-1), buf.log_prob.view(-1), buf.adv.view(-1), buf.ret.view(-1),
-                                    self.loss_cfg, row_index=self.idx_mb, metrics=self.metrics)
-            net.backward_trunk(obs_flat, acts, M, row_index=self.idx_mb)
+        if window is None:
+            ops.slice_i32(self.idx_mb, self.perm, self.ctr_mb)
+            ops.counter_add(self.ctr_mb, 1)
+            idx = self.idx_mb
         else:
-            net.forward(obs_flat, acts, M, row_index=self.idx_mb)
-            self._loss_step(acts)
-            net.backward(obs_flat, acts, M, row_index=self.idx_mb)
+            idx = self.perm[window * M:(window + 1) * M]
+        self._idx_cur = idx
+        defer = getattr(net, "deferred_reduce", False)
+        if defer:
+            ops.reduce_defer_begin()   # the layers' partial-gradient folds run as one launch at the end
+        self._n_sumsq = 0
+        try:
+            if getattr(self.cfg, "fused_heads", True) and getattr(net, "can_fuse_heads", False):
+                net.forward_trunk(obs_flat, acts, M, row_index=idx)
+                net.heads_loss_backward(acts, M, buf.action.view(-1), buf.log_prob.view(-1), buf.adv.view(-1), buf.ret.view(-1),
+                                        self.loss_cfg, row_index=idx, metrics=self.metrics)
+                net.backward_trunk(obs_flat, acts, M, row_index=idx)
+            else:
+                net.forward(obs_flat, acts, M, row_index=idx)
+                self._loss_step(acts)
+                net.backward(obs_flat, acts, M, row_index=idx)
+        finally:
+            if defer:
+                # single GPU: the fold also leaves the sums of squares for the clip (every gradient passes through it)
+                fuse_norm = self.world == 1 and self.cfg.max_grad_norm > 0
+                n, covered = ops.reduce_flush(self.optimizer.sumsq_partials if fuse_norm else None)
+                if fuse_norm:
+                    assert covered == self.net.fp.n_params(), "the merged fold must produce every gradient element for the fused clip"
+                    self._n_sumsq = n
 
     def _opt_body(self):
-        self.optimizer.launch(max_norm=self.cfg.max_grad_norm, grad_scale=1.0 / self.world)
+        if self._n_sumsq > 0:
+            self.optimizer.launch_clipped(self._n_sumsq, max_norm=self.cfg.max_grad_norm, grad_scale=1.0 / self.world)
+        else:
+            self.optimizer.launch(max_norm=self.cfg.max_grad_norm, grad_scale=1.0 / self.world)
 
-    def _minibatch_body(self):
-        self._fwd_bwd_body()
+    def _minibatch_body(self, window: Optional[int] = None):
+        self._fwd_bwd_body(window)
         self._opt_body()
+
+    def _epoch_body(self):
+        for w in range(self.n_mb):
+            self._minibatch_body(w)
 
     def _capture(self, fn):
         torch.cuda.synchronize()
@@ -395,10 +437,13 @@ class PPOTrainer:
         self.metrics.copy_(s["metrics"])
 
     def _ensure_update_graphs(self):
-        if not self.cfg.use_cuda_graph or self._g_mb is not None or self._g_mb_bwd is not None:
+        if not self.cfg.use_cuda_graph or self._g_mb is not None or self._g_mb_bwd is not None or self._g_epoch is not None:
             return
         snap = self._snapshot()  # capture warm-ups execute real steps: undo them
-        if self.world == 1:
+        if self.world == 1 and self.n_mb <= self.MAX_EPOCH_GRAPH_MINIBATCHES:
+            # a whole epoch as one graph: every minibatch reads its window of the permutation through a static view
+            self._g_epoch = self._capture(self._epoch_body)
+        elif self.world == 1:
             self._g_mb = self._capture(self._minibatch_body)
         else:
             self._g_mb_bwd = self._capture(self._fwd_bwd_body)
@@ -408,15 +453,10 @@ class PPOTrainer:
     def total_launches(self) -> int:
         return _ffi.launch_count() + self.graph_launches
 
-    def update(self, next_value=None, read_metrics: bool = True) -> dict:
-        cfg, buf = self.cfg, self.buffer
-        adv, _ = self.compute_gae(next_value)
-        # advantage normalisation, numpy semantics (ddof = 0, ref :236); global over all shards
-        self.adv_sums.zero_()
-        ops.sum_sumsq(adv, self.adv_sums[:2])
-        count = gdist.global_moments_(self.adv_sums, adv.numel())
-        ops.normalize_inplace(adv, self.adv_sums, count, ddof=0, eps=1e-8)
-
+    def _run_epochs(self):
+        """num_epochs passes over the rollout in shuffled minibatches (ref :258-330): per epoch one device permutation, then
+        either one graph replay for the whole epoch, one per minibatch, or (multi-GPU) backward / all-reduce / optimiser."""
+        cfg = self.cfg
         self.optimizer.sync_lr()
         self._ensure_update_graphs()
         self.metrics.zero_()
@@ -424,6 +464,9 @@ class PPOTrainer:
             ops.random_permutation(self.N * self.T, seed=self.seed + 7919 * self.rank, draw_base=self.ctr_perm, out=self.perm)
             ops.counter_add(self.ctr_perm, 1)
             self.ctr_mb.zero_()
+            if self._g_epoch is not None:
+                self._replay(self._g_epoch)
+                continue
             for _ in range(self.n_mb):
                 if self.world == 1:
                     if self._g_mb is not None:
@@ -440,6 +483,17 @@ class PPOTrainer:
                         self._replay(self._g_opt)
                     else:
                         self._opt_body()
+
+    def update(self, next_value=None, read_metrics: bool = True) -> dict:
+        cfg, buf = self.cfg, self.buffer
+        adv, _ = self.compute_gae(next_value)
+        # advantage normalisation, numpy semantics (ddof = 0, ref :236); global over all shards
+        self.adv_sums.zero_()
+        ops.sum_sumsq(adv, self.adv_sums[:2])
+        count = gdist.global_moments_(self.adv_sums, adv.numel())
+        ops.normalize_inplace(adv, self.adv_sums, count, ddof=0, eps=1e-8)
+
+        self._run_epochs()
         if not read_metrics:
             return {}
         m = self.metrics.tolist()  # the single D2H of the update (ref: 5 .item() per minibatch, :309-322)

@@ -38,6 +38,7 @@ SOURCES = {
     "linear_tc.cu": [],
     "linear_skinny.cu": [],
     "optim.cu": [],
+    "reduce.cu": [],
     "replay.cu": [],
     "qlearn.cu": [],
     "mhc.cu": [],

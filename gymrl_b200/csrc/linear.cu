@@ -46,6 +46,7 @@ void reduce_pair(const float* part_w, long long stride_w, const float* part_b, l
                  float* out_w, float* out_b, int accumulate, cudaStream_t s);
 int smallk_dw(const float* dy, int lddy, const float* x, int ldx, const int32_t* rows, float* part_w, float* part_b, int M, int N, int K,
               int chunks, cudaStream_t s);
+int smallk_dw_chunks(const float* dy, int lddy, int M, int N);
 static int g_skinny = 1;   // GYMRL_SKINNY=0 disables the degenerate-shape kernels (debug / A-B comparison)
 
 // GEMM engine selection: 0 = fp32 FFMA tiles (this file), 1 = tcgen05 3xTF32 (linear_tc.cu) where the shape gate allows.
@@ -470,6 +471,7 @@ extern "C" int gymrl_linear_backward_weight(const float* d_dy, int lddy, const f
     if (g_skinny && ((N <= 8 && skinny_dw_supported(N)) || (N >= 32 && smallk_dw_supported(K)))) {
         int chunks = ceil_div(M, 32);
         if (chunks > 512) chunks = 512;
+        if (N > 8) chunks = smallk_dw_chunks(d_dy, lddy, M, N);
         float* part_w = ws;
         float* part_b = ws + (size_t)chunks * N * K;
         if (N <= 8) skinny_dw(d_dy, lddy, d_x, ldx, d_row_index, part_w, d_db ? part_b : nullptr, M, N, K, chunks, s);

@@ -9,6 +9,7 @@
 //   small-K dW/db      dW[N][K] = sum_m dy[m][n] x[idx[m]][k]        thread per n, row chunks -> partials -> reduce
 // fp32 FMA throughout (these are < 1 % of the flops).
 #include "common.cuh"
+#include <cstdlib>
 
 void gymrl_count_launch(int n = 1);
 
@@ -194,42 +195,125 @@ int skinny_dw(const float* dy, int lddy, const float* x, int ldx, const int32_t*
     return GYMRL_OK;
 }
 
-// ---- small-K forward: thread per output column, rows looped; W[N][K] in smem --------------------------------------------------
+// ---- small-K forward: thread per output column, rows looped; the block's x rows staged in smem once ---------------------
+// One gather per block (rows_per_block x K floats, two dependent L2 round trips when the rows are index-gathered), then every
+// thread walks the rows for its column: smem broadcast reads, K FMAs, activation, one coalesced 1 KB store per row and block.
+// (The first version staged 16 rows at a time: four gather latencies and eight barriers per block, 14.5 us at M = 16384.)
+constexpr int kSmallKRowsMax = 64;
 template <int K>
 __global__ void __launch_bounds__(256) smallk_fwd_kernel(const float* __restrict__ x, int ldx, const int32_t* __restrict__ rows,
                                                          const float* __restrict__ w, const float* __restrict__ b,
                                                          float* __restrict__ y, int ldy, int M, int N, int act, int rows_per_block) {
     const int n = blockIdx.x * blockDim.x + threadIdx.x;
+    const int m_beg = blockIdx.y * rows_per_block, m_end = min(M, m_beg + rows_per_block);
+    const int nrows = m_end - m_beg;
+    __shared__ __align__(16) float sx[kSmallKRowsMax][K];
+    for (int i = threadIdx.x; i < nrows * K; i += blockDim.x) {
+        const int mm = m_beg + i / K;
+        sx[i / K][i % K] = x[(size_t)(rows ? rows[mm] : mm) * ldx + (i % K)];
+    }
     float wr[K];
 #pragma unroll
     for (int k = 0; k < K; ++k) wr[k] = n < N ? w[(size_t)n * K + k] : 0.f;
     const float bias = (b && n < N) ? b[n] : 0.f;
-    const int m_beg = blockIdx.y * rows_per_block, m_end = min(M, m_beg + rows_per_block);
-    __shared__ float sx[16][K];
-    for (int m0 = m_beg; m0 < m_end; m0 += 16) {
-        __syncthreads();
-        for (int i = threadIdx.x; i < 16 * K; i += blockDim.x) {
-            const int mm = m0 + i / K;
-            sx[i / K][i % K] = mm < m_end ? x[(size_t)(rows ? rows[mm] : mm) * ldx + (i % K)] : 0.f;
-        }
-        __syncthreads();
-        const int lim = min(16, m_end - m0);
-        if (n < N)
-            for (int r = 0; r < lim; ++r) {
-                float acc = bias;
+    __syncthreads();
+    if (n >= N) return;
+    float* yp = y + (size_t)m_beg * ldy + n;
+    int r = 0;
+    for (; r + 4 <= nrows; r += 4) {
+        float acc[4];
 #pragma unroll
-                for (int k = 0; k < K; ++k) acc = fmaf(sx[r][k], wr[k], acc);
-                y[(size_t)(m0 + r) * ldy + n] = apply_act(acc, act);
-            }
+        for (int q = 0; q < 4; ++q) {
+            acc[q] = bias;
+#pragma unroll
+            for (int k = 0; k < K; ++k) acc[q] = fmaf(sx[r + q][k], wr[k], acc[q]);
+        }
+#pragma unroll
+        for (int q = 0; q < 4; ++q) yp[(size_t)(r + q) * ldy] = apply_act(acc[q], act);
+    }
+    for (; r < nrows; ++r) {
+        float acc = bias;
+#pragma unroll
+        for (int k = 0; k < K; ++k) acc = fmaf(sx[r][k], wr[k], acc);
+        yp[(size_t)r * ldy] = apply_act(acc, act);
     }
 }
 
+// Vector variant (N % 4 == 0, 16 B-aligned y / ldy): a thread owns 4 adjacent output columns (their 4 x K weights live in
+// registers) and walks every 4th row of the block, so one broadcast read of an x row (K floats) feeds 4K FMAs and the result
+// leaves as one STG.128.  The scalar kernel above spends 8 shared-memory reads per output element and is bound by the
+// shared-memory pipe (13.7 us for 16384 x 256 x 8); this one is bound by the activation math and the 16 MB it writes.
+template <int K>
+__global__ void __launch_bounds__(256) smallk_fwd4_kernel(const float* __restrict__ x, int ldx, const int32_t* __restrict__ rows,
+                                                          const float* __restrict__ w, const float* __restrict__ b,
+                                                          float* __restrict__ y, int ldy, int M, int N, int act, int rows_per_block) {
+    const int cg = threadIdx.x & 63, rg = threadIdx.x >> 6;      // a warp shares rg: its x-row reads are broadcasts
+    const int n = (blockIdx.x * 64 + cg) * 4;
+    const int m_beg = blockIdx.y * rows_per_block, m_end = min(M, m_beg + rows_per_block);
+    const int nrows = m_end - m_beg;
+    __shared__ __align__(16) float sx[kSmallKRowsMax][K == 3 ? 4 : K];
+    constexpr int KP = K == 3 ? 4 : K;
+    for (int i = threadIdx.x; i < nrows * K; i += blockDim.x) {
+        const int mm = m_beg + i / K;
+        sx[i / K][i % K] = x[(size_t)(rows ? rows[mm] : mm) * ldx + (i % K)];
+    }
+    // the block's 256 x K weights: coalesced into shared memory (a thread's 4 x K values are 16 K bytes apart from its
+    // neighbour's: read straight from global they cost 32 lines per load instruction), group pitch 4K+1 -> conflict-free reads
+    __shared__ float sw[64][4 * K + 1];
+    const int n_blk = blockIdx.x * 256;
+    for (int i = threadIdx.x; i < 256 * K; i += blockDim.x) {
+        const int col = i / K;
+        sw[col >> 2][(col & 3) * K + (i % K)] = (n_blk + col) < N ? w[(size_t)n_blk * K + i] : 0.f;
+    }
+    float4 bias = make_float4(0.f, 0.f, 0.f, 0.f);
+    if (n < N && b) bias = *reinterpret_cast<const float4*>(b + n);
+    __syncthreads();
+    if (n >= N) return;
+    float wr[4][K];
+#pragma unroll
+    for (int c = 0; c < 4; ++c)
+#pragma unroll
+        for (int k = 0; k < K; ++k) wr[c][k] = sw[cg][c * K + k];
+    (void)KP;
+#pragma unroll 2
+    for (int r = rg; r < nrows; r += 4) {
+        float xr[K];
+#pragma unroll
+        for (int k = 0; k < K; ++k) xr[k] = sx[r][k];
+        float o[4] = {bias.x, bias.y, bias.z, bias.w};
+#pragma unroll
+        for (int c = 0; c < 4; ++c)
+#pragma unroll
+            for (int k = 0; k < K; ++k) o[c] = fmaf(xr[k], wr[c][k], o[c]);
+        *reinterpret_cast<float4*>(y + (size_t)(m_beg + r) * ldy + n) =
+            make_float4(apply_act(o[0], act), apply_act(o[1], act), apply_act(o[2], act), apply_act(o[3], act));
+    }
+}
+
+// GYMRL_SMALLK_VEC=0 keeps the scalar small-K kernels (A/B comparison)
+static bool smallk_vec_enabled() {
+    static const bool on = [] { const char* e = getenv("GYMRL_SMALLK_VEC"); return !(e && e[0] == '0'); }();
+    return on;
+}
+static int smallk_rows_target() {
+    static const int v = [] { const char* e = getenv("GYMRL_SMALLK_BLOCKS_PER_SM"); return e ? atoi(e) : 2; }();
+    return v < 1 ? 1 : v;
+}
 bool smallk_forward_supported(int K) { return K == 3 || K == 4 || K == 8; }
 int smallk_forward(const float* x, int ldx, const int32_t* rows, const float* w, const float* b, float* y, int ldy, int M, int N, int K,
                    int act, cudaStream_t s) {
-    const int rpb = 64;
+    // two blocks per SM when M allows it (measured on B200 at 16384 x 256 x 8: 7.4 us with 2, 8.1 with 4, 8.6 with 8 blocks per
+    // SM - the per-block weight staging outweighs the extra latency hiding), at most kSmallKRowsMax rows each
+    int rpb = ceil_div(M, smallk_rows_target() * GYMRL_NUM_SMS / ceil_div(N, 256));
+    rpb = rpb < 8 ? 8 : (rpb > kSmallKRowsMax ? kSmallKRowsMax : (rpb + 7) / 8 * 8);
     dim3 grid(ceil_div(N, 256), ceil_div(M, rpb));
-    if (K == 3) smallk_fwd_kernel<3><<<grid, 256, 0, s>>>(x, ldx, rows, w, b, y, ldy, M, N, act, rpb);
+    const bool vec = smallk_vec_enabled() && (N % 4 == 0) && (ldy % 4 == 0) && ((reinterpret_cast<uintptr_t>(y) & 15) == 0) &&
+                     (!b || (reinterpret_cast<uintptr_t>(b) & 15) == 0);
+    if (vec) {
+        if (K == 3) smallk_fwd4_kernel<3><<<grid, 256, 0, s>>>(x, ldx, rows, w, b, y, ldy, M, N, act, rpb);
+        else if (K == 4) smallk_fwd4_kernel<4><<<grid, 256, 0, s>>>(x, ldx, rows, w, b, y, ldy, M, N, act, rpb);
+        else smallk_fwd4_kernel<8><<<grid, 256, 0, s>>>(x, ldx, rows, w, b, y, ldy, M, N, act, rpb);
+    } else if (K == 3) smallk_fwd_kernel<3><<<grid, 256, 0, s>>>(x, ldx, rows, w, b, y, ldy, M, N, act, rpb);
     else if (K == 4) smallk_fwd_kernel<4><<<grid, 256, 0, s>>>(x, ldx, rows, w, b, y, ldy, M, N, act, rpb);
     else smallk_fwd_kernel<8><<<grid, 256, 0, s>>>(x, ldx, rows, w, b, y, ldy, M, N, act, rpb);
     gymrl_count_launch();
@@ -248,18 +332,22 @@ __global__ void __launch_bounds__(256) smallk_dw_kernel(const float* __restrict_
 #pragma unroll
     for (int k = 0; k < K; ++k) acc[k] = 0.f;
     for (int m0 = m_beg; m0 < m_end; m0 += 32) {
+        const int lim = min(32, m_end - m0);
+        // the dY column loads do not depend on the staged x rows: issue them before the barriers so that their L2 round
+        // trip overlaps the (index -> row) gather instead of following it
+        float g[32];
+        if (n < N && lim == 32) {
+#pragma unroll
+            for (int r = 0; r < 32; ++r) g[r] = dy[(size_t)(m0 + r) * lddy + n];
+        }
         __syncthreads();
         for (int i = threadIdx.x; i < 32 * K; i += blockDim.x) {
             const int mm = m0 + i / K;
             sx[i / K][i % K] = mm < m_end ? x[(size_t)(rows ? rows[mm] : mm) * ldx + (i % K)] : 0.f;
         }
         __syncthreads();
-        const int lim = min(32, m_end - m0);
         if (n < N) {
             if (lim == 32) {
-                float g[32];
-#pragma unroll
-                for (int r = 0; r < 32; ++r) g[r] = dy[(size_t)(m0 + r) * lddy + n];
 #pragma unroll
                 for (int r = 0; r < 32; ++r) {
                     accb += g[r];
@@ -268,10 +356,10 @@ __global__ void __launch_bounds__(256) smallk_dw_kernel(const float* __restrict_
                 }
             } else {
                 for (int r = 0; r < lim; ++r) {
-                    const float g = dy[(size_t)(m0 + r) * lddy + n];
-                    accb += g;
+                    const float gv = dy[(size_t)(m0 + r) * lddy + n];
+                    accb += gv;
 #pragma unroll
-                    for (int k = 0; k < K; ++k) acc[k] = fmaf(g, sx[r][k], acc[k]);
+                    for (int k = 0; k < K; ++k) acc[k] = fmaf(gv, sx[r][k], acc[k]);
                 }
             }
         }
@@ -283,9 +371,101 @@ __global__ void __launch_bounds__(256) smallk_dw_kernel(const float* __restrict_
     }
 }
 
+// Vector variant (N % 4 == 0, 16 B-aligned dy / lddy): a thread owns 4 adjacent output units (4 x K + 4 accumulators), the
+// block's four row groups walk every 4th row of the chunk (one LDG.128 of dY and one broadcast read of the x row feed 4K
+// FMAs), and are folded through shared memory in a fixed order before the partial is written.
+constexpr int kSmallKDwRows = 64;   // rows per chunk
+template <int K>
+__global__ void __launch_bounds__(256) smallk_dw4_kernel(const float* __restrict__ dy, int lddy, const float* __restrict__ x, int ldx,
+                                                         const int32_t* __restrict__ rows, float* __restrict__ part_w,
+                                                         float* __restrict__ part_b, int M, int N) {
+    const int cg = threadIdx.x & 63, rg = threadIdx.x >> 6;
+    const int n = (blockIdx.x * 64 + cg) * 4;
+    const int m_beg = blockIdx.y * kSmallKDwRows, m_end = min(M, m_beg + kSmallKDwRows);
+    const int nrows = m_end - m_beg;
+    __shared__ __align__(16) float sx[kSmallKDwRows][K == 3 ? 4 : K];
+    __shared__ float red[3][64][4 * K + 4 + 1];   // +1: odd pitch, conflict-free column-group writes
+    // dY loads first: they do not depend on the staged x rows
+    constexpr int RPT = kSmallKDwRows / 4;         // rows per thread
+    float4 g[RPT];
+    const bool ok = n < N;
+#pragma unroll
+    for (int i = 0; i < RPT; ++i) {
+        const int r = rg + 4 * i;
+        g[i] = (ok && r < nrows) ? *reinterpret_cast<const float4*>(dy + (size_t)(m_beg + r) * lddy + n) : make_float4(0.f, 0.f, 0.f, 0.f);
+    }
+    for (int i = threadIdx.x; i < kSmallKDwRows * K; i += blockDim.x) {
+        const int r = i / K, mm = m_beg + r;
+        sx[r][i % K] = r < nrows ? x[(size_t)(rows ? rows[mm] : mm) * ldx + (i % K)] : 0.f;
+    }
+    __syncthreads();
+    float acc[4][K], accb[4] = {0.f, 0.f, 0.f, 0.f};
+#pragma unroll
+    for (int c = 0; c < 4; ++c)
+#pragma unroll
+        for (int k = 0; k < K; ++k) acc[c][k] = 0.f;
+#pragma unroll
+    for (int i = 0; i < RPT; ++i) {
+        const int r = rg + 4 * i;
+        float xr[K];
+#pragma unroll
+        for (int k = 0; k < K; ++k) xr[k] = sx[r][k];
+        const float gv[4] = {g[i].x, g[i].y, g[i].z, g[i].w};
+#pragma unroll
+        for (int c = 0; c < 4; ++c) {
+            accb[c] += gv[c];
+#pragma unroll
+            for (int k = 0; k < K; ++k) acc[c][k] = fmaf(gv[c], xr[k], acc[c][k]);
+        }
+    }
+    if (rg > 0) {
+        float* q = red[rg - 1][cg];
+#pragma unroll
+        for (int c = 0; c < 4; ++c) {
+#pragma unroll
+            for (int k = 0; k < K; ++k) q[c * K + k] = acc[c][k];
+            q[4 * K + c] = accb[c];
+        }
+    }
+    __syncthreads();
+    if (rg != 0 || !ok) return;
+#pragma unroll
+    for (int s = 0; s < 3; ++s) {
+        const float* q = red[s][cg];
+#pragma unroll
+        for (int c = 0; c < 4; ++c) {
+#pragma unroll
+            for (int k = 0; k < K; ++k) acc[c][k] += q[c * K + k];
+            accb[c] += q[4 * K + c];
+        }
+    }
+#pragma unroll
+    for (int c = 0; c < 4; ++c) {
+#pragma unroll
+        for (int k = 0; k < K; ++k) part_w[((size_t)blockIdx.y * N + n + c) * K + k] = acc[c][k];
+        if (part_b) part_b[(size_t)blockIdx.y * N + n + c] = accb[c];
+    }
+}
+
 bool smallk_dw_supported(int K) { return K == 3 || K == 4 || K == 8; }
+// chunks the dW sweep will write for M rows (the caller sizes the partial buffers with it)
+int smallk_dw_chunks(const float* dy, int lddy, int M, int N) {
+    const bool vec = smallk_vec_enabled() && (N % 4 == 0) && (lddy % 4 == 0) && ((reinterpret_cast<uintptr_t>(dy) & 15) == 0);
+    if (vec && ceil_div(M, kSmallKDwRows) <= 512) return ceil_div(M, kSmallKDwRows);
+    const int chunks = ceil_div(M, 32);
+    return chunks > 512 ? 512 : chunks;
+}
 int smallk_dw(const float* dy, int lddy, const float* x, int ldx, const int32_t* rows, float* part_w, float* part_b, int M, int N, int K,
               int chunks, cudaStream_t s) {
+    const bool vec = smallk_vec_enabled() && (N % 4 == 0) && (lddy % 4 == 0) && ((reinterpret_cast<uintptr_t>(dy) & 15) == 0);
+    if (vec && chunks == ceil_div(M, kSmallKDwRows)) {
+        dim3 grid(ceil_div(N, 256), chunks);
+        if (K == 3) smallk_dw4_kernel<3><<<grid, 256, 0, s>>>(dy, lddy, x, ldx, rows, part_w, part_b, M, N);
+        else if (K == 4) smallk_dw4_kernel<4><<<grid, 256, 0, s>>>(dy, lddy, x, ldx, rows, part_w, part_b, M, N);
+        else smallk_dw4_kernel<8><<<grid, 256, 0, s>>>(dy, lddy, x, ldx, rows, part_w, part_b, M, N);
+        gymrl_count_launch();
+        return GYMRL_OK;
+    }
     const int rpc = ceil_div(M, chunks);
     dim3 grid(ceil_div(N, 256), chunks);
     if (K == 3) smallk_dw_kernel<3><<<grid, 256, 0, s>>>(dy, lddy, x, ldx, rows, part_w, part_b, M, N, rpc);
@@ -400,8 +580,15 @@ __global__ void __launch_bounds__(256) reduce_pair_kernel(const float* __restric
     else if (is_b) out_b[i - cnt_w] = accumulate ? out_b[i - cnt_w] + s : s;
 }
 
+bool gymrl_defer_reduce(const float* part, long long stride, int splits, long long count, float* out, int accumulate);
+
 void reduce_pair(const float* part_w, long long stride_w, const float* part_b, long long stride_b, int splits, long long cnt_w, int cnt_b,
                  float* out_w, float* out_b, int accumulate, cudaStream_t s) {
+    // inside a deferral scope (reduce.cu) the fold is recorded and runs with every other pending one in gymrl_reduce_flush
+    if (gymrl_defer_reduce(part_w, stride_w, splits, cnt_w, out_w, accumulate)) {
+        gymrl_defer_reduce(part_b, stride_b, splits, cnt_b, out_b, accumulate);
+        return;
+    }
     const long long total = cnt_w + (out_b ? cnt_b : 0);
     if (splits >= 32 && total <= 16384)
         reduce_pair_kernel<8><<<(unsigned)ceil_div_ll(total, 32), 256, 0, s>>>(part_w, stride_w, part_b, stride_b, splits, cnt_w, cnt_b, out_w,

@@ -96,6 +96,70 @@ extern "C" int gymrl_adam_step(float* d_param, const float* d_grad, float* d_exp
     return GYMRL_OK;
 }
 
+// Clip + Adam with the global norm taken from per-block sums of squares (gymrl_reduce_flush) and the step counter advanced
+// by the last block to finish: one launch instead of grad_sumsq + adam + adam_post.  Every block folds the partials in the
+// same fixed order (thread-strided, then the block tree), so all blocks see the same norm bit for bit.
+__global__ void __launch_bounds__(256) clip_adam_kernel(float* __restrict__ param, const float* __restrict__ grad, float* __restrict__ m,
+                                                        float* __restrict__ v, long long n, const double* __restrict__ lr, float beta1,
+                                                        float beta2, float eps, int32_t* __restrict__ step,
+                                                        const double* __restrict__ sumsq_partials, int n_partials, float max_norm,
+                                                        float grad_scale, uint32_t* __restrict__ done_counter) {
+    __shared__ double scratch[32];
+    __shared__ float s_coef;
+    const int t = *step + 1;
+    double q = 0.0;
+    for (int i = threadIdx.x; i < n_partials; i += blockDim.x) q += sumsq_partials[i];
+    q = block_sum(q, scratch);
+    if (threadIdx.x == 0) {
+        const float total_norm = (float)sqrt(q * (double)grad_scale * (double)grad_scale);
+        s_coef = grad_scale * fminf(max_norm / (total_norm + 1e-6f), 1.0f);
+    }
+    __syncthreads();
+    const float coef = s_coef;
+    const double bc1 = 1.0 - pow((double)beta1, (double)t);
+    const double bc2 = 1.0 - pow((double)beta2, (double)t);
+    const float step_size = (float)(-(*lr / bc1));
+    const float bc2_sqrt = (float)sqrt(bc2);
+    const float w1 = (float)(1.0 - (double)beta1), w2 = (float)(1.0 - (double)beta2);
+    for (long long i = (long long)blockIdx.x * blockDim.x + threadIdx.x; i < n; i += (long long)gridDim.x * blockDim.x) {
+        const float g = grad[i] * coef;
+        float mi = m[i], vi = v[i];
+        mi = mi + w1 * (g - mi);
+        vi = vi * beta2 + (w2 * g) * g;
+        const float denom = sqrtf(vi) / bc2_sqrt + eps;
+        param[i] = param[i] + (step_size * mi) / denom;
+        m[i] = mi;
+        v[i] = vi;
+    }
+    // every block read *step before it got here, so the last one to arrive may advance it
+    __syncthreads();
+    if (threadIdx.x == 0) {
+        __threadfence();
+        if (atomicAdd(done_counter, 1u) == gridDim.x - 1) {
+            *step = t;
+            *done_counter = 0u;
+        }
+    }
+}
+
+extern "C" int gymrl_clip_adam_step(float* d_param, const float* d_grad, float* d_exp_avg, float* d_exp_avg_sq, long long n,
+                                    const double* d_lr, float beta1, float beta2, float eps, int32_t* d_step,
+                                    const double* d_sumsq_partials, int n_partials, float max_norm, float grad_scale,
+                                    uint32_t* d_done_counter, void* stream) {
+    GYMRL_REQUIRE(d_param && d_grad && d_exp_avg && d_exp_avg_sq && d_lr && d_step && d_sumsq_partials && d_done_counter && n > 0,
+                  "bad arguments");
+    GYMRL_REQUIRE(n_partials > 0 && max_norm > 0.f, "clip_adam_step needs the sum-of-squares partials and a positive max_norm");
+    const int threads = 256;
+    long long blocks = ceil_div_ll(n, threads);
+    if (blocks > GYMRL_NUM_SMS * 4) blocks = GYMRL_NUM_SMS * 4;
+    clip_adam_kernel<<<(int)blocks, threads, 0, as_stream(stream)>>>(d_param, d_grad, d_exp_avg, d_exp_avg_sq, n, d_lr, beta1, beta2, eps,
+                                                                   d_step, d_sumsq_partials, n_partials, max_norm, grad_scale,
+                                                                   d_done_counter);
+    gymrl_count_launch();
+    GYMRL_LAUNCH_CHECK("clip_adam_step");
+    return GYMRL_OK;
+}
+
 __global__ void polyak_kernel(float* __restrict__ target, const float* __restrict__ source, long long n, float tau) {
     const float omt = (float)(1.0 - (double)tau);
     for (long long i = (long long)blockIdx.x * blockDim.x + threadIdx.x; i < n; i += (long long)gridDim.x * blockDim.x)

@@ -18,6 +18,7 @@
 #include "rowwise.cuh"
 
 void gymrl_count_launch(int n = 1);
+bool gymrl_defer_reduce(const float* part, long long stride, int splits, long long count, float* out, int accumulate);
 
 #define MAX_A 16
 
@@ -332,8 +333,15 @@ extern "C" int gymrl_ppo_heads_fused(const float* d_h, int ldh, const float* d_W
         ppo_heads_fused_kernel<1, 4><<<grid, kHeadsWarps * 32, smem, s>>>(d_h, ldh, d_Wa, d_ba, d_Wc, d_bc, d_row_index, d_action, d_logp_old, d_adv,
                                                                            d_ret, d_entropy_old, d_value_old, d_dh, lddh, act_in, d_lv_out, partials,
                                                                            d_metrics, batch, *cfg);
-    launch_reduce_blocks(partials, grid, P, d_dWa, A * H, d_dba, A, d_dWc, H, d_dbc, 1, accumulate, s);
-    gymrl_count_launch(2);
+    if (gymrl_defer_reduce(partials, P, grid, A * H, d_dWa, accumulate)) {
+        gymrl_defer_reduce(partials + A * H, P, grid, A, d_dba, accumulate);
+        gymrl_defer_reduce(partials + A * H + A, P, grid, H, d_dWc, accumulate);
+        gymrl_defer_reduce(partials + A * H + A + H, P, grid, 1, d_dbc, accumulate);
+        gymrl_count_launch(1);
+    } else {
+        launch_reduce_blocks(partials, grid, P, d_dWa, A * H, d_dba, A, d_dWc, H, d_dbc, 1, accumulate, s);
+        gymrl_count_launch(2);
+    }
     GYMRL_LAUNCH_CHECK("ppo_heads_fused");
     return GYMRL_OK;
 }

@@ -85,6 +85,16 @@ class FlatParams:
     def numel(self) -> int:
         return self.flat.numel()
 
+    def n_params(self) -> int:
+        """Parameter elements without the alignment padding of the flat buffer (whose gradient stays zero)."""
+        n = 0
+        for (_, shape) in self.views.values():
+            k = 1
+            for s in shape:
+                k *= s
+            n += k
+        return n
+
     def refresh_views(self):
         """Re-point nn.Parameter.data at the flat buffer (after load_state_dict replaced storages)."""
         named = dict(self.module.named_parameters())
@@ -109,6 +119,8 @@ class FusedAdam:
         self.step_t = torch.zeros(1, device=dev, dtype=torch.int32)
         self.lr_t = torch.full((1,), float(lr), device=dev, dtype=torch.float64)
         self.sumsq = torch.zeros(1, device=dev, dtype=torch.float64)
+        self.sumsq_partials = torch.zeros(4096, device=dev, dtype=torch.float64)   # reduce_flush's per-block sums of squares
+        self.done_ctr = torch.zeros(1, device=dev, dtype=torch.int32)
         self._lr_host = float(lr)
         self.betas, self.eps = betas, eps
         self.param_groups: List[dict] = [{"lr": float(lr), "betas": betas, "eps": eps, "params": list(params.module.parameters())}]
@@ -132,6 +144,13 @@ class FusedAdam:
         ops.adam_step(self.fp.flat, self.fp.grad, self.exp_avg, self.exp_avg_sq, self.lr_t, self.step_t,
                       beta1=self.betas[0], beta2=self.betas[1], eps=self.eps,
                       sumsq=self.sumsq if max_norm > 0.0 else None, max_norm=max_norm, clamp=clamp, grad_scale=grad_scale)
+
+    def launch_clipped(self, n_partials: int, max_norm: float, grad_scale: float = 1.0):
+        """Clip + Adam in one launch, the norm taken from self.sumsq_partials[:n_partials] (filled by
+        ops.reduce_flush(self.sumsq_partials) over *all* of this optimiser's gradients)."""
+        ops.clip_adam_step(self.fp.flat, self.fp.grad, self.exp_avg, self.exp_avg_sq, self.lr_t, self.step_t,
+                           sumsq_partials=self.sumsq_partials, n_partials=n_partials, done_counter=self.done_ctr, max_norm=max_norm,
+                           beta1=self.betas[0], beta2=self.betas[1], eps=self.eps, grad_scale=grad_scale)
 
     def step(self, max_norm: float = 0.0, clamp: float = 0.0, grad_scale: float = 1.0):
         self.sync_lr()

@@ -296,6 +296,28 @@ def adam_step(param, grad, exp_avg, exp_avg_sq, lr, step, *, beta1=0.9, beta2=0.
                                  float(max_norm), float(clamp), float(grad_scale), stream_ptr()))
 
 
+def clip_adam_step(param, grad, exp_avg, exp_avg_sq, lr, step, *, sumsq_partials, n_partials, done_counter, max_norm, beta1=0.9,
+                   beta2=0.999, eps=1e-8, grad_scale=1.0):
+    """Clip-by-global-norm + Adam in one launch; the norm comes from reduce_flush's per-block sums of squares."""
+    check(load().gymrl_clip_adam_step(ptr(param, f32), ptr(grad, f32), ptr(exp_avg, f32), ptr(exp_avg_sq, f32), param.numel(),
+                                      ptr(lr, f64), float(beta1), float(beta2), float(eps), ptr(step, i32), ptr(sumsq_partials, f64),
+                                      int(n_partials), float(max_norm), float(grad_scale), ptr(done_counter, i32), stream_ptr()))
+
+
+def reduce_defer_begin():
+    """Open a deferral scope: backward calls record their partial-gradient folds until reduce_flush()."""
+    check(load().gymrl_reduce_defer_begin())
+
+
+def reduce_flush(sumsq_partials=None):
+    """Fold everything recorded since reduce_defer_begin() in one launch.  Returns (number of blocks = entries written to
+    `sumsq_partials`, float64 [capacity], when given; number of gradient elements produced)."""
+    n, cnt = C.c_int(0), C.c_longlong(0)
+    cap = sumsq_partials.numel() if sumsq_partials is not None else 0
+    check(load().gymrl_reduce_flush(ptr(sumsq_partials, f64), int(cap), C.byref(n), C.byref(cnt), stream_ptr()))
+    return int(n.value), int(cnt.value)
+
+
 def polyak(target, source, tau):
     check(load().gymrl_polyak(ptr(target, f32), ptr(source, f32), target.numel(), float(tau), stream_ptr()))
 

@@ -239,6 +239,25 @@ int gymrl_adam_step(float* d_param, const float* d_grad, float* d_exp_avg, float
                     long long n, const double* d_lr, float beta1, float beta2, float eps,
                     int32_t* d_step, const double* d_sumsq, float max_norm, float clamp,
                     float grad_scale, void* stream);
+
+/* Deferred, merged fold of parameter-gradient partials.  Between gymrl_reduce_defer_begin() and gymrl_reduce_flush()
+ * (per host thread) the backward entry points (gymrl_linear_backward, gymrl_linear_backward_weight,
+ * gymrl_ppo_heads_fused) record their pending "dW/db = fixed-order sum of per-CTA partials" instead of launching one
+ * small fold kernel each; the flush folds everything recorded in ONE launch.  Each recorded call must have been given
+ * its own workspace, which has to stay untouched until the flush has executed (at most 24 pending sums per scope).
+ * With d_sumsq_partials != NULL the flush also writes, per block, the float64 sum of squares of the final gradient
+ * values it produced (*n_partials entries, <= capacity; *n_outputs = how many gradient elements they cover, so the
+ * caller can check that the whole flat gradient went through the scope): the global norm of clip_grad_norm_
+ * (algorithms/ppo_lunarlander.py:304-306) for gymrl_clip_adam_step, without another pass over the gradient. */
+int gymrl_reduce_defer_begin(void);
+int gymrl_reduce_flush(double* d_sumsq_partials, int capacity, int* n_partials, long long* n_outputs, void* stream);
+/* gymrl_adam_step with clip_grad_norm_(max_norm) taken from gymrl_reduce_flush's partial sums of squares (folded in a
+ * fixed order by every block), the step counter advanced by the last block to finish (d_done_counter: device uint32,
+ * zero before the first call): one launch for algorithms/ppo_lunarlander.py:304-306. */
+int gymrl_clip_adam_step(float* d_param, const float* d_grad, float* d_exp_avg, float* d_exp_avg_sq, long long n,
+                         const double* d_lr, float beta1, float beta2, float eps, int32_t* d_step,
+                         const double* d_sumsq_partials, int n_partials, float max_norm, float grad_scale,
+                         uint32_t* d_done_counter, void* stream);
 /* target = tau * source + (1 - tau) * target   (rainbow_dqn_cartpole.py:347-352,
  * sac_pendulum.py:194-199, td3_pendulum.py:150-155); tau = 1 is the hard copy of dqn_cartpole.py:193. */
 int gymrl_polyak(float* d_target, const float* d_source, long long n, float tau, void* stream);

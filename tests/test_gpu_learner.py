@@ -283,6 +283,62 @@ def test_ppo_heads_fused_rejects_unsupported_shapes(ops):
                             dba=z(4), dWc=z(1, H), dbc=z(1), workspace=ops.ppo_heads_workspace(256, 4), M=B)
 
 
+def test_deferred_reduce_scope_and_clip_adam(ops):
+    """reduce_defer_begin / reduce_flush: the layers' partial-gradient folds as one launch give the same gradients as the
+    per-layer folds, the per-block sums of squares add up to |g|^2, and clip_adam_step == grad_sumsq + adam_step."""
+    from gymrl_b200 import _ffi
+    torch.manual_seed(5)
+    shapes = [(16384, 512, 256), (16384, 4, 256), (4096, 256, 8), (1000, 70, 19)]
+    layers = []
+    for (M, N, K) in shapes:
+        dy, x, w = torch.randn(M, N, device="cuda") / M, torch.tanh(torch.randn(M, K, device="cuda")), torch.randn(N, K, device="cuda") / 16
+        ws = torch.empty(ops.backward_weight_workspace(M, N, K), dtype=torch.uint8, device="cuda")
+        layers.append((dy, x, w, ws))
+    ref = []
+    for (dy, x, w, ws) in layers:
+        dw, db = torch.empty_like(w), torch.empty(w.shape[0], device="cuda")
+        ops.linear_backward(dy, x, w, dw, db, workspace=ws)
+        ref.append((dw, db))
+    flat = torch.full((sum(w.numel() + w.shape[0] for (_, _, w, _) in layers),), float("nan"), device="cuda")
+    outs, o = [], 0
+    for (_, _, w, _) in layers:
+        dw = flat[o:o + w.numel()].view_as(w); o += w.numel()
+        db = flat[o:o + w.shape[0]]; o += w.shape[0]
+        outs.append((dw, db))
+    partials = torch.zeros(4096, dtype=torch.float64, device="cuda")
+    ops.reduce_defer_begin()
+    for (dy, x, w, ws), (dw, db) in zip(layers, outs):
+        ops.linear_backward(dy, x, w, dw, db, workspace=ws)
+    assert torch.isnan(flat).all()          # nothing folded yet
+    n, covered = ops.reduce_flush(partials)
+    assert covered == flat.numel() and 0 < n <= 4096
+    for (dw, db), (rw, rb) in zip(outs, ref):
+        torch.testing.assert_close(dw, rw, rtol=2e-5, atol=1e-7)
+        torch.testing.assert_close(db, rb, rtol=2e-5, atol=1e-7)
+    sq = float(partials[:n].sum().item())
+    np.testing.assert_allclose(sq, float((flat.double() ** 2).sum().item()), rtol=1e-12)
+    with pytest.raises(RuntimeError):
+        ops.reduce_flush()                  # no scope open
+    # clip + Adam from the partials == grad_sumsq + adam_step
+    P = flat.numel()
+    p0 = torch.randn(P, device="cuda")
+    lr, sumsq = torch.full((1,), 3e-4, dtype=torch.float64, device="cuda"), torch.zeros(1, dtype=torch.float64, device="cuda")
+    res = []
+    for fused in (False, True):
+        p, m, v = p0.clone(), torch.zeros(P, device="cuda"), torch.zeros(P, device="cuda")
+        step, ctr = torch.zeros(1, dtype=torch.int32, device="cuda"), torch.zeros(1, dtype=torch.int32, device="cuda")
+        for _ in range(3):
+            if fused:
+                ops.clip_adam_step(p, flat, m, v, lr, step, sumsq_partials=partials, n_partials=n, done_counter=ctr, max_norm=0.5, eps=1e-5)
+            else:
+                ops.grad_sumsq(flat, out=sumsq)
+                ops.adam_step(p, flat, m, v, lr, step, eps=1e-5, sumsq=sumsq, max_norm=0.5)
+        assert int(step.item()) == 3 and int(ctr.item()) == 0
+        res.append((p, m, v))
+    for a, b in zip(*res):
+        torch.testing.assert_close(a, b, rtol=1e-6, atol=1e-9)
+
+
 # ------------------------------------------------------------------------------------------------ dense layers
 @pytest.mark.parametrize("M,N,K,act", [(16384, 256, 256, 1), (4096, 512, 256, 1), (4096, 256, 8, 1), (333, 70, 19, 2),
                                        (4096, 4, 256, 0), (4096, 1, 256, 0), (128, 256, 3, 2), (64, 2, 256, 0), (1, 256, 8, 1)])
