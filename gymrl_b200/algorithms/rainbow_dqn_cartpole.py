@@ -49,6 +49,7 @@ class Config:
         # ---- engine extras ----
         self.num_envs = 1
         self.max_locksteps = None
+        self.use_cuda_graph = True   # train(): act -> env step -> n-step/PER store -> update as ONE captured graph per lockstep
 
 
 class NoisyLinear(nn.Module):
@@ -93,6 +94,7 @@ class DuelingEngine:
         self.eps_in_a, self.eps_out_a, self.eps_in_v, self.eps_out_v = z(H), z(A), z(H), z(1)
         self.out = z(M, A + 1)
         self.draws = 0
+        self.ctr = torch.zeros(1, device=dev, dtype=i32)   # device mirror of `draws`: captured graphs draw fresh noise per replay
         if backward:
             self.dout = z(M, A + 1)
             self.dW, self.db = z(A + 1, H), z(A + 1)
@@ -106,7 +108,8 @@ class DuelingEngine:
             for k, (eps, ent) in enumerate(((self.eps_in_a, 0), (self.eps_out_a, 1), (self.eps_in_v, 2), (self.eps_out_v, 3))):
                 key = ("in_a", "out_a", "in_v", "out_v")[k]
                 off.noisy_sample(eps, xi[key] if xi is not None else None, seed=self.seed, entity=self.entity * 16 + ent * 4096,
-                                 draw=self.draws)
+                                 draw=1, draw_base=self.ctr)
+            ops.counter_add(self.ctr, 1)
         else:
             for eps in (self.eps_in_a, self.eps_out_a, self.eps_in_v, self.eps_out_v):
                 eps.zero_()
@@ -180,11 +183,16 @@ class PrioritizedNStepBuffer:
         self.store_lockstep(t(state, f32).reshape(1, -1), t([action], i32), t([reward], f32), t(next_state, f32).reshape(1, -1),
                             t([bool(terminal)], u8), t([bool(done)], u8))
 
-    def sample(self, total_steps: int, max_train_steps: int, uniforms=None, seed=0, draw=0):
+    def set_beta(self, total_steps: int, max_train_steps: int):
+        """IS exponent schedule (ref :222): host value -> device scalar (outside any captured graph)."""
         self.beta = self.beta_init + (1 - self.beta_init) * (total_steps / max_train_steps)
         self.beta_t.fill_(self.beta)
+
+    def sample(self, total_steps: int, max_train_steps: int, uniforms=None, seed=0, draw=0, draw_base=None, set_beta=True):
+        if set_beta:
+            self.set_beta(total_steps, max_train_steps)
         self.sum_tree.sample(self.batch_size, self.ring.state, self.beta_t, uniforms=uniforms, out_idx=self.batch_index,
-                             out_w=self.is_weight, seed=seed, draw=draw)
+                             out_w=self.is_weight, seed=seed, draw=draw, draw_base=draw_base)
         return self.batch_index, self.is_weight
 
     def update_priorities(self, batch_index, td_errors):
@@ -223,6 +231,10 @@ class RainbowDQNTrainer:
         self.done = torch.zeros(N, device=dev, dtype=u8)
         self.total_steps = 0
         self.update_count = 0
+        self.ctr_upd = torch.zeros(1, device=dev, dtype=i32)   # device mirror of update_count (PER sampling draw)
+        self.cur = torch.zeros(N, D, device=dev, dtype=f32)
+        self._g_lockstep = None
+        self.graph_launches = 0
         self.episode_rewards = deque(maxlen=100)
         print(f"Device: {dev}")
         print(f"State dim: {D}, Action dim: {A}")
@@ -246,12 +258,29 @@ class RainbowDQNTrainer:
         return int(ops.select_eps_greedy(out[:, :self.action_dim], 0.0).item())
 
     def update(self, uniforms=None, xi_next=None, xi_cur=None):
-        cfg, B, A, mem = self.cfg, int(self.cfg.batch_size), self.action_dim, self.memory
+        cfg, B, mem = self.cfg, int(self.cfg.batch_size), self.memory
         if len(mem) < B:
             return 0.0
         self.update_count += 1
+        mem.set_beta(self.total_steps, self.max_train_steps)
+        self.optimizer.sync_lr()
+        self._update_device(uniforms, xi_next, xi_cur)
+        self._schedule_lr()
+        return self.loss_acc[0]
+
+    def _schedule_lr(self):
+        cfg = self.cfg
+        lr_now = 0.9 * cfg.lr * (1 - self.total_steps / self.max_train_steps) + 0.1 * cfg.lr
+        for g in self.optimizer.param_groups:
+            g["lr"] = lr_now
+
+    def _update_device(self, uniforms=None, xi_next=None, xi_cur=None):
+        """The device side of update() (ref :311-361): capture-safe — beta, the learning rate and the draw counter are device
+        scalars set outside."""
+        cfg, B, A, mem = self.cfg, int(self.cfg.batch_size), self.action_dim, self.memory
         ring = mem.ring
-        idx, w = mem.sample(self.total_steps, self.max_train_steps, uniforms=uniforms, seed=self.seed, draw=self.update_count)
+        idx, w = mem.sample(self.total_steps, self.max_train_steps, uniforms=uniforms, seed=self.seed, draw=1, draw_base=self.ctr_upd,
+                            set_beta=False)
         qo = self.net_nxt.forward(ring.next_obs, B, row_index=idx, noisy=True, xi=xi_next)       # online net, fresh noise (q8)
         qt = self.net_tgt.forward(ring.next_obs, B, row_index=idx, noisy=False)                  # target net is .eval(): mu only
         q = self.net_upd.forward(ring.obs, B, row_index=idx, noisy=True, xi=xi_cur)
@@ -261,12 +290,59 @@ class RainbowDQNTrainer:
                      dv=self.net_upd.dout[:, A:], td_error=self.td, loss_acc=self.loss_acc)
         mem.update_priorities(idx, self.td)                                                     # before backward (ref :340)
         self.net_upd.backward(ring.obs, B, row_index=idx)
-        self.optimizer.step(max_norm=cfg.grad_clip)
+        self.optimizer.launch(max_norm=cfg.grad_clip)
         ops.polyak(self._target_params(), self._policy_params(), cfg.tau)
-        lr_now = 0.9 * cfg.lr * (1 - self.total_steps / self.max_train_steps) + 0.1 * cfg.lr
-        for g in self.optimizer.param_groups:
-            g["lr"] = lr_now
-        return self.loss_acc[0]
+        ops.counter_add(self.ctr_upd, 1)
+
+    # ---------------------------------------------------------------- one lockstep (ref train() loop body :371-388)
+    def _lockstep_body(self):
+        """act -> env.step -> n-step window / PER store -> update -> carry the observation.  Capture-safe once the n-step
+        window is full and the ring holds a batch."""
+        env, mem, cur, A = self.env, self.memory, self.cur, self.action_dim
+        out = self.net_act.forward(cur, self.N, noisy=True)
+        a = ops.select_eps_greedy(out[:, :A], 0.0, action=self.action)
+        obs, r, te, tr, nobs = env.step(a, done=self.done)
+        terminal = te & (1 - tr)                       # time-limit truncation is not terminal (ref :376, SURVEY q7)
+        mem.store_lockstep(cur, a, r, nobs, terminal, self.done)
+        self._update_device()
+        cur.copy_(obs)
+
+    def lockstep(self):
+        """One lockstep of all N envs: eager while the n-step window / the ring are filling, then one CUDA-graph replay per
+        lockstep with the host-scheduled scalars (PER beta, learning rate) written to their device slots first."""
+        from ..graphs import capture
+        cfg, mem, B = self.cfg, self.memory, int(self.cfg.batch_size)
+        ready = len(mem) >= B and mem.window.pushed_host >= mem.n_steps
+        if not getattr(cfg, "use_cuda_graph", True) or not ready:
+            cur = self.cur
+            a = self.act(cur)
+            obs, r, te, tr, nobs = self.env.step(a, done=self.done)
+            mem.store_lockstep(cur, a, r, nobs, te & (1 - tr), self.done)
+            self.update()
+            cur.copy_(obs)
+            return
+        self.total_steps += 1
+        self.update_count += 1
+        mem.set_beta(self.total_steps, self.max_train_steps)
+        self.optimizer.sync_lr()
+        if self._g_lockstep is None:
+            mirrors = (mem.window.pushed_host, mem.ring._size_host, [e.draws for e in self._engines()])
+            self._g_lockstep = capture(self._lockstep_body)   # the capture's eager pass is this lockstep
+            mem.window.pushed_host, mem.ring._size_host = mirrors[0], mirrors[1]
+            for e, d in zip(self._engines(), mirrors[2]):
+                e.draws = d
+        else:
+            self._g_lockstep.replay()
+            self.graph_launches += self._g_lockstep.n_kernels
+        # host mirrors of the counters the device body advanced
+        mem.window.pushed_host += 1
+        mem.ring._size_host = min(mem.ring.capacity, mem.ring._size_host + self.N)
+        for e in (self.net_act, self.net_nxt, self.net_upd):
+            e.draws += 1
+        self._schedule_lr()
+
+    def _engines(self):
+        return (self.net_act, self.net_upd, self.net_nxt, self.net_tgt)
 
     # Polyak touches parameters only; both nets share the flat layout so one kernel covers them all (buffers are not in `flat`)
     def _policy_params(self):
@@ -278,16 +354,11 @@ class RainbowDQNTrainer:
     def train(self):
         print("Starting training...")
         cfg, env, mem = self.cfg, self.env, self.memory
-        cur = env.reset().clone()
+        env.reset(out=self.cur)
         max_lock = cfg.max_locksteps or int(cfg.max_episodes * cfg.max_steps / self.N)
         t0, last_total = time.time(), 0
         for step in range(max_lock):
-            a = self.act(cur)
-            obs, r, te, tr, nobs = env.step(a, done=self.done)
-            terminal = te & (1 - tr)                       # time-limit truncation is not terminal (ref :376)
-            mem.store_lockstep(cur, a, r, nobs, terminal, self.done)
-            self.update()
-            cur.copy_(obs)
+            self.lockstep()
             if step % 100 == 99:
                 avg, _, total = env.episode_stats(100)
                 if total != last_total:

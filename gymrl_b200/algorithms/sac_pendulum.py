@@ -47,6 +47,7 @@ class Config:
         # ---- engine extras ----
         self.num_envs = 1
         self.max_locksteps = None
+        self.use_cuda_graph = True   # train(): act -> env step -> store -> update as ONE captured graph per lockstep
 
 
 class Actor(nn.Module):
@@ -132,6 +133,12 @@ class SACTrainer:
         self.done = z(N, dt=u8)
         self.update_count = 0
         self.act_count = 0
+        # RNG draw counters on the device (the kernels add them to their `draw` argument), so that a captured lockstep
+        # draws fresh noise on every replay: act (+1 per act), sample (+1 per update), normals (+2 per update)
+        self.ctr_act, self.ctr_upd, self.ctr_nz = z(1, dt=i32), z(1, dt=i32), z(1, dt=i32)
+        self.cur = z(N, D)
+        self._g_lockstep = None
+        self.graph_launches = 0
         self.episode_rewards = deque(maxlen=100)
         print(f"Device: {dev}")
         print(f"State dim: {D}, Action dim: {A}")
@@ -150,7 +157,9 @@ class SACTrainer:
         out = self.pi_act.forward(obs, self.N)
         self.act_count += 1
         ops.sample_tanh_gaussian(out[:, :A], out[:, A:], self.action_bound, self.cfg.log_std_min, self.cfg.log_std_max,
-                                 seed=self.seed, draw=self.act_count, deterministic=deterministic, action=self.action, want_logp=False)
+                                 seed=self.seed, draw=1, draw_base=self.ctr_act, deterministic=deterministic, action=self.action,
+                                 want_logp=False)
+        ops.counter_add(self.ctr_act, 1)
         return self.action
 
     @torch.no_grad()
@@ -171,13 +180,12 @@ class SACTrainer:
         if len(mem) < B:
             return 0.0, 0.0, 0.0
         self.update_count += 1
-        u = self.update_count
         if idx is None:
-            idx = mem.sample_indices(B, seed=self.seed, draw=u, out=self.idx)
+            idx = mem.sample_indices(B, seed=self.seed, draw=1, draw_base=self.ctr_upd, out=self.idx)
         lsmin, lsmax, bound = cfg.log_std_min, cfg.log_std_max, self.action_bound
         # ---- target (ref :233-237) ----
         out = self.pi_upd.forward(mem.next_obs, B, row_index=idx)
-        nz = noise_next if noise_next is not None else off.fill_normal(self.noise_b, seed=self.seed, entity0=0, draw=2 * u)
+        nz = noise_next if noise_next is not None else off.fill_normal(self.noise_b, seed=self.seed, entity0=0, draw=2, draw_base=self.ctr_nz)
         ops.sample_tanh_gaussian(out[:, :A], out[:, A:], bound, lsmin, lsmax, nz, action=self.act_b, logp=self.logp_b)
         off.gather_concat(mem.next_obs, idx, self.act_b, None, out=self.sa2, n=B)
         q1t, q2t = self.q1t.forward(self.sa2, B), self.q2t.forward(self.sa2, B)
@@ -193,7 +201,7 @@ class SACTrainer:
         self.critic_optimizer.step()
         # ---- actor (ref :248-255) ----
         out = self.pi_upd.forward(mem.obs, B, row_index=idx)
-        nz = noise_new if noise_new is not None else off.fill_normal(self.noise_b, seed=self.seed, entity0=0, draw=2 * u + 1)
+        nz = noise_new if noise_new is not None else off.fill_normal(self.noise_b, seed=self.seed, entity0=0, draw=3, draw_base=self.ctr_nz)
         ops.sample_tanh_gaussian(out[:, :A], out[:, A:], bound, lsmin, lsmax, nz, action=self.act_b, logp=self.logp_b,
                                  pre_tanh=self.pre_b)
         off.gather_concat(mem.obs, idx, self.act_b, None, out=self.sa2, n=B)
@@ -211,7 +219,38 @@ class SACTrainer:
         # ---- alpha (ref :257-263) and target sync (ref :265) ----
         off.sac_alpha_step(self.log_alpha, self.alpha_state, self.acc, B, self.target_entropy, cfg.lr_alpha, loss_out=self.acc[3:4])
         self.soft_update()
+        ops.counter_add(self.ctr_upd, 1)
+        ops.counter_add(self.ctr_nz, 2)
         return self.acc, self.closs
+
+    # ---------------------------------------------------------------- one lockstep (ref train() loop body :278-294)
+    def _lockstep_body(self):
+        """act -> env.step -> store -> update -> carry the observation; capture-safe once the replay holds a batch."""
+        env, mem, cur = self.env, self.memory, self.cur
+        a = self.act(cur)
+        obs, r, te, tr, nobs = env.step(a, done=self.done)
+        mem.store(cur, a, r, nobs, self.done)      # done = terminated | truncated (ref :281-283, SURVEY q11)
+        self.update()
+        cur.copy_(obs)
+
+    def lockstep(self):
+        """One lockstep of all N envs.  Eager until the replay buffer holds a batch (the update is a host-side no-op before
+        that), then one CUDA-graph replay per lockstep (cfg.use_cuda_graph)."""
+        from ..graphs import capture
+        if not getattr(self.cfg, "use_cuda_graph", True) or len(self.memory) < self.B:
+            return self._lockstep_body()
+        if self._g_lockstep is None:
+            mirrors = (self.act_count, self.update_count, self.memory._size_host)
+            self._g_lockstep = capture(self._lockstep_body)   # the capture's eager pass is this lockstep ...
+            self.act_count, self.update_count = mirrors[0] + 1, mirrors[1] + 1   # ... the recording pass is not
+            self.memory._size_host = min(self.memory.capacity, mirrors[2] + self.N)
+            return
+        self._g_lockstep.replay()
+        self.graph_launches += self._g_lockstep.n_kernels
+        # host mirrors of what the replayed body would have counted
+        self.act_count += 1
+        self.update_count += 1
+        self.memory._size_host = min(self.memory.capacity, self.memory._size_host + self.N)
 
     def losses(self):
         """(actor_loss, critic_loss, alpha_loss) as floats — one D2H, call at log time."""
@@ -221,15 +260,11 @@ class SACTrainer:
     def train(self):
         print("Starting training...")
         cfg, env, mem = self.cfg, self.env, self.memory
-        cur = env.reset().clone()
+        env.reset(out=self.cur)
         max_lock = cfg.max_locksteps or int(cfg.max_episodes * cfg.max_steps / self.N)
         t0, last_total = time.time(), 0
         for step in range(max_lock):
-            a = self.act(cur)
-            obs, r, te, tr, nobs = env.step(a, done=self.done)
-            mem.store(cur, a, r, nobs, self.done)      # done = terminated | truncated (ref :281-283)
-            self.update()
-            cur.copy_(obs)
+            self.lockstep()
             if step % cfg.max_steps == cfg.max_steps - 1:
                 avg, _, total = env.episode_stats(100)
                 if total != last_total:

@@ -255,3 +255,34 @@ def test_offpolicy_trainers_run_vectorised(algo):
     assert torch.isfinite(flat.flat).all()
     r = t.eval(4)
     assert len(r) == 4 and all(np.isfinite(r))
+
+
+@pytest.mark.parametrize("algo", ["rainbow", "sac"])
+def test_graph_lockstep_equals_eager_lockstep(algo):
+    """train()'s captured lockstep (act -> env step -> store -> update as one CUDA graph, RNG draw counters / PER beta /
+    learning rate in device scalars) leaves the same parameters, replay contents and env stream as the eager lockstep."""
+    import importlib
+    name = {"rainbow": "rainbow_dqn_cartpole", "sac": "sac_pendulum"}[algo]
+    M = importlib.import_module(f"gymrl_b200.algorithms.{name}")
+    cls = [getattr(M, k) for k in dir(M) if k.endswith("Trainer")][0]
+    res = []
+    for use_graph in (False, True):
+        cfg = M.Config()
+        cfg.num_envs, cfg.seed, cfg.batch_size, cfg.memory_capacity, cfg.use_cuda_graph = 256, 5, 256, 1 << 14, use_graph
+        torch.manual_seed(0)
+        t = cls(cfg)
+        t.env.reset(out=t.cur)
+        for _ in range(40):
+            t.lockstep()
+        torch.cuda.synchronize()
+        assert (t._g_lockstep is not None) == use_graph
+        if use_graph:
+            assert t.graph_launches > 0
+        fps = [getattr(t, k) for k in ("fp", "fp_t", "fp_a", "fp_c", "fp_ct") if hasattr(t, k)]
+        ring = t.memory.ring if hasattr(t.memory, "ring") else t.memory
+        res.append(([f.flat.clone() for f in fps], t.cur.clone(), ring.obs.clone(), ring.reward.clone(), ring.state.clone(), len(t.memory)))
+    (pa, ca, oa, ra, sa, la), (pb, cb, ob, rb, sb, lb) = res
+    assert la == lb and torch.equal(sa, sb)
+    assert torch.equal(ca, cb) and torch.equal(oa, ob) and torch.equal(ra, rb)
+    for a, b in zip(pa, pb):
+        torch.testing.assert_close(a, b, rtol=1e-6, atol=1e-7)

@@ -38,21 +38,17 @@ def c3(a):
     cfg = R.Config()
     cfg.num_envs, cfg.batch_size, cfg.memory_capacity, cfg.seed = 8192, 8192, 1 << 21, 0
     cfg.max_episodes = 10 ** 6   # keeps the LR / beta schedules away from their end points during the probe
+    cfg.use_cuda_graph = not a.eager
     tr = R.RainbowDQNTrainer(cfg)
-    cur = tr.env.reset().clone()
-
-    def step():
-        act = tr.act(cur)
-        obs, r, te, tru, nobs = tr.env.step(act, done=tr.done)
-        tr.memory.store_lockstep(cur, act, r, nobs, te & (1 - tru), tr.done)
-        tr.update()
-        cur.copy_(obs)
+    tr.env.reset(out=tr.cur)
+    step = tr.lockstep
 
     c0 = _ffi.launch_count()
     ms, wall = timed_locksteps(step, 20, a.locksteps)
-    launches = (_ffi.launch_count() - c0) / (a.locksteps + 20)
+    launches = (_ffi.launch_count() - c0 + tr.graph_launches) / (a.locksteps + 20)
     return {"config": "C3 Rainbow CartPole-v1, 8192 envs, B=8192, capacity 2^21, U=1", "ms_per_lockstep": round(ms, 4),
-            "host_ms_per_lockstep": round(wall, 4), "env_steps_per_s": round(cfg.num_envs / (ms * 1e-3)), "launches_per_lockstep": round(launches, 1)}
+            "host_ms_per_lockstep": round(wall, 4), "env_steps_per_s": round(cfg.num_envs / (ms * 1e-3)), "launches_per_lockstep": round(launches, 1),
+            "cuda_graph": not a.eager}
 
 
 def c4(a):
@@ -60,21 +56,17 @@ def c4(a):
     from gymrl_b200.algorithms import sac_pendulum as S
     cfg = S.Config()
     cfg.num_envs, cfg.batch_size, cfg.memory_capacity, cfg.seed = 4096, 4096, 1 << 20, 0
+    cfg.use_cuda_graph = not a.eager
     tr = S.SACTrainer(cfg)
-    cur = tr.env.reset().clone()
-
-    def step():
-        act = tr.act(cur)
-        obs, r, te, tru, nobs = tr.env.step(act, done=tr.done)
-        tr.memory.store(cur, act, r, nobs, tr.done)
-        tr.update()
-        cur.copy_(obs)
+    tr.env.reset(out=tr.cur)
+    step = tr.lockstep
 
     c0 = _ffi.launch_count()
     ms, wall = timed_locksteps(step, 20, a.locksteps)
-    launches = (_ffi.launch_count() - c0) / (a.locksteps + 20)
+    launches = (_ffi.launch_count() - c0 + tr.graph_launches) / (a.locksteps + 20)
     return {"config": "C4 SAC Pendulum-v1, 4096 envs, B=4096, capacity 2^20, U=1", "ms_per_lockstep": round(ms, 4),
-            "host_ms_per_lockstep": round(wall, 4), "env_steps_per_s": round(cfg.num_envs / (ms * 1e-3)), "launches_per_lockstep": round(launches, 1)}
+            "host_ms_per_lockstep": round(wall, 4), "env_steps_per_s": round(cfg.num_envs / (ms * 1e-3)), "launches_per_lockstep": round(launches, 1),
+            "cuda_graph": not a.eager}
 
 
 def c5(a):
@@ -101,6 +93,7 @@ def main():
     ap = argparse.ArgumentParser()
     ap.add_argument("which", nargs="*", default=["c3", "c4", "c5"])
     ap.add_argument("--locksteps", type=int, default=300)
+    ap.add_argument("--eager", action="store_true", help="off-policy locksteps as eager launches instead of one CUDA graph")
     a = ap.parse_args()
     for w in a.which:
         print(json.dumps({"c3": c3, "c4": c4, "c5": c5}[w](a)), flush=True)
