@@ -77,6 +77,14 @@ static inline v2 cross_vs(v2 a, float s) { return V(s * a.y, -s * a.x); }  /* b2
 static inline v2 cross_sv(float s, v2 a) { return V(-s * a.y, s * a.x); }  /* b2Cross(s, v) */
 static inline float clampf(float a, float lo, float hi) { return fmaxf(lo, fminf(a, hi)); }
 
+/* Fused helpers of the velocity iterations (the step's serial chain): explicit fmaf, so that the CUDA kernel (built with
+ * -fmad=false) and this file (built with -ffp-contract=off) fuse exactly the same multiply-adds and round alike. */
+static inline float fdot(v2 a, v2 b) { return fmaf(a.x, b.x, a.y * b.y); }
+static inline float fcross(v2 a, v2 b) { return fmaf(a.x, b.y, -(a.y * b.x)); }
+static inline v2 axpy(float s, v2 x, v2 y) { return V(fmaf(s, x.x, y.x), fmaf(s, x.y, y.y)); }                 /* y + s x */
+static inline v2 add_cross_sv(v2 a, float s, v2 r) { return V(fmaf(-s, r.y, a.x), fmaf(s, r.x, a.y)); }       /* a + b2Cross(s, r) */
+static inline v2 sub_cross_sv(v2 a, float s, v2 r) { return V(fmaf(s, r.y, a.x), fmaf(-s, r.x, a.y)); }       /* a - b2Cross(s, r) */
+
 /* ---- fixed-sequence sin/cos (Cody-Waite pi/2 reduction + cephes minimax polynomials) ---------- */
 static void det_sincosf(float a, float* s, float* c) {
     const float k = rintf(a * 0.636619772367581343f);
@@ -747,16 +755,15 @@ static void ll_world_step(LLEnv* e) {
             /* motor */
             if (J->limit_state != 3) {
                 float Cdot = wB - wA - joint_motor_speed(j);
-                float impulse = -motor_mass[j] * Cdot;
                 float old = J->motor_impulse;
                 float maxImp = h * (float)LEG_SPRING_TORQUE;
-                J->motor_impulse = clampf(old + impulse, -maxImp, maxImp);
-                impulse = J->motor_impulse - old;
-                wA -= iA * impulse;
-                wB += iB * impulse;
+                J->motor_impulse = clampf(fmaf(-motor_mass[j], Cdot, old), -maxImp, maxImp);
+                float impulse = J->motor_impulse - old;
+                wA = fmaf(-iA, impulse, wA);
+                wB = fmaf(iB, impulse, wB);
             }
             if (J->limit_state != 0) {
-                v2 Cdot1 = sub(sub(add(vB, cross_sv(wB, rBj[j])), vA), cross_sv(wA, rA[j]));
+                v2 Cdot1 = sub_cross_sv(sub(add_cross_sv(vB, wB, rBj[j]), vA), wA, rA[j]);
                 float Cdot2 = wB - wA;
                 /* impulse = -Solve33(Cdot) */
                 float ix, iy, iz;
@@ -768,13 +775,13 @@ static void ll_world_step(LLEnv* e) {
                     if (det != 0.0f) det = 1.0f / det;
                     float bx = Cdot1.x, by = Cdot1.y, bz = Cdot2;
                     /* x = det * dot(b, cross(ey, ez)) */
-                    float sx = det * (bx * cx + by * cy + bz * cz);
+                    float sx = det * fmaf(bx, cx, fmaf(by, cy, bz * cz));
                     /* y = det * dot(ex, cross(b, ez)) */
-                    float c2x = by * ezz - bz * ezy, c2y = bz * ezx - bx * ezz, c2z = bx * ezy - by * ezx;
-                    float sy = det * (exx * c2x + exy * c2y + exz * c2z);
+                    float c2x = fmaf(by, ezz, -(bz * ezy)), c2y = fmaf(bz, ezx, -(bx * ezz)), c2z = fmaf(bx, ezy, -(by * ezx));
+                    float sy = det * fmaf(exx, c2x, fmaf(exy, c2y, exz * c2z));
                     /* z = det * dot(ex, cross(ey, b)) */
-                    float c3x = eyy * bz - eyz * by, c3y = eyz * bx - eyx * bz, c3z = eyx * by - eyy * bx;
-                    float sz = det * (exx * c3x + exy * c3y + exz * c3z);
+                    float c3x = fmaf(eyy, bz, -(eyz * by)), c3y = fmaf(eyz, bx, -(eyx * bz)), c3z = fmaf(eyx, by, -(eyy * bx));
+                    float sz = det * fmaf(exx, c3x, fmaf(exy, c3y, exz * c3z));
                     ix = -sx; iy = -sy; iz = -sz;
                 }
                 if (J->limit_state == 3) {
@@ -783,13 +790,13 @@ static void ll_world_step(LLEnv* e) {
                     float newImpulse = J->imp_z + iz;
                     int violate = J->limit_state == 1 ? (newImpulse < 0.0f) : (newImpulse > 0.0f);
                     if (violate) {
-                        v2 rhs = add(neg(Cdot1), mul(J->imp_z, V(M[6], M[7])));
+                        v2 rhs = axpy(J->imp_z, V(M[6], M[7]), neg(Cdot1));
                         /* Solve22 */
                         float a11 = M[0], a12 = M[3], a21 = M[1], a22 = M[4];
                         float det = a11 * a22 - a12 * a21;
                         if (det != 0.0f) det = 1.0f / det;
-                        float rx = det * (a22 * rhs.x - a12 * rhs.y);
-                        float ry = det * (a11 * rhs.y - a21 * rhs.x);
+                        float rx = det * fmaf(a22, rhs.x, -(a12 * rhs.y));
+                        float ry = det * fmaf(a11, rhs.y, -(a21 * rhs.x));
                         ix = rx; iy = ry; iz = -J->imp_z;
                         J->imp_x += rx; J->imp_y += ry; J->imp_z = 0.0f;
                     } else {
@@ -797,22 +804,22 @@ static void ll_world_step(LLEnv* e) {
                     }
                 }
                 v2 P = V(ix, iy);
-                vA = sub(vA, mul(mA, P));
-                wA -= iA * (cross(rA[j], P) + iz);
-                vB = add(vB, mul(mB, P));
-                wB += iB * (cross(rBj[j], P) + iz);
+                vA = axpy(-mA, P, vA);
+                wA = fmaf(-iA, fcross(rA[j], P) + iz, wA);
+                vB = axpy(mB, P, vB);
+                wB = fmaf(iB, fcross(rBj[j], P) + iz, wB);
             } else {
-                v2 Cdot = sub(sub(add(vB, cross_sv(wB, rBj[j])), vA), cross_sv(wA, rA[j]));
+                v2 Cdot = sub_cross_sv(sub(add_cross_sv(vB, wB, rBj[j]), vA), wA, rA[j]);
                 float a11 = M[0], a12 = M[3], a21 = M[1], a22 = M[4];
                 float det = a11 * a22 - a12 * a21;
                 if (det != 0.0f) det = 1.0f / det;
                 float bx = -Cdot.x, by = -Cdot.y;
-                v2 imp = V(det * (a22 * bx - a12 * by), det * (a11 * by - a21 * bx));
+                v2 imp = V(det * fmaf(a22, bx, -(a12 * by)), det * fmaf(a11, by, -(a21 * bx)));
                 J->imp_x += imp.x; J->imp_y += imp.y;
-                vA = sub(vA, mul(mA, imp));
-                wA -= iA * cross(rA[j], imp);
-                vB = add(vB, mul(mB, imp));
-                wB += iB * cross(rBj[j], imp);
+                vA = axpy(-mA, imp, vA);
+                wA = fmaf(-iA, fcross(rA[j], imp), wA);
+                vB = axpy(mB, imp, vB);
+                wB = fmaf(iB, fcross(rBj[j], imp), wB);
             }
             B[bA].v = vA; B[bA].w = wA; B[bB].v = vB; B[bB].w = wB;
         }
@@ -824,49 +831,47 @@ static void ll_world_step(LLEnv* e) {
             float wB = B[b].w;
             v2 normal = c->normal, tangent = cross_vs(normal, 1.0f);
             for (int j = 0; j < c->vc_count; ++j) {
-                v2 dv = add(vB, cross_sv(wB, c->rB[j]));
-                float vt = dot(dv, tangent) - 0.0f;
-                float lambda = c->tangent_mass[j] * (-vt);
+                v2 dv = add_cross_sv(vB, wB, c->rB[j]);
+                float vt = fdot(dv, tangent) - 0.0f;
                 float maxF = c->friction * c->nimp[j];
-                float newImp = clampf(c->timp[j] + lambda, -maxF, maxF);
-                lambda = newImp - c->timp[j];
+                float newImp = clampf(fmaf(c->tangent_mass[j], -vt, c->timp[j]), -maxF, maxF);
+                float lambda = newImp - c->timp[j];
                 c->timp[j] = newImp;
                 v2 P = mul(lambda, tangent);
-                vB = add(vB, mul(mB, P));
-                wB += iB * cross(c->rB[j], P);
+                vB = axpy(mB, P, vB);
+                wB = fmaf(iB, fcross(c->rB[j], P), wB);
             }
             if (c->vc_count == 1) {
-                v2 dv = add(vB, cross_sv(wB, c->rB[0]));
-                float vn = dot(dv, normal);
-                float lambda = -c->normal_mass[0] * (vn - c->velocity_bias[0]);
-                float newImp = fmaxf(c->nimp[0] + lambda, 0.0f);
-                lambda = newImp - c->nimp[0];
+                v2 dv = add_cross_sv(vB, wB, c->rB[0]);
+                float vn = fdot(dv, normal);
+                float newImp = fmaxf(fmaf(-c->normal_mass[0], vn - c->velocity_bias[0], c->nimp[0]), 0.0f);
+                float lambda = newImp - c->nimp[0];
                 c->nimp[0] = newImp;
                 v2 P = mul(lambda, normal);
-                vB = add(vB, mul(mB, P));
-                wB += iB * cross(c->rB[0], P);
+                vB = axpy(mB, P, vB);
+                wB = fmaf(iB, fcross(c->rB[0], P), wB);
             } else {
                 float a0 = c->nimp[0], a1 = c->nimp[1];
-                v2 dv1 = add(vB, cross_sv(wB, c->rB[0]));
-                v2 dv2 = add(vB, cross_sv(wB, c->rB[1]));
-                float vn1 = dot(dv1, normal), vn2 = dot(dv2, normal);
+                v2 dv1 = add_cross_sv(vB, wB, c->rB[0]);
+                v2 dv2 = add_cross_sv(vB, wB, c->rB[1]);
+                float vn1 = fdot(dv1, normal), vn2 = fdot(dv2, normal);
                 float bx = vn1 - c->velocity_bias[0], by = vn2 - c->velocity_bias[1];
-                bx -= c->K11 * a0 + c->K12 * a1;
-                by -= c->K12 * a0 + c->K22 * a1;
+                bx -= fmaf(c->K11, a0, c->K12 * a1);
+                by -= fmaf(c->K12, a0, c->K22 * a1);
                 float x0, x1;
                 int solved = 0;
                 /* case 1 */
-                x0 = -(c->NM11 * bx + c->NM21 * by);
-                x1 = -(c->NM12 * bx + c->NM22 * by);
+                x0 = -fmaf(c->NM11, bx, c->NM21 * by);
+                x1 = -fmaf(c->NM12, bx, c->NM22 * by);
                 if (x0 >= 0.0f && x1 >= 0.0f) solved = 1;
                 if (!solved) { /* case 2 */
                     x0 = -c->normal_mass[0] * bx; x1 = 0.0f;
-                    vn2 = c->K12 * x0 + by;
+                    vn2 = fmaf(c->K12, x0, by);
                     if (x0 >= 0.0f && vn2 >= 0.0f) solved = 1;
                 }
                 if (!solved) { /* case 3 */
                     x0 = 0.0f; x1 = -c->normal_mass[1] * by;
-                    vn1 = c->K12 * x1 + bx;
+                    vn1 = fmaf(c->K12, x1, bx);
                     if (x1 >= 0.0f && vn1 >= 0.0f) solved = 1;
                 }
                 if (!solved) { /* case 4 */
@@ -876,8 +881,8 @@ static void ll_world_step(LLEnv* e) {
                 if (solved) {
                     float d0 = x0 - a0, d1 = x1 - a1;
                     v2 P1 = mul(d0, normal), P2 = mul(d1, normal);
-                    vB = add(vB, mul(mB, add(P1, P2)));
-                    wB += iB * (cross(c->rB[0], P1) + cross(c->rB[1], P2));
+                    vB = axpy(mB, add(P1, P2), vB);
+                    wB = fmaf(iB, fcross(c->rB[0], P1) + fcross(c->rB[1], P2), wB);
                     c->nimp[0] = x0; c->nimp[1] = x1;
                 }
             }
