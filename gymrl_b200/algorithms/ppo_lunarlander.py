@@ -67,6 +67,7 @@ class Config:
         self.num_minibatches = None
         self.reset_each_rollout = None
         self.use_cuda_graph = True
+        self.dist_epoch_graph = True   # multi-GPU: capture the per-minibatch NCCL all-reduce inside the epoch graph
         self.fused_heads = True   # heads + loss + heads backward as one kernel where the shape allows (H in {128,256}, 4 actions)
 
 
@@ -407,7 +408,15 @@ class PPOTrainer:
         for w in range(self.n_mb):
             self._minibatch_body(w)
 
-    def _capture(self, fn):
+    def _epoch_body_dist(self):
+        """Multi-GPU epoch: per minibatch backward -> the gradient sum-all-reduce -> clip + Adam, all on one stream so the
+        whole epoch (NCCL kernels included) can be one CUDA graph."""
+        for w in range(self.n_mb):
+            self._fwd_bwd_body(w)
+            gdist.allreduce_sum_(self.net.fp.grad)
+            self._opt_body()
+
+    def _capture(self, fn, error_mode: str = "global"):
         torch.cuda.synchronize()
         s = torch.cuda.Stream()
         s.wait_stream(torch.cuda.current_stream())
@@ -417,7 +426,7 @@ class PPOTrainer:
         torch.cuda.synchronize()
         g = torch.cuda.CUDAGraph()
         c0 = _ffi.launch_count()
-        with torch.cuda.graph(g):
+        with torch.cuda.graph(g, capture_error_mode=error_mode):
             fn()
         g.n_kernels = _ffi.launch_count() - c0   # our kernels recorded in this graph (one launch call each)
         return g
@@ -445,6 +454,10 @@ class PPOTrainer:
             self._g_epoch = self._capture(self._epoch_body)
         elif self.world == 1:
             self._g_mb = self._capture(self._minibatch_body)
+        elif getattr(self.cfg, "dist_epoch_graph", True) and self.n_mb <= self.MAX_EPOCH_GRAPH_MINIBATCHES:
+            # NCCL collectives are capturable: one graph per epoch instead of 2 replays + 1 eager all-reduce per minibatch.
+            # thread_local: the NCCL watchdog thread may touch CUDA while this thread captures.
+            self._g_epoch = self._capture(self._epoch_body_dist, error_mode="thread_local")
         else:
             self._g_mb_bwd = self._capture(self._fwd_bwd_body)
             self._g_opt = self._capture(self._opt_body)

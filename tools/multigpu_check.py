@@ -17,11 +17,27 @@ import torch.distributed as dist
 sys.path.insert(0, str(Path(__file__).resolve().parent.parent))
 
 
-def make_trainer(P, n_envs, graph=False):
+def make_trainer(P, n_envs, graph=False, n_mb=1, epochs=1):
     cfg = P.Config()
-    cfg.num_envs, cfg.num_steps, cfg.num_minibatches, cfg.num_epochs, cfg.seed, cfg.use_cuda_graph = n_envs, 16, 1, 1, 11, graph
+    cfg.num_envs, cfg.num_steps, cfg.num_minibatches, cfg.num_epochs, cfg.seed, cfg.use_cuda_graph = n_envs, 16, n_mb, epochs, 11, graph
     torch.manual_seed(0)
     return P.PPOTrainer(cfg)
+
+
+def graph_vs_eager(P, N):
+    """The epoch graph with the captured NCCL all-reduce must leave the parameters of the eager multi-GPU path
+    (2 epochs x 2 minibatches; rollout buffers are made identical by construction: same seeds, same shard)."""
+    flats = []
+    for graph in (False, True):
+        tr = make_trainer(P, N, graph=graph, n_mb=2, epochs=2)
+        tr.cfg.use_cuda_graph = False           # eager rollout in both, so the two runs see identical buffers
+        tr.collect_rollout()
+        tr.cfg.use_cuda_graph = graph
+        tr.update(None)
+        if graph:
+            assert tr._g_epoch is not None, "the distributed epoch graph was not captured"
+        flats.append(tr.net.fp.flat.clone())
+    return (flats[0] - flats[1]).abs().max().item()
 
 
 def main():
@@ -65,6 +81,11 @@ def main():
               f"max |param diff| vs single GPU on the concatenated batch: {dpar:.3e} (param scale {scale:.2f})")
         ok = bool(same.item()) and e_obs and e_act and dpar < 2e-5
         print("MULTIGPU_CHECK", "PASS" if ok else "FAIL")
+    dgraph = graph_vs_eager(P, N)
+    if rank == 0:
+        print(f"epoch graph (captured all-reduce) vs eager multi-GPU update: max |param diff| {dgraph:.3e}")
+        ok = ok and dgraph < 1e-6
+        print("MULTIGPU_GRAPH_CHECK", "PASS" if dgraph < 1e-6 else "FAIL")
     dist.barrier()
     dist.destroy_process_group()
     sys.exit(0 if ok else 1)
