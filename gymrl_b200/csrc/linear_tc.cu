@@ -21,6 +21,7 @@
 // copy cannot produce them; staging is plain coalesced 128 B row reads instead.
 // All mbarrier waits are bounded (trap on timeout) so a descriptor bug cannot hang the GPU.
 #include "common.cuh"
+#include <cstdlib>
 
 void gymrl_count_launch(int n = 1);
 
@@ -474,6 +475,231 @@ __global__ void __launch_bounds__(TC_LAUNCH_THREADS, 1) gemm_tf32x3_kernel(const
     }
 }
 
+
+// =====================================================================================================================
+// Variant with the A operand in tensor memory (tcgen05.mma "TS" form).
+// The SS kernel above is bound by the 128 B/clk shared-memory port: per 32-k slab the tensor core reads 12 x (4 KB A + BN*32 B)
+// and the converters write both operands' hi/lo images (240 KB at BN = 256 -> 1875 cycles against 1536 cycles of MMA).
+// Here the converters write A's hi/lo images straight into TMEM with tcgen05.st (lane = output row, column = k), so A costs
+// no shared-memory traffic at all (160 KB per slab -> 1250 cycles: the MMAs become the bound) and the stage ring holds B only,
+// which makes room for a third stage.  TMEM: columns [0, BN) accumulator, then NST x 64 columns of A (hi 32 | lo 32).
+// A thread owns one row of the tile and half of the slab's 32 k-values (two warps per TMEM lane quarter):
+//   K-major A  (A[m][k]):  four LDG.128 from its own row (64 contiguous bytes);
+//   MN-major A (A[k][m]):  sixteen LDG.32, coalesced across the warp (the transposition costs nothing: TMEM is written row-wise).
+// =====================================================================================================================
+template <int NREG>
+__device__ __forceinline__ void tmem_st16(uint32_t taddr, const uint32_t (&r)[NREG]) {
+    static_assert(NREG == 16, "x16");
+    asm volatile(
+        "tcgen05.st.sync.aligned.32x32b.x16.b32 [%0], {%1, %2, %3, %4, %5, %6, %7, %8, %9, %10, %11, %12, %13, %14, %15, %16};"
+        ::"r"(taddr), "r"(r[0]), "r"(r[1]), "r"(r[2]), "r"(r[3]), "r"(r[4]), "r"(r[5]), "r"(r[6]), "r"(r[7]), "r"(r[8]), "r"(r[9]),
+          "r"(r[10]), "r"(r[11]), "r"(r[12]), "r"(r[13]), "r"(r[14]), "r"(r[15]) : "memory");
+}
+__device__ __forceinline__ void umma_tf32_ts(uint32_t tmem_d, uint32_t tmem_a, uint64_t desc_b, uint32_t idesc, uint32_t accumulate) {
+    asm volatile("{\n.reg .pred p;\nsetp.ne.b32 p, %4, 0;\ntcgen05.mma.cta_group::1.kind::tf32 [%0], [%1], %2, %3, p;\n}\n"
+                 ::"r"(tmem_d), "r"(tmem_a), "l"(desc_b), "r"(idesc), "r"(accumulate) : "memory");
+}
+
+// A-operand loader of one thread: 16 k-values of its row per slab.
+template <bool KMAJOR>
+struct ARowLoader {
+    const float* ptr;
+    long long ld;
+    __device__ __forceinline__ void init(const float* g, int ld_, const int32_t* rows_, int row, int m_total, int kbeg, int khalf) {
+        const int m = min(row, m_total - 1);   // out-of-range rows are clamped onto a valid one (their outputs are never written)
+        ld = ld_;
+        if (KMAJOR) ptr = g + (rows_ ? (long long)rows_[m] : (long long)m) * ld_ + kbeg + 16 * khalf;
+        else ptr = g + (long long)(kbeg + 16 * khalf) * ld_ + m;
+    }
+    __device__ __forceinline__ void load(float (&v)[16]) {
+        if (KMAJOR) {
+#pragma unroll
+            for (int i = 0; i < 4; ++i) {
+                const float4 q = __ldg(reinterpret_cast<const float4*>(ptr) + i);
+                v[4 * i] = q.x; v[4 * i + 1] = q.y; v[4 * i + 2] = q.z; v[4 * i + 3] = q.w;
+            }
+            ptr += 32;
+        } else {
+#pragma unroll
+            for (int i = 0; i < 16; ++i) v[i] = __ldg(ptr + (long long)i * ld);
+            ptr += 32 * ld;
+        }
+    }
+};
+
+template <int BN, bool A_KMAJOR, bool B_KMAJOR>
+__global__ void __launch_bounds__(TC_LAUNCH_THREADS, 1) gemm_tf32x3_ts_kernel(const TcGemmParams p) {
+    constexpr int BM = 128;
+    constexpr int NST = BN == 256 ? 3 : 4;                                // B-only stages: 64 KB each at BN = 256
+    constexpr uint32_t B_BYTES = BN * 128;                                // one image (hi or lo) of one 32-k slab of B
+    constexpr uint32_t STAGE_BYTES = 2 * B_BYTES;
+    constexpr uint32_t TMEM_COLS = (BN + 64 * NST) <= 256 ? 256 : 512;
+    static_assert(BN + 64 * NST <= 512, "TMEM columns");
+    extern __shared__ __align__(1024) uint8_t smem_raw[];
+    uint8_t* smem = reinterpret_cast<uint8_t*>((reinterpret_cast<uintptr_t>(smem_raw) + 1023) & ~(uintptr_t)1023);
+    __shared__ __align__(8) uint64_t bar_full[NST];   // producers -> MMA warp: stage converted (TC_THREADS arrivals)
+    __shared__ __align__(8) uint64_t bar_free[NST];   // tensor core -> producers: the MMAs reading the stage retired
+    __shared__ __align__(8) uint64_t bar_acc;         // tensor core -> epilogue: accumulator complete
+    __shared__ uint32_t tmem_base_s;
+
+    const int t = threadIdx.x, warp = t >> 5, lane = t & 31;
+    const int m0 = blockIdx.y * BM, n0 = blockIdx.x * BN;
+    long long* cdbg = (g_tc_cta_dbg && t == 0) ? g_tc_cta_dbg + 8ll * (blockIdx.x + gridDim.x * (blockIdx.y + gridDim.y * blockIdx.z)) : nullptr;
+    TC_GSTAMP(0);
+    if (cdbg) { uint32_t smid; asm volatile("mov.u32 %0, %%smid;" : "=r"(smid)); cdbg[6] = smid; }
+    const int kbeg = blockIdx.z * p.k_chunk;
+    const int kend = min(p.K, kbeg + p.k_chunk);
+    const int nslab = (kend - kbeg + 31) / 32;
+
+    if (t == 0) {
+#pragma unroll
+        for (int s = 0; s < NST; ++s) { mbar_init(&bar_full[s], TC_THREADS); mbar_init(&bar_free[s], 1); }
+        mbar_init(&bar_acc, 1);
+        asm volatile("fence.mbarrier_init.release.cluster;" ::: "memory");
+    }
+    if (warp == 0) {
+        asm volatile("tcgen05.alloc.cta_group::1.sync.aligned.shared::cta.b32 [%0], %1;" ::"r"(smem_u32(&tmem_base_s)), "n"(TMEM_COLS) : "memory");
+        asm volatile("tcgen05.relinquish_alloc_permit.cta_group::1.sync.aligned;" ::: "memory");
+    }
+    asm volatile("tcgen05.fence::before_thread_sync;" ::: "memory");
+    __syncthreads();
+    asm volatile("tcgen05.fence::after_thread_sync;" ::: "memory");
+    const uint32_t tmem_d = tmem_base_s;
+    long long* dbg = nullptr;
+    TC_GSTAMP(1);
+
+    if (warp == TC_THREADS / 32) {
+        // ===== MMA-issue warp =====
+        if (lane == 0) {
+            // A from TMEM is always K-major in the descriptor
+            constexpr uint32_t IDESC = (1u << 4) | (2u << 7) | (2u << 10) | (0u << 15) | ((B_KMAJOR ? 0u : 1u) << 16) |
+                                       ((uint32_t)(BN >> 3) << 17) | ((uint32_t)(BM >> 4) << 24);
+            int s = 0, ph = 0;
+            for (int kb = 0; kb < nslab; ++kb) {
+                mbar_wait(&bar_full[s], (uint32_t)ph);
+                asm volatile("tcgen05.fence::after_thread_sync;" ::: "memory");
+                const uint32_t st = smem_u32(smem + (size_t)s * STAGE_BYTES);
+                const uint32_t bh = st, bl = st + B_BYTES;
+                const uint32_t a_hi = tmem_d + (uint32_t)(BN + 64 * s), a_lo = a_hi + 32u;
+#pragma unroll
+                for (int j = 0; j < 4; ++j) {   // 4 k-steps of 8
+                    const uint64_t dbh = B_KMAJOR ? make_desc(bh + j * 32, 16, 1024) : make_desc_mn<BN>(bh, j);
+                    const uint64_t dbl = B_KMAJOR ? make_desc(bl + j * 32, 16, 1024) : make_desc_mn<BN>(bl, j);
+                    umma_tf32_ts(tmem_d, a_lo + 8u * j, dbh, IDESC, (kb | j) ? 1u : 0u);
+                    umma_tf32_ts(tmem_d, a_hi + 8u * j, dbl, IDESC, 1u);
+                    umma_tf32_ts(tmem_d, a_hi + 8u * j, dbh, IDESC, 1u);
+                }
+                umma_commit(&bar_free[s]);
+                if (kb == nslab - 1) umma_commit(&bar_acc);
+                if (++s == NST) { s = 0; ph ^= 1; }
+            }
+        }
+    } else {
+        // ===== producer warps =====
+        const uint32_t smem_base = smem_u32(smem);
+        const int lane_q = warp & 3, khalf = warp >> 2;
+        ARowLoader<A_KMAJOR> la;
+        la.init(p.A, p.lda, A_KMAJOR ? p.a_rows : nullptr, m0 + lane_q * 32 + lane, p.M, kbeg, khalf);
+        Stager<BN, B_KMAJOR> sb;
+        sb.init(p.B, p.ldb, p.b_rows, n0, p.N, kbeg);
+        float va0[16], va1[16];
+        float4 vb0[Stager<BN, B_KMAJOR>::PASSES], vb1[Stager<BN, B_KMAJOR>::PASSES];
+        const bool do_colsum = !A_KMAJOR && p.colsum != nullptr && blockIdx.x == 0;
+        float csum = 0.f;
+        const uint32_t a_lane = tmem_d + ((uint32_t)(lane_q * 32) << 16) + (uint32_t)(BN + 16 * khalf);
+        int s = 0, ph = 0;
+
+        auto consume = [&](int kb, const float (&va)[16], const float4 (&vb)[Stager<BN, B_KMAJOR>::PASSES]) {
+            if (kb >= NST) mbar_wait(&bar_free[s], (uint32_t)(ph ^ 1));   // the MMAs that read this stage have retired
+            asm volatile("tcgen05.fence::after_thread_sync;" ::: "memory");
+            uint32_t hi[16], lo[16];
+#pragma unroll
+            for (int i = 0; i < 16; ++i) {
+                hi[i] = to_tf32(va[i]);
+                lo[i] = to_tf32(va[i] - __uint_as_float(hi[i]));
+            }
+            const uint32_t ta = a_lane + (uint32_t)(64 * s);
+            tmem_st16(ta, hi);
+            tmem_st16(ta + 32u, lo);
+            const uint32_t st = smem_base + (uint32_t)s * STAGE_BYTES;
+            sb.store(st, st + B_BYTES, vb);
+            if (!A_KMAJOR && do_colsum) {
+#pragma unroll
+                for (int i = 0; i < 16; ++i) csum += va[i];
+            }
+            asm volatile("tcgen05.wait::st.sync.aligned;" ::: "memory");
+            asm volatile("tcgen05.fence::before_thread_sync;" ::: "memory");
+            asm volatile("fence.proxy.async.shared::cta;" ::: "memory");
+            mbar_arrive(&bar_full[s]);
+            if (++s == NST) { s = 0; ph ^= 1; }
+        };
+
+        if (nslab > 0) { la.load(va0); sb.load(vb0); }
+        for (int kb = 0; kb < nslab; kb += 2) {
+            if (kb + 1 < nslab) { la.load(va1); sb.load(vb1); }
+            consume(kb, va0, vb0);
+            if (kb + 1 < nslab) {
+                if (kb + 2 < nslab) { la.load(va0); sb.load(vb0); }
+                consume(kb + 1, va1, vb1);
+            }
+        }
+
+        // ---- epilogue ----
+        TC_GSTAMP(2);
+        if (nslab > 0) mbar_wait(&bar_acc, 0);
+        TC_GSTAMP(3);
+        asm volatile("tcgen05.fence::after_thread_sync;" ::: "memory");
+        if (!A_KMAJOR && do_colsum) {
+            // a thread summed its row's 16 k-values per slab: fold the two k-halves of a row in fixed order
+            float* red = reinterpret_cast<float*>(smem + 32 * 1024);
+            red[khalf * BM + lane_q * 32 + lane] = csum;
+            producers_sync();
+            if (t < BM && m0 + t < p.M) p.colsum[(long long)blockIdx.z * p.M + m0 + t] = red[t] + red[BM + t];
+        }
+        const int col_half = warp >> 2;
+        float* Cbase = p.C + (long long)blockIdx.z * p.c_split_stride;
+        EpiArgs ea;
+        ea.scr = smem_base + (uint32_t)warp * 4096u; ea.tmem_row = tmem_d + ((uint32_t)(lane_q * 32) << 16); ea.lane = lane;
+        ea.c_begin = col_half * (BN / 2); ea.c_end = (col_half + 1) * (BN / 2);
+        ea.m_base = m0 + lane_q * 32; ea.n0 = n0; ea.C = Cbase; ea.have_acc = nslab > 0; ea.dbg = dbg;
+        if (p.H == nullptr) {
+            if (p.act == GYMRL_ACT_TANH) epilogue_chunks<EPI_TANH>(p, ea);
+            else if (p.act == GYMRL_ACT_RELU) epilogue_chunks<EPI_RELU>(p, ea);
+            else epilogue_chunks<EPI_PLAIN>(p, ea);
+        } else if (p.act == GYMRL_ACT_NONE && p.act_in == GYMRL_ACT_TANH) {
+            epilogue_chunks<EPI_DTANH>(p, ea);
+        } else if (p.act == GYMRL_ACT_NONE && p.act_in == GYMRL_ACT_RELU) {
+            epilogue_chunks<EPI_DRELU>(p, ea);
+        } else {
+            epilogue_chunks<EPI_GENERIC>(p, ea);
+        }
+        TC_GSTAMP(4);
+    }
+    asm volatile("tcgen05.fence::before_thread_sync;" ::: "memory");
+    __syncthreads();
+    TC_GSTAMP(5);
+    if (warp == 0) {
+        asm volatile("tcgen05.dealloc.cta_group::1.sync.aligned.b32 %0, %1;" ::"r"(tmem_d), "n"(TMEM_COLS) : "memory");
+    }
+}
+
+template <int BN, bool AK, bool BKM>
+static int launch_tc_ts(const TcGemmParams& p, int splits, cudaStream_t s) {
+    constexpr int NST = BN == 256 ? 3 : 4;
+    constexpr size_t STAGES = (size_t)NST * 2 * BN * 128;
+    constexpr size_t SMEM = (STAGES > 40 * 1024 ? STAGES : 40 * 1024) + 1024;   // >= 32 KB epilogue scratch + colsum fold
+    static bool configured = false;
+    if (!configured) {
+        cudaError_t e = cudaFuncSetAttribute(gemm_tf32x3_ts_kernel<BN, AK, BKM>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)SMEM);
+        if (e != cudaSuccess) GYMRL_FAIL(GYMRL_ECUDA, "cudaFuncSetAttribute(smem=%zu) failed: %s", SMEM, cudaGetErrorString(e));
+        configured = true;
+    }
+    dim3 grid(p.N / BN, ceil_div(p.M, 128), splits);
+    gemm_tf32x3_ts_kernel<BN, AK, BKM><<<grid, TC_LAUNCH_THREADS, SMEM, s>>>(p);
+    gymrl_count_launch();
+    return GYMRL_OK;
+}
+
 // ---- host side ------------------------------------------------------------------------------------------
 template <int BN, bool AK, bool BKM>
 static int launch_tc(const TcGemmParams& p, int splits, cudaStream_t s) {
@@ -509,11 +735,17 @@ int tc_gemm_launch(const TcGemmParams& p, bool a_kmajor, bool b_kmajor, int spli
     int bn = 64;
     if (p.N % 256 == 0 && mt * (p.N / 256) >= 120) bn = 256;
     else if (p.N % 128 == 0 && mt * (p.N / 128) >= 120) bn = 128;
-#define TC_DISPATCH(AK, BKM)                                             \
-    switch (bn) {                                                        \
-        case 256: return launch_tc<256, AK, BKM>(p, splits, s);          \
-        case 128: return launch_tc<128, AK, BKM>(p, splits, s);          \
-        default: return launch_tc<64, AK, BKM>(p, splits, s);            \
+    // A through tensor memory (TS kernel) for MN-major A, i.e. the dW GEMMs: there a thread's 16 k-values of its row are
+    // coalesced loads and the variant measured 8 % faster (26.9 -> 24.7 us at 512 x 256 x 16384).  For K-major A the row-owned
+    // 64 B loads touch 32 lines per instruction and it measured 10 % slower than the SS kernel (17.2 -> 18.9 us at
+    // 16384 x 256 x 256), so those stay on the shared-memory path.  GYMRL_TC_ATMEM = 0 / 1 / 2: never / MN-major only / always.
+    static const int atmem_env = [] { const char* e = getenv("GYMRL_TC_ATMEM"); return e ? atoi(e) : 1; }();
+    const bool atmem = atmem_env == 2 ? (a_kmajor || p.a_rows == nullptr) : (atmem_env == 1 && !a_kmajor && p.a_rows == nullptr);
+#define TC_DISPATCH(AK, BKM)                                                                                   \
+    switch (bn) {                                                                                              \
+        case 256: return atmem ? launch_tc_ts<256, AK, BKM>(p, splits, s) : launch_tc<256, AK, BKM>(p, splits, s); \
+        case 128: return atmem ? launch_tc_ts<128, AK, BKM>(p, splits, s) : launch_tc<128, AK, BKM>(p, splits, s); \
+        default: return atmem ? launch_tc_ts<64, AK, BKM>(p, splits, s) : launch_tc<64, AK, BKM>(p, splits, s);    \
     }
     if (a_kmajor && b_kmajor) { TC_DISPATCH(true, true) }
     if (a_kmajor && !b_kmajor) { TC_DISPATCH(true, false) }
