@@ -32,7 +32,9 @@ namespace {
 constexpr int kWarpsPerBlock = 8;
 constexpr int kMaxBlocks = 2 * GYMRL_NUM_SMS;
 
-__device__ __forceinline__ float sigmoidf_(float x) { return 1.0f / (1.0f + expf(-x)); }
+// 1 / (1 + e^-x) with ex2.approx / rcp.approx (a few ulp): the IEEE expf + division pair costs ~25 instructions per element and
+// the SiLU / SiLU' of every activation element goes through it (parity: same golden tolerances).
+__device__ __forceinline__ float sigmoidf_(float x) { return rcp_approx(1.0f + exp2f_approx(-1.4426950408889634f * x)); }
 __device__ __forceinline__ float siluf_(float x) { return x * sigmoidf_(x); }
 __device__ __forceinline__ float silu_gradf_(float x) {
     const float s = sigmoidf_(x);
@@ -102,10 +104,13 @@ __device__ __forceinline__ void stage_coefficients(const float4 (&h)[2][NCH], co
     float u0 = 1.f, u1 = 1.f, v0 = 1.f, v1 = 1.f;
     const float eps = 1e-8f;
     for (int it = 0; it < sk_iters; ++it) {
-        u0 = 1.0f / (e00 * v0 + e01 * v1 + eps);
-        u1 = 1.0f / (e10 * v0 + e11 * v1 + eps);
-        v0 = 1.0f / (e00 * u0 + e10 * u1 + eps);
-        v1 = 1.0f / (e01 * u0 + e11 * u1 + eps);
+        // rcp.approx (1 ulp): an IEEE division is ~10 dependent instructions, and these 4 x sk_iters reciprocals are a serial
+        // chain evaluated on every lane — they were two thirds of the stage kernels' instructions.  The iteration is a
+        // contraction, so the 1-ulp errors do not accumulate (goldens: same tolerance as before).
+        u0 = rcp_approx(e00 * v0 + e01 * v1 + eps);
+        u1 = rcp_approx(e10 * v0 + e11 * v1 + eps);
+        v0 = rcp_approx(e00 * u0 + e10 * u1 + eps);
+        v1 = rcp_approx(e01 * u0 + e11 * u1 + eps);
     }
     c.P[0][0] = u0 * e00 * v0; c.P[0][1] = u0 * e01 * v1;
     c.P[1][0] = u1 * e10 * v0; c.P[1][1] = u1 * e11 * v1;
