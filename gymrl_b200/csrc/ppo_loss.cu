@@ -38,18 +38,25 @@ __device__ __forceinline__ void ppo_sample(const float* z, float V, int a, float
 #pragma unroll
     for (int j = 1; j < MAX_A; ++j)
         if (j < A) mx = fmaxf(mx, z[j]);
+    // softmax numerators through ex2.approx (relative error ~|z - max| * 6e-8, far inside the 1e-5 parity bar) and the
+    // probabilities as e_j / s instead of a second exponential per action: the loss is evaluated per sample on a serial
+    // chain (on every lane in the fused heads kernel), where the eight libdevice expf calls were ~80 instructions
     float s = 0.f;
 #pragma unroll
     for (int j = 0; j < MAX_A; ++j)
-        if (j < A) s += expf(z[j] - mx);
+        if (j < A) {
+            p[j] = exp2f_approx((z[j] - mx) * 1.4426950408889634f);
+            s += p[j];
+        }
     const float lse = logf(s) + mx;
+    const float inv_s = 1.0f / s;
     float H = 0.f;
     float lp = 0.f;
 #pragma unroll
     for (int j = 0; j < MAX_A; ++j)
         if (j < A) {
             ln[j] = z[j] - lse;
-            p[j] = expf(ln[j]);
+            p[j] *= inv_s;
             H -= p[j] * ln[j];
             lp = j == a ? ln[j] : lp;
         }
@@ -189,7 +196,10 @@ ppo_heads_fused_kernel(const float* __restrict__ h, int ldh, const float* __rest
     const int warp = blockIdx.x * kHeadsWarps + wid, nwarps = gridDim.x * kHeadsWarps;
     for (int i = threadIdx.x; i < P; i += blockDim.x) s_acc[i] = 0.f;
     float4 wa[A][NCH], wc[NCH], gwa[A][NCH], gwc[NCH];
-    float bav[A], gb[A + 1];
+    float bav[A];
+    // every lane evaluates the same loss, so the scalar sums (A + 1 bias gradients, 6 metrics) are spread over lanes 0..A+6:
+    // one accumulator register per lane instead of A + 7 on all of them (the kernel is at its 128-register budget)
+    float lane_acc = 0.f;
 #pragma unroll
     for (int j = 0; j < NCH; ++j) {
 #pragma unroll
@@ -201,12 +211,10 @@ ppo_heads_fused_kernel(const float* __restrict__ h, int ldh, const float* __rest
         gwc[j] = make_float4(0.f, 0.f, 0.f, 0.f);
     }
 #pragma unroll
-    for (int a = 0; a < A; ++a) { bav[a] = ba[a]; gb[a] = 0.f; }
-    gb[A] = 0.f;
+    for (int a = 0; a < A; ++a) bav[a] = ba[a];
     const float bcv = bc[0];
     const float invB = 1.0f / (float)M;
     const float ent_coef = cfg.d_entropy_coef ? *cfg.d_entropy_coef : cfg.entropy_coef;
-    float met[6] = {0.f, 0.f, 0.f, 0.f, 0.f, 0.f};
     for (int row = warp; row < M; row += nwarps) {
         const float* hp = h + (size_t)row * ldh;
         float4 ha[NCH], hc[NCH];
@@ -237,10 +245,18 @@ ppo_heads_fused_kernel(const float* __restrict__ h, int ldh, const float* __rest
             for (int a = 0; a < A; ++a) lv_out[(size_t)row * 8 + a] = z[a];
             lv_out[(size_t)row * 8 + A] = V;
         }
-        met[0] += o.m_pol; met[1] += o.m_val; met[2] += o.m_ent; met[3] += o.m_clip; met[4] += o.m_kl; met[5] += o.m_erc;
+        {
+            float v = o.m_erc;                       // lane A + 6
 #pragma unroll
-        for (int a = 0; a < A; ++a) gb[a] += o.dlogits[a];
-        gb[A] += o.dvalue;
+            for (int a = 0; a < A; ++a) v = lane == a ? o.dlogits[a] : v;
+            v = lane == A ? o.dvalue : v;
+            v = lane == A + 1 ? o.m_pol : v;
+            v = lane == A + 2 ? o.m_val : v;
+            v = lane == A + 3 ? o.m_ent : v;
+            v = lane == A + 4 ? o.m_clip : v;
+            v = lane == A + 5 ? o.m_kl : v;
+            lane_acc += v;
+        }
         float* dp = dh + (size_t)row * lddh;
 #pragma unroll
         for (int j = 0; j < NCH; ++j) {
@@ -273,13 +289,9 @@ ppo_heads_fused_kernel(const float* __restrict__ h, int ldh, const float* __rest
                 float* q = s_acc + A * H + A + 128 * j + 4 * lane;
                 q[0] += gwc[j].x; q[1] += gwc[j].y; q[2] += gwc[j].z; q[3] += gwc[j].w;
             }
-            if (lane == 0) {
-#pragma unroll
-                for (int a = 0; a < A; ++a) s_acc[A * H + a] += gb[a];
-                s_acc[A * H + A + H] += gb[A];
-#pragma unroll
-                for (int k = 0; k < 6; ++k) s_met[wid][k] = met[k];
-            }
+            if (lane < A) s_acc[A * H + lane] += lane_acc;
+            else if (lane == A) s_acc[A * H + A + H] += lane_acc;
+            else if (lane < A + 7) s_met[wid][lane - A - 1] = lane_acc;
         }
         __syncthreads();
     }
