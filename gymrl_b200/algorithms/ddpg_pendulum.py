@@ -16,6 +16,7 @@ import torch
 import torch.nn as nn
 
 from .. import _ffi, ops, ops_offpolicy as off
+from ..graphs import LockstepGraphs
 from ..mlp import Chain
 from ..nn import FlatParams, FusedAdam
 from .sac_pendulum import ReplayBuffer
@@ -43,6 +44,7 @@ class Config:
         # ---- engine extras ----
         self.num_envs = 1
         self.max_locksteps = None
+        self.use_cuda_graph = True   # train(): act -> env step -> store -> update as ONE captured graph per lockstep
 
 
 class Critic(nn.Module):
@@ -55,7 +57,7 @@ class Critic(nn.Module):
     Q = [("fc1.weight", "fc1.bias", RELU), ("fc2.weight", "fc2.bias", RELU), ("fc3.weight", "fc3.bias", NONE)]
 
 
-class DDPGTrainer:
+class DDPGTrainer(LockstepGraphs):
     def __init__(self, config: Config):
         _ffi.require_cuda()
         self.cfg = cfg = config
@@ -88,6 +90,9 @@ class DDPGTrainer:
         self.mu_n, self.action = z(N, A), z(N, A)
         self.done = z(N, dt=u8)
         self.total_updates = self.act_count = 0
+        self.ctr_act, self.ctr_upd = z(1, dt=i32), z(1, dt=i32)   # device mirrors of act_count / total_updates (RNG draws)
+        self.cur = z(N, D)
+        self.graph_launches = 0
         self.episode_rewards = deque(maxlen=100)
         print(f"Device: {dev}")
         print(f"State dim: {D}, Action dim: {A}")
@@ -102,8 +107,10 @@ class DDPGTrainer:
         if deterministic:
             return self.mu_n
         self.act_count += 1
-        return ops.add_gaussian_noise_clip(self.mu_n, self.cfg.noise_std * self.action_bound, self.action_bound, 0.0, noise,
-                                           seed=self.seed, first_id=0, draw=self.act_count, action=self.action)
+        a = ops.add_gaussian_noise_clip(self.mu_n, self.cfg.noise_std * self.action_bound, self.action_bound, 0.0, noise,
+                                        seed=self.seed, first_id=0, draw=1, draw_base=self.ctr_act, action=self.action)
+        ops.counter_add(self.ctr_act, 1)
+        return a
 
     @torch.no_grad()
     def select_action(self, state: np.ndarray, deterministic: bool = False) -> np.ndarray:
@@ -123,7 +130,7 @@ class DDPGTrainer:
             return 0.0, 0.0
         self.total_updates += 1
         if idx is None:
-            idx = mem.sample_indices(B, seed=self.seed, draw=self.total_updates, out=self.idx)
+            idx = mem.sample_indices(B, seed=self.seed, draw=1, draw_base=self.ctr_upd, out=self.idx)
         # target (ref :176-179)
         off.tanh_bound(self.pi_tgt.forward(mem.next_obs, B, row_index=idx), bound, out=self.act_b)
         off.gather_concat(mem.next_obs, idx, self.act_b, None, out=self.sa2, n=B)
@@ -147,20 +154,26 @@ class DDPGTrainer:
         self.pi_upd.backward(mem.obs, B, row_index=idx)
         self.actor_optimizer.step()
         self.soft_update()
+        ops.counter_add(self.ctr_upd, 1)
         return self.aloss, self.closs     # closs[0] = 2 x mse (both "heads" are the same Q)
+
+    # ---------------------------------------------------------------- one lockstep (ref train() loop body)
+    def _lockstep_body(self):
+        env, mem, cur = self.env, self.memory, self.cur
+        a = self.act(cur)
+        obs, r, te, tr, nobs = env.step(a, done=self.done)
+        mem.store(cur, a, r, nobs, self.done)
+        self.update()
+        cur.copy_(obs)
 
     def train(self):
         print("Starting training...")
         cfg, env, mem = self.cfg, self.env, self.memory
-        cur = env.reset().clone()
+        env.reset(out=self.cur)
         max_lock = cfg.max_locksteps or int(cfg.max_episodes * cfg.max_steps / self.N)
         t0, last_total = time.time(), 0
         for step in range(max_lock):
-            a = self.act(cur)
-            obs, r, te, tr, nobs = env.step(a, done=self.done)
-            mem.store(cur, a, r, nobs, self.done)
-            self.update()
-            cur.copy_(obs)
+            self.lockstep()
             if step % cfg.max_steps == cfg.max_steps - 1:
                 avg, _, total = env.episode_stats(100)
                 if total != last_total:

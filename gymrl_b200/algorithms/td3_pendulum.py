@@ -17,6 +17,7 @@ import torch
 import torch.nn as nn
 
 from .. import _ffi, ops, ops_offpolicy as off
+from ..graphs import LockstepGraphs
 from ..mlp import Chain
 from ..nn import FlatParams, FusedAdam
 from .sac_pendulum import Critic, ReplayBuffer  # identical twin-critic module and replay ring
@@ -46,6 +47,7 @@ class Config:
         # ---- engine extras ----
         self.num_envs = 1
         self.max_locksteps = None
+        self.use_cuda_graph = True   # train(): one captured graph per lockstep phase (critic-only / critic + actor)
 
 
 class Actor(nn.Module):
@@ -59,7 +61,7 @@ class Actor(nn.Module):
     SPECS = [("fc1.weight", "fc1.bias", RELU), ("fc2.weight", "fc2.bias", RELU), ("fc3.weight", "fc3.bias", NONE)]
 
 
-class TD3Trainer:
+class TD3Trainer(LockstepGraphs):
     def __init__(self, config: Config):
         _ffi.require_cuda()
         self.cfg = cfg = config
@@ -98,6 +100,10 @@ class TD3Trainer:
         self.done = z(N, dt=u8)
         self.total_updates = 0
         self.act_count = 0
+        # device mirrors of act_count / total_updates: the RNG kernels add them to their `draw`, so captured graphs draw afresh
+        self.ctr_act, self.ctr_upd = z(1, dt=i32), z(1, dt=i32)
+        self.cur = z(N, D)
+        self.graph_launches = 0
         self.episode_rewards = deque(maxlen=100)
         print(f"Device: {dev}")
         print(f"State dim: {D}, Action dim: {A}")
@@ -113,8 +119,10 @@ class TD3Trainer:
         if deterministic:
             return self.mu_n
         self.act_count += 1
-        return ops.add_gaussian_noise_clip(self.mu_n, self.cfg.exploration_noise * self.action_bound, self.action_bound, 0.0, noise,
-                                           seed=self.seed, first_id=0, draw=self.act_count, action=self.action)
+        a = ops.add_gaussian_noise_clip(self.mu_n, self.cfg.exploration_noise * self.action_bound, self.action_bound, 0.0, noise,
+                                        seed=self.seed, first_id=0, draw=1, draw_base=self.ctr_act, action=self.action)
+        ops.counter_add(self.ctr_act, 1)
+        return a
 
     @torch.no_grad()
     def select_action(self, state: np.ndarray, deterministic: bool = False) -> np.ndarray:
@@ -135,11 +143,11 @@ class TD3Trainer:
         self.total_updates += 1
         u = self.total_updates
         if idx is None:
-            idx = mem.sample_indices(B, seed=self.seed, draw=u, out=self.idx)
+            idx = mem.sample_indices(B, seed=self.seed, draw=1, draw_base=self.ctr_upd, out=self.idx)
         bound = self.action_bound
         # ---- target with smoothing noise (ref :193-204) ----
         off.tanh_bound(self.pi_tgt.forward(mem.next_obs, B, row_index=idx), bound, out=self.mu_b)
-        nz = noise if noise is not None else off.fill_normal(self.noise_b, seed=self.seed, entity0=0, draw=u)
+        nz = noise if noise is not None else off.fill_normal(self.noise_b, seed=self.seed, entity0=0, draw=1, draw_base=self.ctr_upd)
         ops.add_gaussian_noise_clip(self.mu_b, cfg.policy_noise, bound, cfg.noise_clip, nz, action=self.act_b)
         off.gather_concat(mem.next_obs, idx, self.act_b, None, out=self.sa2, n=B)
         q1t, q2t = self.q1t.forward(self.sa2, B), self.q2t.forward(self.sa2, B)
@@ -165,20 +173,29 @@ class TD3Trainer:
             self.pi_upd.backward(mem.obs, B, row_index=idx)
             self.actor_optimizer.step()
             self.soft_update()
+        ops.counter_add(self.ctr_upd, 1)
         return self.aloss, self.closs
+
+    # ---------------------------------------------------------------- one lockstep (ref train() loop body :239-254)
+    def _lockstep_phases(self) -> int:
+        return int(self.cfg.policy_freq)
+
+    def _lockstep_body(self):
+        env, mem, cur = self.env, self.memory, self.cur
+        a = self.act(cur)
+        obs, r, te, tr, nobs = env.step(a, done=self.done)
+        mem.store(cur, a, r, nobs, self.done)
+        self.update()
+        cur.copy_(obs)
 
     def train(self):
         print("Starting training...")
         cfg, env, mem = self.cfg, self.env, self.memory
-        cur = env.reset().clone()
+        env.reset(out=self.cur)
         max_lock = cfg.max_locksteps or int(cfg.max_episodes * cfg.max_steps / self.N)
         t0, last_total = time.time(), 0
         for step in range(max_lock):
-            a = self.act(cur)
-            obs, r, te, tr, nobs = env.step(a, done=self.done)
-            mem.store(cur, a, r, nobs, self.done)
-            self.update()
-            cur.copy_(obs)
+            self.lockstep()
             if step % cfg.max_steps == cfg.max_steps - 1:
                 avg, _, total = env.episode_stats(100)
                 if total != last_total:

@@ -7,19 +7,51 @@ import torch
 from . import _ffi
 
 
-def capture(fn):
-    """Run `fn` once eagerly on a side stream (first-launch module loads; it is a REAL execution of fn), then record it.
-    Returns the graph; `graph.n_kernels` = launches of this library recorded in it."""
+def capture(fn, warmup: bool = True):
+    """Run `fn` once eagerly on a side stream (first-launch module loads; it is a REAL execution of fn) unless the caller
+    already did (`warmup=False`), then record it.  Returns the graph; `graph.n_kernels` = launches of this library in it."""
     torch.cuda.synchronize()
-    s = torch.cuda.Stream()
-    s.wait_stream(torch.cuda.current_stream())
-    with torch.cuda.stream(s):
-        fn()
-    torch.cuda.current_stream().wait_stream(s)
-    torch.cuda.synchronize()
+    if warmup:
+        s = torch.cuda.Stream()
+        s.wait_stream(torch.cuda.current_stream())
+        with torch.cuda.stream(s):
+            fn()
+        torch.cuda.current_stream().wait_stream(s)
+        torch.cuda.synchronize()
     g = torch.cuda.CUDAGraph()
     c0 = _ffi.launch_count()
     with torch.cuda.graph(g):
         fn()
     g.n_kernels = _ffi.launch_count() - c0
     return g
+
+
+class LockstepGraphs:
+    """Mixin for the continuous-control off-policy trainers (TD3, DDPG): one captured CUDA graph per *phase* of the
+    lockstep (TD3 updates the actor every `policy_freq`-th update, so its lockstep has `policy_freq` phases).
+
+    The trainer provides: `_lockstep_body()` (capture-safe once the replay holds a batch: every per-step-varying scalar in
+    device memory), `memory` (ReplayRing with `_size_host`), `B`, `N`, `total_updates`, `act_count`, `cfg.use_cuda_graph`
+    and optionally `_lockstep_phases()`.
+    """
+
+    def _lockstep_phases(self) -> int:
+        return 1
+
+    def lockstep(self):
+        mem = self.memory
+        if not getattr(self.cfg, "use_cuda_graph", True) or len(mem) < self.B:
+            return self._lockstep_body()
+        graphs = self.__dict__.setdefault("_g_lockstep", {})
+        phase = (self.total_updates + 1) % self._lockstep_phases()      # phase of the update this lockstep will run
+        mirrors = (self.act_count, self.total_updates, mem._size_host)
+        if phase not in graphs:
+            self._lockstep_body()                                       # this lockstep, eagerly (also the warm-up) ...
+            self.act_count, self.total_updates, mem._size_host = mirrors   # ... then record the same phase without running it
+            graphs[phase] = capture(self._lockstep_body, warmup=False)
+        else:
+            graphs[phase].replay()
+            self.graph_launches = getattr(self, "graph_launches", 0) + graphs[phase].n_kernels
+        # host mirrors of the counters the device body advanced
+        self.act_count, self.total_updates = mirrors[0] + 1, mirrors[1] + 1
+        mem._size_host = min(mem.capacity, mirrors[2] + self.N)

@@ -283,12 +283,65 @@ def gen_ddpg():
     np.savez(OUT / "ddpg_update.npz", **out)
 
 
+
+# ------------------------------------------------------------------------------------------------ NoisyNet DQN
+def gen_noisy_dqn():
+    """NoisyDQNTrainer.update (algorithms/noisy_dqn_cartpole.py:206-253) x2 on a fixed batch: four NoisyLinear layers with fresh
+    factorised noise per forward (online net on s, then on s'), eval-mode target net, double-Q, MSE, Adam, hard sync on the 2nd.
+
+    NOTE — the unmodified script cannot run its own update(): the second forward (on s', under no_grad, :232) re-draws the noise
+    with in-place `copy_` into the epsilon buffers (:86-87) that the first forward's autograd graph saved, and loss.backward()
+    (:239) raises "one of the variables needed for gradient computation has been modified by an inplace operation".  The golden
+    is therefore generated with NoisyLinear.reset_noise rebinding the two buffers to new tensors (same draws, same order, not in
+    place) — the only reading under which the script's update() executes: the gradient uses the first forward's noise."""
+    rl.install_gymnasium_stub(make=lambda name, **k: rl.FakeEnv(4, n_actions=2, max_steps=500))
+    m = rl.load("algorithms/noisy_dqn_cartpole.py")
+
+    def reset_noise(self):
+        eps_i = self._scale_noise(self.in_features)
+        eps_j = self._scale_noise(self.out_features)
+        self.weight_epsilon = torch.outer(eps_j, eps_i)
+        self.bias_epsilon = eps_j.clone()
+    m.NoisyLinear.reset_noise = reset_noise
+    torch.manual_seed(4)
+    cfg = m.Config(); cfg.device = "cpu"; cfg.batch_size = 256; cfg.hidden_dim = 64; cfg.target_update_freq = 2
+    import io, contextlib
+    with contextlib.redirect_stdout(io.StringIO()):
+        t = m.NoisyDQNTrainer(cfg)
+    with torch.no_grad():
+        for p in t.target_net.parameters():
+            p.add_(0.05 * torch.randn_like(p))
+    rng = np.random.default_rng(6)
+    B, D, H, A = cfg.batch_size, 4, cfg.hidden_dim, 2
+    batch = (rng.standard_normal((B, D)).astype(np.float32), rng.integers(0, A, B), (rng.standard_normal(B) * 2).astype(np.float32),
+             rng.standard_normal((B, D)).astype(np.float32), rng.random(B) < 0.1)
+    out = dict(states=batch[0], action=batch[1].astype(np.int32), reward=batch[2], next_states=batch[3], done=batch[4].astype(np.uint8),
+               gamma=cfg.gamma, lr=cfg.lr)
+    out.update(_sd(t.policy_net, "p0_")); out.update(_sd(t.target_net, "t0_"))
+    t.memory.sample = lambda bs: batch
+    t.memory.buffer = deque([0] * B)
+    dims = {"fc1": (D, H), "fc2": (H, H), "value_stream": (H, 1), "advantage_stream": (H, A)}
+    torch.manual_seed(123)
+    for u in (1, 2):
+        for tag in ("cur", "next"):       # update(): policy_net(states) first, then policy_net(next_states) (ref :229-232)
+            for name in ("fc1", "fc2", "value_stream", "advantage_stream"):      # forward order (ref :126-133)
+                out[f"xi{u}_{tag}_{name}_in"] = torch.randn(dims[name][0]).numpy()
+                out[f"xi{u}_{tag}_{name}_out"] = torch.randn(dims[name][1]).numpy()
+    torch.manual_seed(123)
+    m1 = t.update()
+    out.update(_sd(t.policy_net, "p1_"))
+    m2 = t.update()
+    out.update(_sd(t.policy_net, "p2_")); out.update(_sd(t.target_net, "t2_"))
+    out.update(losses=np.array([m1["loss"], m2["loss"]]))
+    np.savez(OUT / "noisy_dqn_update.npz", **out)
+
 def main():
     torch.set_num_threads(1)
     gen_sumtree()
     gen_per_nstep()
     gen_dqn()
     gen_rainbow()
+    gen_noisy_dqn()
     gen_sac()
     gen_td3()
     gen_ddpg()

@@ -174,6 +174,30 @@ def test_rainbow_update_matches_reference(golden):
     _cmp(t.target_net, g, "t1_", rtol=2e-5, atol=2e-7)
 
 
+
+# ------------------------------------------------------------------------------------------------ NoisyNet DQN
+def test_noisy_dqn_update_matches_reference(golden):
+    """Two updates of algorithms/noisy_dqn_cartpole.py (fresh factorised noise on all four layers per forward, double-Q with an
+    eval-mode target, MSE, Adam, hard target sync on the second) with the reference's own noise draws fed in."""
+    from gymrl_b200.algorithms import noisy_dqn_cartpole as Nd
+    g = golden("noisy_dqn_update.npz")
+    cfg = Nd.Config(); cfg.batch_size, cfg.hidden_dim, cfg.seed, cfg.memory_capacity, cfg.target_update_freq = 256, 64, 0, 1024, 2
+    t = Nd.NoisyDQNTrainer(cfg)
+    _load(t.policy_net, g, "p0_"); t.fp.refresh_views()
+    _load(t.target_net, g, "t0_"); t.fp_t.refresh_views()
+    _fill_ring(t.memory, g["states"], g["action"], g["reward"], g["next_states"], g["done"])
+    idx = torch.arange(256, device="cuda", dtype=i32)
+    xi = lambda u, tag: {n: (cu(g[f"xi{u}_{tag}_{n}_in"]), cu(g[f"xi{u}_{tag}_{n}_out"])) for n in Nd.NoisyDuelingQNetwork.LAYERS}
+    losses = []
+    for u in (1, 2):
+        losses.append(float(t.update(idx, xi_cur=xi(u, "cur"), xi_next=xi(u, "next"))["loss"]))
+        if u == 1:
+            _cmp(t.policy_net, g, "p1_", rtol=2e-4, atol=2e-6)
+    np.testing.assert_allclose(losses, g["losses"], rtol=3e-5)
+    _cmp(t.policy_net, g, "p2_", rtol=3e-4, atol=3e-6)
+    _cmp(t.target_net, g, "t2_", rtol=3e-4, atol=3e-6)           # hard sync happened on the second update
+    torch.testing.assert_close(t.fp_t.flat, t.fp.flat, rtol=0, atol=0)
+
 # ------------------------------------------------------------------------------------------------ SAC
 def test_sac_update_matches_reference(golden):
     from gymrl_b200.algorithms import sac_pendulum as S
@@ -240,10 +264,11 @@ def test_ddpg_update_matches_reference(golden):
 
 
 # ------------------------------------------------------------------------------------------------ smoke at BASELINE sizes
-@pytest.mark.parametrize("algo", ["dqn", "rainbow", "sac", "td3", "ddpg"])
+@pytest.mark.parametrize("algo", ["dqn", "rainbow", "sac", "td3", "ddpg", "noisy_dqn"])
 def test_offpolicy_trainers_run_vectorised(algo):
     import importlib
-    name = {"dqn": "dqn_cartpole", "rainbow": "rainbow_dqn_cartpole", "sac": "sac_pendulum", "td3": "td3_pendulum", "ddpg": "ddpg_pendulum"}[algo]
+    name = {"dqn": "dqn_cartpole", "rainbow": "rainbow_dqn_cartpole", "sac": "sac_pendulum", "td3": "td3_pendulum", "ddpg": "ddpg_pendulum",
+            "noisy_dqn": "noisy_dqn_cartpole"}[algo]
     M = importlib.import_module(f"gymrl_b200.algorithms.{name}")
     cfg = M.Config()
     cfg.num_envs, cfg.seed, cfg.max_locksteps = 1024, 3, 30
@@ -257,12 +282,12 @@ def test_offpolicy_trainers_run_vectorised(algo):
     assert len(r) == 4 and all(np.isfinite(r))
 
 
-@pytest.mark.parametrize("algo", ["rainbow", "sac"])
+@pytest.mark.parametrize("algo", ["rainbow", "sac", "td3", "ddpg"])
 def test_graph_lockstep_equals_eager_lockstep(algo):
     """train()'s captured lockstep (act -> env step -> store -> update as one CUDA graph, RNG draw counters / PER beta /
     learning rate in device scalars) leaves the same parameters, replay contents and env stream as the eager lockstep."""
     import importlib
-    name = {"rainbow": "rainbow_dqn_cartpole", "sac": "sac_pendulum"}[algo]
+    name = {"rainbow": "rainbow_dqn_cartpole", "sac": "sac_pendulum", "td3": "td3_pendulum", "ddpg": "ddpg_pendulum"}[algo]
     M = importlib.import_module(f"gymrl_b200.algorithms.{name}")
     cls = [getattr(M, k) for k in dir(M) if k.endswith("Trainer")][0]
     res = []
@@ -275,10 +300,12 @@ def test_graph_lockstep_equals_eager_lockstep(algo):
         for _ in range(40):
             t.lockstep()
         torch.cuda.synchronize()
-        assert (t._g_lockstep is not None) == use_graph
+        assert bool(getattr(t, "_g_lockstep", None)) == use_graph
         if use_graph:
             assert t.graph_launches > 0
-        fps = [getattr(t, k) for k in ("fp", "fp_t", "fp_a", "fp_c", "fp_ct") if hasattr(t, k)]
+        if algo == "td3" and use_graph:
+            assert sorted(t._g_lockstep) == [0, 1]          # one graph per phase: critic + actor / critic only
+        fps = [getattr(t, k) for k in ("fp", "fp_t", "fp_a", "fp_at", "fp_c", "fp_ct") if hasattr(t, k)]
         ring = t.memory.ring if hasattr(t.memory, "ring") else t.memory
         res.append(([f.flat.clone() for f in fps], t.cur.clone(), ring.obs.clone(), ring.reward.clone(), ring.state.clone(), len(t.memory)))
     (pa, ca, oa, ra, sa, la), (pb, cb, ob, rb, sb, lb) = res
