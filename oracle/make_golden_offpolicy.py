@@ -335,6 +335,45 @@ def gen_noisy_dqn():
     out.update(losses=np.array([m1["loss"], m2["loss"]]))
     np.savez(OUT / "noisy_dqn_update.npz", **out)
 
+
+# ------------------------------------------------------------------------------------------------ DDQN + PER (dialect B)
+def gen_ddqn_per(duel: bool):
+    """DDQNPER(Duel)Trainer.update x2 (algorithms/ddqn_per_cartpole.py:206-247 / ddqn_per_duel_cartpole.py): stratified SumTree
+    sample with beta += 0.001, double-Q target, IS-weighted loss, priorities min(|td| + 1e-4, 1)^0.6, grad clamp(+-1), Adam."""
+    import random
+    rl.install_gymnasium_stub(make=lambda name, **k: rl.FakeEnv(4, n_actions=2, max_steps=500))
+    m = rl.load("algorithms/ddqn_per_duel_cartpole.py" if duel else "algorithms/ddqn_per_cartpole.py")
+    torch.manual_seed(7 + duel)
+    cfg = m.Config(); cfg.device = "cpu"; cfg.memory_capacity = 1024; cfg.batch_size = 128; cfg.hidden_dim = 64
+    import io, contextlib
+    with contextlib.redirect_stdout(io.StringIO()):
+        t = (m.DDQNPERDuelTrainer if duel else m.DDQNPERTrainer)(cfg)
+    with torch.no_grad():
+        for p in t.target_net.parameters():
+            p.add_(0.05 * torch.randn_like(p))
+    rng = np.random.default_rng(8 + duel)
+    T = 700
+    S = rng.standard_normal((T, 4)).astype(np.float32); S2 = rng.standard_normal((T, 4)).astype(np.float32)
+    A = rng.integers(0, 2, T); R = (rng.standard_normal(T)).astype(np.float32); done = rng.random(T) < 0.08
+    for k in range(T):
+        t.memory.push((S[k], int(A[k]), float(R[k]), S2[k], bool(done[k])))
+    pr = rng.random(T) + 0.05                      # non-uniform priorities
+    for i, p in enumerate(pr):
+        t.memory.tree.update(i + cfg.memory_capacity - 1, float(p))
+    out = dict(S=S, S2=S2, A=A.astype(np.int32), R=R, done=done.astype(np.uint8), prio=pr, tree0=t.memory.tree.tree.copy(),
+               gamma=cfg.gamma, lr=cfg.lr, capacity=cfg.memory_capacity, batch_size=cfg.batch_size, beta0=cfg.beta)
+    out.update(_sd(t.policy_net, "p0_")); out.update(_sd(t.target_net, "t0_"))
+    random.seed(21)
+    out["u1"] = np.array([random.random() for _ in range(cfg.batch_size)])      # random.uniform(a, b) = a + (b - a) * random()
+    out["u2"] = np.array([random.random() for _ in range(cfg.batch_size)])
+    random.seed(21)
+    l1 = t.update()
+    out.update(_sd(t.policy_net, "p1_")); out["tree1"] = t.memory.tree.tree.copy()
+    l2 = t.update()
+    out.update(_sd(t.policy_net, "p2_")); out["tree2"] = t.memory.tree.tree.copy()
+    out.update(losses=np.array([l1, l2]), beta2=cfg.beta)
+    np.savez(OUT / ("ddqn_per_duel_update.npz" if duel else "ddqn_per_update.npz"), **out)
+
 def main():
     torch.set_num_threads(1)
     gen_sumtree()
@@ -342,6 +381,8 @@ def main():
     gen_dqn()
     gen_rainbow()
     gen_noisy_dqn()
+    gen_ddqn_per(False)
+    gen_ddqn_per(True)
     gen_sac()
     gen_td3()
     gen_ddpg()

@@ -198,6 +198,37 @@ def test_noisy_dqn_update_matches_reference(golden):
     _cmp(t.target_net, g, "t2_", rtol=3e-4, atol=3e-6)           # hard sync happened on the second update
     torch.testing.assert_close(t.fp_t.flat, t.fp.flat, rtol=0, atol=0)
 
+
+# ------------------------------------------------------------------------------------------------ DDQN + PER (dialect B)
+@pytest.mark.parametrize("duel", [False, True])
+def test_ddqn_per_update_matches_reference(golden, duel):
+    """Two updates of algorithms/ddqn_per(_duel)_cartpole.py with the reference's random.uniform draws fed in: sampled leaves /
+    IS weights (beta += 0.001 per sample), double-Q target, IS-weighted loss, priorities min(|td| + 1e-4, 1)^0.6 written to the
+    tree, grad clamp, Adam."""
+    import importlib
+    M = importlib.import_module("gymrl_b200.algorithms." + ("ddqn_per_duel_cartpole" if duel else "ddqn_per_cartpole"))
+    g = golden("ddqn_per_duel_update.npz" if duel else "ddqn_per_update.npz")
+    cfg = M.Config()
+    cfg.memory_capacity, cfg.batch_size, cfg.hidden_dim, cfg.seed = int(g["capacity"]), int(g["batch_size"]), 64, 0
+    t = (M.DDQNPERDuelTrainer if duel else M.DDQNPERTrainer)(cfg)
+    _load(t.policy_net, g, "p0_"); t.fp.refresh_views()
+    _load(t.target_net, g, "t0_"); t.fp_t.refresh_views()
+    n = len(g["A"])
+    t.memory.store(cu(g["S"]), cu(g["A"]).reshape(n, 1), cu(g["R"]), cu(g["S2"]), cu(g["done"]))
+    assert len(t.memory) == n
+    t.memory.tree.tree.copy_(cu(g["tree0"], f64))
+    cap = cfg.memory_capacity
+    losses = []
+    for u, tree_key, p_key in (("u1", "tree1", "p1_"), ("u2", "tree2", "p2_")):
+        losses.append(float(t.update(uniforms=cu(g[u], f64))))
+        np.testing.assert_allclose(t.memory.tree.tree.cpu().numpy()[cap - 1:], g[tree_key][cap - 1:], rtol=3e-4, atol=1e-7, err_msg=tree_key)
+        _cmp(t.policy_net, g, p_key, rtol=3e-4, atol=3e-6)
+    np.testing.assert_allclose(losses, g["losses"], rtol=5e-5)
+    assert abs(cfg.beta - float(g["beta2"])) < 1e-15
+    # facade: leaves are addressed by tree index in this dialect (ref :75-107)
+    leaf, prio = t.memory.tree.get_leaf(0.5 * t.memory.tree.total_priority())
+    assert cap - 1 <= leaf < 2 * cap - 1 and prio > 0
+
 # ------------------------------------------------------------------------------------------------ SAC
 def test_sac_update_matches_reference(golden):
     from gymrl_b200.algorithms import sac_pendulum as S
@@ -264,11 +295,11 @@ def test_ddpg_update_matches_reference(golden):
 
 
 # ------------------------------------------------------------------------------------------------ smoke at BASELINE sizes
-@pytest.mark.parametrize("algo", ["dqn", "rainbow", "sac", "td3", "ddpg", "noisy_dqn"])
+@pytest.mark.parametrize("algo", ["dqn", "rainbow", "sac", "td3", "ddpg", "noisy_dqn", "ddqn_per", "ddqn_per_duel"])
 def test_offpolicy_trainers_run_vectorised(algo):
     import importlib
     name = {"dqn": "dqn_cartpole", "rainbow": "rainbow_dqn_cartpole", "sac": "sac_pendulum", "td3": "td3_pendulum", "ddpg": "ddpg_pendulum",
-            "noisy_dqn": "noisy_dqn_cartpole"}[algo]
+            "noisy_dqn": "noisy_dqn_cartpole", "ddqn_per": "ddqn_per_cartpole", "ddqn_per_duel": "ddqn_per_duel_cartpole"}[algo]
     M = importlib.import_module(f"gymrl_b200.algorithms.{name}")
     cfg = M.Config()
     cfg.num_envs, cfg.seed, cfg.max_locksteps = 1024, 3, 30
