@@ -70,6 +70,10 @@ SIGNATURES = {
     "gymrl_reduce_flush": (c_int, [_P, c_int, C.POINTER(c_int), C.POINTER(c_ll), _P]),
     "gymrl_clip_adam_step": (c_int, [_P, _P, _P, _P, c_ll, _P, c_float, c_float, c_float, _P, _P, c_int, c_float, c_float, _P, _P]),
     "gymrl_polyak": (c_int, [_P, _P, c_ll, c_float, _P]),
+    "gymrl_sac_discrete_target": (c_int, [_P, c_int, _P, c_int, _P, c_int, _P, _P, _P, _P, c_float, _P, c_int, c_int, _P]),
+    "gymrl_sac_discrete_critic_loss": (c_int, [_P, c_int, _P, c_int, _P, _P, _P, _P, c_int, _P, c_int, _P, c_int, c_int, _P]),
+    "gymrl_sac_discrete_actor_grad": (c_int, [_P, c_int, _P, c_int, _P, c_int, _P, _P, c_int, _P, c_int, c_int, _P]),
+    "gymrl_sac_discrete_alpha_step": (c_int, [_P, _P, _P, c_int, c_float, c_float, _P, _P]),
     "gymrl_random_permutation": (c_int, [_P, c_int, c_u64, c_u32, _P, _P]),
     "gymrl_ppo_heads_workspace_bytes": (c_size_t, [c_int, c_int]),
     "gymrl_ppo_heads_fused": (c_int, [_P, c_int, _P, _P, _P, _P, _P, _P, _P, _P, _P, _P, _P, _P, c_int, c_int, _P, _P, _P, _P, _P, _P, _P,

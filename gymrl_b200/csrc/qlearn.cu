@@ -314,6 +314,154 @@ extern "C" int gymrl_sac_alpha_step(double* d_log_alpha, double* d_adam_state, c
     return GYMRL_OK;
 }
 
+// ------------------------------------------------------------------------------------------------ discrete SAC (sac_cartpole)
+// softmax policy over A actions: p = softmax(z), lp = log(p + 1e-8), H = -sum p lp   (sac_cartpole.py:96-99, :166-168, :191-193)
+__device__ __forceinline__ void softmax_entropy(const float* z, int A, float* p, float* lp, float& H) {
+    float mx = z[0];
+    for (int j = 1; j < A; ++j) mx = fmaxf(mx, z[j]);
+    float s = 0.f;
+    for (int j = 0; j < A; ++j) { p[j] = expf(z[j] - mx); s += p[j]; }
+    H = 0.f;
+    for (int j = 0; j < A; ++j) {
+        p[j] = p[j] / s;
+        lp[j] = logf(p[j] + 1e-8f);
+        H -= p[j] * lp[j];
+    }
+}
+
+// y = r + gamma (1 - d) (sum_a p_a min(Q1t, Q2t)_a + alpha H(p)),  p = softmax(logits of the actor on s')   (ref :164-176)
+__global__ void sacd_target_kernel(const float* __restrict__ logits, int ldz, const float* __restrict__ q1t, int ld1,
+                                   const float* __restrict__ q2t, int ld2, const float* __restrict__ reward,
+                                   const float* __restrict__ done, const int32_t* __restrict__ row_index,
+                                   const float* __restrict__ log_alpha, float gamma, float* __restrict__ y, int B, int A) {
+    const int i = blockIdx.x * blockDim.x + threadIdx.x;
+    if (i >= B) return;
+    const int r = row_index ? row_index[i] : i;
+    float p[MAX_A], lp[MAX_A], H;
+    softmax_entropy(logits + (size_t)i * ldz, A, p, lp, H);
+    float mq = 0.f;
+    for (int j = 0; j < A; ++j) mq += p[j] * fminf(q1t[(size_t)i * ld1 + j], q2t[(size_t)i * ld2 + j]);
+    const float alpha = expf(*log_alpha);
+    const float next_value = mq + alpha * H;
+    y[i] = reward[r] + (gamma * (1.0f - done[r])) * next_value;
+}
+
+// critic losses mse(Q1(s)[a], y), mse(Q2(s)[a], y) and their gradients (zero for the actions not taken)   (ref :178-189)
+__global__ void sacd_critic_loss_kernel(const float* __restrict__ q1, int ld1, const float* __restrict__ q2, int ld2,
+                                        const int32_t* __restrict__ action, const int32_t* __restrict__ row_index,
+                                        const float* __restrict__ y, float* __restrict__ dq1, int ldd1, float* __restrict__ dq2,
+                                        int ldd2, float* __restrict__ loss_acc, int B, int A) {
+    __shared__ float scratch[32];
+    const int i = blockIdx.x * blockDim.x + threadIdx.x;
+    float l1 = 0.f, l2 = 0.f;
+    if (i < B) {
+        const int r = row_index ? row_index[i] : i;
+        const int a = action[r];
+        const float e1 = q1[(size_t)i * ld1 + a] - y[i], e2 = q2[(size_t)i * ld2 + a] - y[i];
+        l1 = e1 * e1 / (float)B;
+        l2 = e2 * e2 / (float)B;
+        for (int j = 0; j < A; ++j) {
+            dq1[(size_t)i * ldd1 + j] = j == a ? 2.0f * e1 / (float)B : 0.0f;
+            dq2[(size_t)i * ldd2 + j] = j == a ? 2.0f * e2 / (float)B : 0.0f;
+        }
+    }
+    l1 = block_sum(l1, scratch);
+    l2 = block_sum(l2, scratch);
+    if (threadIdx.x == 0 && loss_acc) { atomicAdd(&loss_acc[0], l1); atomicAdd(&loss_acc[1], l2); }
+}
+
+// actor loss mean(-alpha H - sum_a p_a min(Q1, Q2)_a) and its gradient wrt the logits (through softmax and log(p + 1e-8));
+// acc[0] += actor loss, acc[1] += sum_i H_i (consumed by the alpha step)   (ref :191-200)
+__global__ void sacd_actor_grad_kernel(const float* __restrict__ logits, int ldz, const float* __restrict__ q1, int ld1,
+                                       const float* __restrict__ q2, int ld2, const float* __restrict__ log_alpha,
+                                       float* __restrict__ dlogits, int lddz, float* __restrict__ acc, int B, int A) {
+    __shared__ float scratch[32];
+    const int i = blockIdx.x * blockDim.x + threadIdx.x;
+    float li = 0.f, hi = 0.f;
+    if (i < B) {
+        float p[MAX_A], lp[MAX_A], H;
+        softmax_entropy(logits + (size_t)i * ldz, A, p, lp, H);
+        const float alpha = expf(*log_alpha);
+        float g[MAX_A], mq = 0.f, pg = 0.f;
+        for (int j = 0; j < A; ++j) {
+            const float m = fminf(q1[(size_t)i * ld1 + j], q2[(size_t)i * ld2 + j]);
+            mq += p[j] * m;
+            g[j] = alpha * (lp[j] + p[j] / (p[j] + 1e-8f)) - m;     // dL_i / dp_j
+            pg += p[j] * g[j];
+        }
+        for (int j = 0; j < A; ++j) dlogits[(size_t)i * lddz + j] = p[j] * (g[j] - pg) / (float)B;
+        li = (-alpha * H - mq) / (float)B;
+        hi = H;
+    }
+    li = block_sum(li, scratch);
+    hi = block_sum(hi, scratch);
+    if (threadIdx.x == 0 && acc) { atomicAdd(&acc[0], li); atomicAdd(&acc[1], hi); }
+}
+
+// alpha_loss = mean(exp(log_alpha) (H - target).detach()); one float32 Adam step on log_alpha (state = {exp_avg, exp_avg_sq, step})
+__global__ void sacd_alpha_step_kernel(float* log_alpha, float* state, const float* acc, int B, float target_entropy, float lr,
+                                       float* loss_out) {
+    const float alpha = expf(*log_alpha);
+    const float mean_dh = acc[1] / (float)B - target_entropy;
+    const float g = alpha * mean_dh;
+    if (loss_out) *loss_out = alpha * mean_dh;
+    const float b1 = 0.9f, b2 = 0.999f, eps = 1e-8f;
+    float m = state[0], v = state[1];
+    const float t = state[2] + 1.0f;
+    m = m + (1.0f - b1) * (g - m);
+    v = v * b2 + (1.0f - b2) * g * g;
+    const double bc1 = 1.0 - pow((double)b1, (double)t), bc2 = 1.0 - pow((double)b2, (double)t);
+    const float step_size = (float)(-((double)lr / bc1));
+    const float denom = sqrtf(v) / (float)sqrt(bc2) + eps;
+    *log_alpha = *log_alpha + (step_size * m) / denom;
+    state[0] = m; state[1] = v; state[2] = t;
+}
+
+extern "C" int gymrl_sac_discrete_target(const float* d_logits_next, int ld_logits, const float* d_q1t, int ld_q1t, const float* d_q2t,
+                                         int ld_q2t, const float* d_reward, const float* d_done, const int32_t* d_row_index,
+                                         const float* d_log_alpha, float gamma, float* d_y, int batch, int n_actions, void* stream) {
+    GYMRL_REQUIRE(d_logits_next && d_q1t && d_q2t && d_reward && d_done && d_log_alpha && d_y && batch > 0, "bad arguments");
+    GYMRL_REQUIRE(n_actions >= 1 && n_actions <= MAX_A, "n_actions out of range");
+    sacd_target_kernel<<<ceil_div(batch, 256), 256, 0, as_stream(stream)>>>(d_logits_next, ld_logits, d_q1t, ld_q1t, d_q2t, ld_q2t, d_reward,
+                                                                            d_done, d_row_index, d_log_alpha, gamma, d_y, batch, n_actions);
+    gymrl_count_launch();
+    GYMRL_LAUNCH_CHECK("sac_discrete_target");
+    return GYMRL_OK;
+}
+
+extern "C" int gymrl_sac_discrete_critic_loss(const float* d_q1, int ld_q1, const float* d_q2, int ld_q2, const int32_t* d_action,
+                                              const int32_t* d_row_index, const float* d_y, float* d_dq1, int ld_dq1, float* d_dq2,
+                                              int ld_dq2, float* d_loss_acc, int batch, int n_actions, void* stream) {
+    GYMRL_REQUIRE(d_q1 && d_q2 && d_action && d_y && d_dq1 && d_dq2 && batch > 0, "bad arguments");
+    GYMRL_REQUIRE(n_actions >= 1 && n_actions <= MAX_A, "n_actions out of range");
+    sacd_critic_loss_kernel<<<ceil_div(batch, 256), 256, 0, as_stream(stream)>>>(d_q1, ld_q1, d_q2, ld_q2, d_action, d_row_index, d_y, d_dq1,
+                                                                                 ld_dq1, d_dq2, ld_dq2, d_loss_acc, batch, n_actions);
+    gymrl_count_launch();
+    GYMRL_LAUNCH_CHECK("sac_discrete_critic_loss");
+    return GYMRL_OK;
+}
+
+extern "C" int gymrl_sac_discrete_actor_grad(const float* d_logits, int ld_logits, const float* d_q1, int ld_q1, const float* d_q2,
+                                             int ld_q2, const float* d_log_alpha, float* d_dlogits, int ld_dlogits, float* d_acc,
+                                             int batch, int n_actions, void* stream) {
+    GYMRL_REQUIRE(d_logits && d_q1 && d_q2 && d_log_alpha && d_dlogits && batch > 0, "bad arguments");
+    GYMRL_REQUIRE(n_actions >= 1 && n_actions <= MAX_A, "n_actions out of range");
+    sacd_actor_grad_kernel<<<ceil_div(batch, 256), 256, 0, as_stream(stream)>>>(d_logits, ld_logits, d_q1, ld_q1, d_q2, ld_q2, d_log_alpha,
+                                                                                d_dlogits, ld_dlogits, d_acc, batch, n_actions);
+    gymrl_count_launch();
+    GYMRL_LAUNCH_CHECK("sac_discrete_actor_grad");
+    return GYMRL_OK;
+}
+
+extern "C" int gymrl_sac_discrete_alpha_step(float* d_log_alpha, float* d_adam_state, const float* d_acc, int batch, float target_entropy,
+                                             float lr, float* d_loss_out, void* stream) {
+    GYMRL_REQUIRE(d_log_alpha && d_adam_state && d_acc && batch > 0, "bad arguments");
+    sacd_alpha_step_kernel<<<1, 1, 0, as_stream(stream)>>>(d_log_alpha, d_adam_state, d_acc, batch, target_entropy, lr, d_loss_out);
+    gymrl_count_launch();
+    GYMRL_LAUNCH_CHECK("sac_discrete_alpha_step");
+    return GYMRL_OK;
+}
+
 // ------------------------------------------------------------------------------------------------ NoisyLinear
 // eps = f(xi), f(x) = sign(x) sqrt|x|, xi ~ N(0,1)  (scale_noise, rainbow :76-79); d_xi optional pre-drawn normals
 __global__ void noisy_sample_kernel(float* __restrict__ eps, const float* __restrict__ xi_in, int n, uint64_t seed, uint64_t entity,

@@ -168,6 +168,34 @@ def sac_alpha_step(log_alpha, adam_state, acc, batch, target_entropy, lr, loss_o
                                       ptr(loss_out, f32), stream_ptr()))
 
 
+# ------------------------------------------------------------------------------------------------ discrete SAC
+def sac_discrete_target(logits_next, q1t, q2t, reward, done, log_alpha, gamma, *, row_index=None, out=None):
+    B, A = logits_next.shape
+    out = torch.empty(B, device=q1t.device, dtype=f32) if out is None else out
+    check(load().gymrl_sac_discrete_target(ptr(logits_next, f32), _ld(logits_next), ptr(q1t, f32), _ld(q1t), ptr(q2t, f32), _ld(q2t),
+                                           ptr(reward, f32), ptr(done, f32), ptr(row_index, i32), ptr(log_alpha, f32), float(gamma),
+                                           ptr(out, f32), B, A, stream_ptr()))
+    return out
+
+
+def sac_discrete_critic_loss(q1, q2, action, y, dq1, dq2, *, row_index=None, loss_acc=None):
+    B, A = q1.shape
+    check(load().gymrl_sac_discrete_critic_loss(ptr(q1, f32), _ld(q1), ptr(q2, f32), _ld(q2), ptr(action, i32), ptr(row_index, i32),
+                                                ptr(y, f32), ptr(dq1, f32), _ld(dq1), ptr(dq2, f32), _ld(dq2), ptr(loss_acc, f32), B, A,
+                                                stream_ptr()))
+
+
+def sac_discrete_actor_grad(logits, q1, q2, log_alpha, dlogits, acc=None):
+    B, A = logits.shape
+    check(load().gymrl_sac_discrete_actor_grad(ptr(logits, f32), _ld(logits), ptr(q1, f32), _ld(q1), ptr(q2, f32), _ld(q2),
+                                               ptr(log_alpha, f32), ptr(dlogits, f32), _ld(dlogits), ptr(acc, f32), B, A, stream_ptr()))
+
+
+def sac_discrete_alpha_step(log_alpha, adam_state, acc, batch, target_entropy, lr, loss_out=None):
+    check(load().gymrl_sac_discrete_alpha_step(ptr(log_alpha, f32), ptr(adam_state, f32), ptr(acc, f32), int(batch), float(target_entropy),
+                                               float(lr), ptr(loss_out, f32), stream_ptr()))
+
+
 def tanh_bound(z, bound, out=None):
     B, A = z.shape
     out = torch.empty(B, A, device=z.device, dtype=f32) if out is None else out

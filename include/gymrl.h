@@ -359,6 +359,23 @@ int gymrl_sac_actor_grad(const float* d_pre_tanh, const float* d_noise, const fl
  * scalar log_alpha (sac :257-263). d_adam_state = float64[3] {exp_avg, exp_avg_sq, step}. */
 int gymrl_sac_alpha_step(double* d_log_alpha, double* d_adam_state, const float* d_acc, int batch, double target_entropy,
                          double lr, float* d_loss_out, void* stream);
+/* Discrete SAC (algorithms/sac_cartpole.py): softmax policy p = softmax(logits), lp = log(p + 1e-8), H = -sum p lp.
+ *  target      y = r + gamma (1 - d) (sum_a p_a min(Q1t, Q2t)_a + alpha H) with the actor's logits on s' (ref :164-176);
+ *  critic_loss mse(Q1(s)[a], y), mse(Q2(s)[a], y): d_loss_acc[0], [1] += the two losses, gradients zero off the taken action (:178-189);
+ *  actor_grad  d/dlogits of mean(-alpha H - sum_a p_a min(Q1, Q2)_a); d_acc[0] += that loss, d_acc[1] += sum_i H_i (:191-200);
+ *  alpha_step  alpha_loss = mean(exp(log_alpha) (H - target_entropy).detach()) and one float32 Adam step on log_alpha,
+ *              d_adam_state = float32[3] {exp_avg, exp_avg_sq, step} (:202-207).  log_alpha is a float32 device scalar here. */
+int gymrl_sac_discrete_target(const float* d_logits_next, int ld_logits, const float* d_q1t, int ld_q1t, const float* d_q2t,
+                              int ld_q2t, const float* d_reward, const float* d_done, const int32_t* d_row_index,
+                              const float* d_log_alpha, float gamma, float* d_y, int batch, int n_actions, void* stream);
+int gymrl_sac_discrete_critic_loss(const float* d_q1, int ld_q1, const float* d_q2, int ld_q2, const int32_t* d_action,
+                                   const int32_t* d_row_index, const float* d_y, float* d_dq1, int ld_dq1, float* d_dq2,
+                                   int ld_dq2, float* d_loss_acc, int batch, int n_actions, void* stream);
+int gymrl_sac_discrete_actor_grad(const float* d_logits, int ld_logits, const float* d_q1, int ld_q1, const float* d_q2,
+                                  int ld_q2, const float* d_log_alpha, float* d_dlogits, int ld_dlogits, float* d_acc,
+                                  int batch, int n_actions, void* stream);
+int gymrl_sac_discrete_alpha_step(float* d_log_alpha, float* d_adam_state, const float* d_acc, int batch, float target_entropy,
+                                  float lr, float* d_loss_out, void* stream);
 /* a = tanh(z)*bound (td3_pendulum.py:59-62) and its backward dz = da * bound * (1 - (a/bound)^2) (td3 :215-217). */
 int gymrl_tanh_bound(const float* d_z, int ld_z, float* d_action, float bound, int batch, int act_dim, void* stream);
 int gymrl_tanh_bound_grad(const float* d_action, const float* d_dq_daction, int ld_dq, float* d_dz, int ld_dz, float bound,

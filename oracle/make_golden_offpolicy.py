@@ -374,6 +374,44 @@ def gen_ddqn_per(duel: bool):
     out.update(losses=np.array([l1, l2]), beta2=cfg.beta)
     np.savez(OUT / ("ddqn_per_duel_update.npz" if duel else "ddqn_per_update.npz"), **out)
 
+
+# ------------------------------------------------------------------------------------------------ discrete SAC
+def gen_sac_discrete():
+    """SACTrainer.update x2 (algorithms/sac_cartpole.py:155-221) on a fixed batch: softmax actor, twin critics with separate
+    optimisers, entropy-regularised target, float32 log_alpha with its own Adam, Polyak of both targets."""
+    rl.install_gymnasium_stub(make=lambda name, **k: rl.FakeEnv(4, n_actions=2, max_steps=500))
+    m = rl.load("algorithms/sac_cartpole.py")
+    torch.manual_seed(12)
+    cfg = m.Config(); cfg.device = "cpu"; cfg.batch_size = 256; cfg.hidden_dim = 64
+    import io, contextlib
+    with contextlib.redirect_stdout(io.StringIO()):
+        t = m.SACTrainer(cfg)
+    with torch.no_grad():
+        for net in (t.critic1_target, t.critic2_target):
+            for p in net.parameters():
+                p.add_(0.05 * torch.randn_like(p))
+        t.actor.fc3.weight.mul_(3.0)               # a policy that is not uniform
+        t.log_alpha.fill_(float(np.log(0.2)))
+    rng = np.random.default_rng(13)
+    B = cfg.batch_size
+    batch = (rng.standard_normal((B, 4)).astype(np.float32), rng.integers(0, 2, B), (rng.standard_normal(B) * 2).astype(np.float32),
+             rng.standard_normal((B, 4)).astype(np.float32), rng.random(B) < 0.1)
+    out = dict(states=batch[0], action=batch[1].astype(np.int32), reward=batch[2], next_states=batch[3], done=batch[4].astype(np.uint8),
+               gamma=cfg.gamma, tau=cfg.tau, log_alpha0=float(t.log_alpha.item()))
+    nets = dict(a=t.actor, c1=t.critic1, c2=t.critic2, c1t=t.critic1_target, c2t=t.critic2_target)
+    for k, net in nets.items():
+        out.update(_sd(net, f"{k}0_"))
+    t.memory.sample = lambda bs: batch
+    t.memory.buffer = deque([0] * B)
+    losses = []
+    for u in (1, 2):
+        losses.append(t.update())
+        for k, net in nets.items():
+            out.update(_sd(net, f"{k}{u}_"))
+        out[f"log_alpha{u}"] = float(t.log_alpha.item())
+    out["losses"] = np.array(losses)               # rows: (actor, critic1, critic2, alpha)
+    np.savez(OUT / "sac_discrete_update.npz", **out)
+
 def main():
     torch.set_num_threads(1)
     gen_sumtree()
@@ -383,6 +421,7 @@ def main():
     gen_noisy_dqn()
     gen_ddqn_per(False)
     gen_ddqn_per(True)
+    gen_sac_discrete()
     gen_sac()
     gen_td3()
     gen_ddpg()

@@ -229,6 +229,28 @@ def test_ddqn_per_update_matches_reference(golden, duel):
     leaf, prio = t.memory.tree.get_leaf(0.5 * t.memory.tree.total_priority())
     assert cap - 1 <= leaf < 2 * cap - 1 and prio > 0
 
+
+# ------------------------------------------------------------------------------------------------ discrete SAC
+def test_sac_discrete_update_matches_reference(golden):
+    """Two updates of algorithms/sac_cartpole.py: every network, log_alpha and the four losses after each update."""
+    from gymrl_b200.algorithms import sac_cartpole as Sd
+    g = golden("sac_discrete_update.npz")
+    cfg = Sd.Config(); cfg.batch_size, cfg.hidden_dim, cfg.seed, cfg.memory_capacity = 256, 64, 0, 1024
+    t = Sd.SACTrainer(cfg)
+    nets = dict(a=(t.actor, t.fp_a), c1=(t.critic1, t.fp_c1), c2=(t.critic2, t.fp_c2), c1t=(t.critic1_target, t.fp_c1t),
+                c2t=(t.critic2_target, t.fp_c2t))
+    for k, (net, fp) in nets.items():
+        _load(net, g, f"{k}0_"); fp.refresh_views()
+    t.log_alpha.fill_(float(g["log_alpha0"]))
+    _fill_ring(t.memory, g["states"], g["action"], g["reward"], g["next_states"], g["done"])
+    idx = torch.arange(256, device="cuda", dtype=i32)
+    for u in (1, 2):
+        t.update(idx)
+        np.testing.assert_allclose(t.losses(), g["losses"][u - 1], rtol=2e-4, atol=2e-6)
+        for k, (net, _) in nets.items():
+            _cmp(net, g, f"{k}{u}_", rtol=3e-4, atol=3e-6)
+        np.testing.assert_allclose(float(t.log_alpha.item()), float(g[f"log_alpha{u}"]), rtol=1e-5)
+
 # ------------------------------------------------------------------------------------------------ SAC
 def test_sac_update_matches_reference(golden):
     from gymrl_b200.algorithms import sac_pendulum as S
@@ -295,11 +317,12 @@ def test_ddpg_update_matches_reference(golden):
 
 
 # ------------------------------------------------------------------------------------------------ smoke at BASELINE sizes
-@pytest.mark.parametrize("algo", ["dqn", "rainbow", "sac", "td3", "ddpg", "noisy_dqn", "ddqn_per", "ddqn_per_duel"])
+@pytest.mark.parametrize("algo", ["dqn", "rainbow", "sac", "td3", "ddpg", "noisy_dqn", "ddqn_per", "ddqn_per_duel", "sac_discrete"])
 def test_offpolicy_trainers_run_vectorised(algo):
     import importlib
     name = {"dqn": "dqn_cartpole", "rainbow": "rainbow_dqn_cartpole", "sac": "sac_pendulum", "td3": "td3_pendulum", "ddpg": "ddpg_pendulum",
-            "noisy_dqn": "noisy_dqn_cartpole", "ddqn_per": "ddqn_per_cartpole", "ddqn_per_duel": "ddqn_per_duel_cartpole"}[algo]
+            "noisy_dqn": "noisy_dqn_cartpole", "ddqn_per": "ddqn_per_cartpole", "ddqn_per_duel": "ddqn_per_duel_cartpole",
+            "sac_discrete": "sac_cartpole"}[algo]
     M = importlib.import_module(f"gymrl_b200.algorithms.{name}")
     cfg = M.Config()
     cfg.num_envs, cfg.seed, cfg.max_locksteps = 1024, 3, 30
@@ -313,12 +336,13 @@ def test_offpolicy_trainers_run_vectorised(algo):
     assert len(r) == 4 and all(np.isfinite(r))
 
 
-@pytest.mark.parametrize("algo", ["rainbow", "sac", "td3", "ddpg"])
+@pytest.mark.parametrize("algo", ["rainbow", "sac", "td3", "ddpg", "sac_discrete"])
 def test_graph_lockstep_equals_eager_lockstep(algo):
     """train()'s captured lockstep (act -> env step -> store -> update as one CUDA graph, RNG draw counters / PER beta /
     learning rate in device scalars) leaves the same parameters, replay contents and env stream as the eager lockstep."""
     import importlib
-    name = {"rainbow": "rainbow_dqn_cartpole", "sac": "sac_pendulum", "td3": "td3_pendulum", "ddpg": "ddpg_pendulum"}[algo]
+    name = {"rainbow": "rainbow_dqn_cartpole", "sac": "sac_pendulum", "td3": "td3_pendulum", "ddpg": "ddpg_pendulum",
+            "sac_discrete": "sac_cartpole"}[algo]
     M = importlib.import_module(f"gymrl_b200.algorithms.{name}")
     cls = [getattr(M, k) for k in dir(M) if k.endswith("Trainer")][0]
     res = []
@@ -336,7 +360,7 @@ def test_graph_lockstep_equals_eager_lockstep(algo):
             assert t.graph_launches > 0
         if algo == "td3" and use_graph:
             assert sorted(t._g_lockstep) == [0, 1]          # one graph per phase: critic + actor / critic only
-        fps = [getattr(t, k) for k in ("fp", "fp_t", "fp_a", "fp_at", "fp_c", "fp_ct") if hasattr(t, k)]
+        fps = [getattr(t, k) for k in ("fp", "fp_t", "fp_a", "fp_at", "fp_c", "fp_ct", "fp_c1", "fp_c2", "fp_c1t", "fp_c2t") if hasattr(t, k)]
         ring = t.memory.ring if hasattr(t.memory, "ring") else t.memory
         res.append(([f.flat.clone() for f in fps], t.cur.clone(), ring.obs.clone(), ring.reward.clone(), ring.state.clone(), len(t.memory)))
     (pa, ca, oa, ra, sa, la), (pb, cb, ob, rb, sb, lb) = res
