@@ -486,7 +486,11 @@ extern "C" int gymrl_linear_backward_weight(const float* d_dy, int lddy, const f
         memset(&t, 0, sizeof(t));
         t.A = d_dy; t.lda = lddy; t.B = d_x; t.ldb = ldx; t.b_rows = d_row_index; t.C = ws; t.ldc = K;
         t.M = N; t.N = K; t.K = M;
-        const int tc_tiles = ceil_div(N, 128) * ceil_div(K, 256);
+        // column-tile width of the dW GEMM: narrower tiles need fewer split-K slices to fill the SMs, i.e. fewer partial tiles to
+        // write and fold, at the price of re-reading dY once per column tile (GYMRL_DW_BN = 64 / 128 / 256 for A/B runs)
+        static const int dw_bn = [] { const char* e = getenv("GYMRL_DW_BN"); const int v = e ? atoi(e) : 256; return (v == 64 || v == 128) ? v : 256; }();
+        t.bn_max = dw_bn;
+        const int tc_tiles = ceil_div(N, 128) * ceil_div(K, dw_bn);
         int tsplits = GYMRL_NUM_SMS / tc_tiles;
         if (tsplits > 64) tsplits = 64;
         if (tsplits > M / 256) tsplits = M / 256;

@@ -732,9 +732,10 @@ int tc_gemm_launch(const TcGemmParams& p, bool a_kmajor, bool b_kmajor, int spli
     // widest tile that still gives (nearly) every SM a CTA: the rollout's M = 4096 forward would otherwise run 32 CTAs
     // on 148 SMs.  (tc_gemm_supported guarantees N % 64 == 0.)
     const long long mt = (long long)ceil_div(p.M, 128) * splits;
+    const int bn_max = p.bn_max > 0 ? p.bn_max : 256;
     int bn = 64;
-    if (p.N % 256 == 0 && mt * (p.N / 256) >= 120) bn = 256;
-    else if (p.N % 128 == 0 && mt * (p.N / 128) >= 120) bn = 128;
+    if (bn_max >= 256 && p.N % 256 == 0 && mt * (p.N / 256) >= 120) bn = 256;
+    else if (bn_max >= 128 && p.N % 128 == 0 && mt * (p.N / 128) >= 120) bn = 128;
     // A through tensor memory (TS kernel) for MN-major A, i.e. the dW GEMMs: there a thread's 16 k-values of its row are
     // coalesced loads and the variant measured 8 % faster (26.9 -> 24.7 us at 512 x 256 x 16384).  For K-major A the row-owned
     // 64 B loads touch 32 lines per instruction and it measured 10 % slower than the SS kernel (17.2 -> 18.9 us at

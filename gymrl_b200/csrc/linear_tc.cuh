@@ -12,6 +12,7 @@ struct TcGemmParams {
     int k_chunk;                 // reduction elements per blockIdx.z (multiple of 32)
     long long c_split_stride;
     float* colsum;               // MN-major A only (dW): colsum[blockIdx.z][M] = sum over this split's k of A[k][m] (nullable)
+    int bn_max;                  // widest column tile to use (0 = 256): narrower tiles = fewer split-K partials for the dW GEMMs
 };
 
 bool tc_gemm_supported(const TcGemmParams& p, bool a_kmajor, bool b_kmajor);
