@@ -249,6 +249,8 @@ __global__ void __launch_bounds__(256) smallk_fwd4_kernel(const float* __restric
                                                           float* __restrict__ y, int ldy, int M, int N, int act, int rows_per_block) {
     const int cg = threadIdx.x & 63, rg = threadIdx.x >> 6;      // a warp shares rg: its x-row reads are broadcasts
     const int n = (blockIdx.x * 64 + cg) * 4;
+    pdl_wait();
+    pdl_launch_dependents();
     const int m_beg = blockIdx.y * rows_per_block, m_end = min(M, m_beg + rows_per_block);
     const int nrows = m_end - m_beg;
     __shared__ __align__(16) float sx[kSmallKRowsMax][K == 3 ? 4 : K];
@@ -310,9 +312,9 @@ int smallk_forward(const float* x, int ldx, const int32_t* rows, const float* w,
     const bool vec = smallk_vec_enabled() && (N % 4 == 0) && (ldy % 4 == 0) && ((reinterpret_cast<uintptr_t>(y) & 15) == 0) &&
                      (!b || (reinterpret_cast<uintptr_t>(b) & 15) == 0);
     if (vec) {
-        if (K == 3) smallk_fwd4_kernel<3><<<grid, 256, 0, s>>>(x, ldx, rows, w, b, y, ldy, M, N, act, rpb);
-        else if (K == 4) smallk_fwd4_kernel<4><<<grid, 256, 0, s>>>(x, ldx, rows, w, b, y, ldy, M, N, act, rpb);
-        else smallk_fwd4_kernel<8><<<grid, 256, 0, s>>>(x, ldx, rows, w, b, y, ldy, M, N, act, rpb);
+        if (K == 3) gymrl_launch_pdl(smallk_fwd4_kernel<3>, grid, dim3(256), 0, s, x, ldx, rows, w, b, y, ldy, M, N, act, rpb);
+        else if (K == 4) gymrl_launch_pdl(smallk_fwd4_kernel<4>, grid, dim3(256), 0, s, x, ldx, rows, w, b, y, ldy, M, N, act, rpb);
+        else gymrl_launch_pdl(smallk_fwd4_kernel<8>, grid, dim3(256), 0, s, x, ldx, rows, w, b, y, ldy, M, N, act, rpb);
     } else if (K == 3) smallk_fwd_kernel<3><<<grid, 256, 0, s>>>(x, ldx, rows, w, b, y, ldy, M, N, act, rpb);
     else if (K == 4) smallk_fwd_kernel<4><<<grid, 256, 0, s>>>(x, ldx, rows, w, b, y, ldy, M, N, act, rpb);
     else smallk_fwd_kernel<8><<<grid, 256, 0, s>>>(x, ldx, rows, w, b, y, ldy, M, N, act, rpb);
@@ -381,6 +383,8 @@ __global__ void __launch_bounds__(256) smallk_dw4_kernel(const float* __restrict
                                                          float* __restrict__ part_b, int M, int N) {
     const int cg = threadIdx.x & 63, rg = threadIdx.x >> 6;
     const int n = (blockIdx.x * 64 + cg) * 4;
+    pdl_wait();
+    pdl_launch_dependents();
     const int m_beg = blockIdx.y * kSmallKDwRows, m_end = min(M, m_beg + kSmallKDwRows);
     const int nrows = m_end - m_beg;
     __shared__ __align__(16) float sx[kSmallKDwRows][K == 3 ? 4 : K];
@@ -460,9 +464,9 @@ int smallk_dw(const float* dy, int lddy, const float* x, int ldx, const int32_t*
     const bool vec = smallk_vec_enabled() && (N % 4 == 0) && (lddy % 4 == 0) && ((reinterpret_cast<uintptr_t>(dy) & 15) == 0);
     if (vec && chunks == ceil_div(M, kSmallKDwRows)) {
         dim3 grid(ceil_div(N, 256), chunks);
-        if (K == 3) smallk_dw4_kernel<3><<<grid, 256, 0, s>>>(dy, lddy, x, ldx, rows, part_w, part_b, M, N);
-        else if (K == 4) smallk_dw4_kernel<4><<<grid, 256, 0, s>>>(dy, lddy, x, ldx, rows, part_w, part_b, M, N);
-        else smallk_dw4_kernel<8><<<grid, 256, 0, s>>>(dy, lddy, x, ldx, rows, part_w, part_b, M, N);
+        if (K == 3) gymrl_launch_pdl(smallk_dw4_kernel<3>, grid, dim3(256), 0, s, dy, lddy, x, ldx, rows, part_w, part_b, M, N);
+        else if (K == 4) gymrl_launch_pdl(smallk_dw4_kernel<4>, grid, dim3(256), 0, s, dy, lddy, x, ldx, rows, part_w, part_b, M, N);
+        else gymrl_launch_pdl(smallk_dw4_kernel<8>, grid, dim3(256), 0, s, dy, lddy, x, ldx, rows, part_w, part_b, M, N);
         gymrl_count_launch();
         return GYMRL_OK;
     }

@@ -6,17 +6,18 @@
 // accumulated as  A_lo*B_hi + A_hi*B_lo + A_hi*B_hi  (the dropped lo*lo term is ~2^-22 relative), which keeps
 // the reference's fp32 parity bar while running on the tensor pipe (kind::tf32, UMMA 128 x BN x 8).
 //
-// One CTA (4 warps) owns a 128 x BN output tile (BN = 64/128/256 -> 64..256 TMEM columns):
-//   (8 warps / 256 threads since v2)
+// One CTA (8 producer / epilogue warps + 1 MMA-issue warp) owns a 128 x BN output tile (BN = 64/128/256 TMEM columns):
 //   stage loop over K in slabs of 32 floats (= one 128-byte swizzle span), two smem stages:
-//     all 128 threads: LDG.128 the A/B slab (row gather fused for A), split hi/lo, STS.128 into the canonical
-//                      UMMA shared-memory layout (SWIZZLE_128B; K-major: 8-row x 128 B atoms, MN-major: 8 k-rows x 128 B
-//                      atoms), fence.proxy.async, __syncthreads
-//     one elected thread: 4 k-steps x 3 tcgen05.mma (descriptors advance 32 B inside the swizzle atom for K-major,
+//     producer warps:  LDG.128 the A/B slab one slab ahead (row gather fused for A), split hi/lo, st.shared.v4 into the
+//                      canonical UMMA shared-memory layout (SWIZZLE_128B; K-major: 8-row x 128 B atoms, MN-major: 128B_BASE32B
+//                      atoms), fence.proxy.async, mbarrier arrive (full)
+//     MMA warp, one lane: 4 k-steps x 3 tcgen05.mma (descriptors advance 32 B inside the swizzle atom for K-major,
 //                      one atom row-block per k-step for MN-major), tcgen05.commit -> mbarrier that frees the stage
-//   so the tensor core works on stage s while the threads fill stage s^1 (operands never round-trip through HBM
-//   in split form).  Epilogue: tcgen05.ld 32 lanes x 32 columns per warp -> bias / tanh / relu / act'(h) -> global.
-//   Backward-weight runs split-K over blockIdx.z with deterministic partial tiles (reduced by linear.cu).
+//   so the tensor core works on stage s while the producers fill stage s^1 (operands never round-trip through HBM
+//   in split form).  Epilogue: tcgen05.ld 32 lanes x 32 columns per warp -> per-warp smem transpose -> bias / tanh / relu /
+//   act'(h) (one instantiation per variant) -> coalesced 128 B row segments.
+//   Backward-weight runs split-K over blockIdx.z with deterministic partial tiles (folded by reduce.cu / linear_skinny.cu);
+//   its MN-major A operand goes through tensor memory instead of shared memory (gemm_tf32x3_ts_kernel below).
 // No TMA: the operands need the register pass for the split (and the minibatch row gather), so a bulk tensor
 // copy cannot produce them; staging is plain coalesced 128 B row reads instead.
 // All mbarrier waits are bounded (trap on timeout) so a descriptor bug cannot hang the GPU.
@@ -322,6 +323,9 @@ __global__ void __launch_bounds__(TC_LAUNCH_THREADS, 1) gemm_tf32x3_kernel(const
     __syncthreads();
     asm volatile("tcgen05.fence::after_thread_sync;" ::: "memory");
     const uint32_t tmem_d = tmem_base_s;
+    // PDL: barrier init and the TMEM allocation above touch no global memory, so they overlap the predecessor's tail
+    pdl_wait();
+    pdl_launch_dependents();
 
     long long* dbg = (g_tc_dbg && blockIdx.x == 0 && blockIdx.y == 0 && blockIdx.z == 0 && (t == 0 || t == TC_THREADS)) ? g_tc_dbg + (t ? 512 : 0) : nullptr;
     TC_STAMP(0);
@@ -565,6 +569,9 @@ __global__ void __launch_bounds__(TC_LAUNCH_THREADS, 1) gemm_tf32x3_ts_kernel(co
     __syncthreads();
     asm volatile("tcgen05.fence::after_thread_sync;" ::: "memory");
     const uint32_t tmem_d = tmem_base_s;
+    // PDL: barrier init and the TMEM allocation above touch no global memory, so they overlap the predecessor's tail
+    pdl_wait();
+    pdl_launch_dependents();
     long long* dbg = nullptr;
     TC_GSTAMP(1);
 
@@ -695,7 +702,7 @@ static int launch_tc_ts(const TcGemmParams& p, int splits, cudaStream_t s) {
         configured = true;
     }
     dim3 grid(p.N / BN, ceil_div(p.M, 128), splits);
-    gemm_tf32x3_ts_kernel<BN, AK, BKM><<<grid, TC_LAUNCH_THREADS, SMEM, s>>>(p);
+    gymrl_launch_pdl(gemm_tf32x3_ts_kernel<BN, AK, BKM>, grid, dim3(TC_LAUNCH_THREADS), SMEM, s, p);
     gymrl_count_launch();
     return GYMRL_OK;
 }
@@ -711,7 +718,7 @@ static int launch_tc(const TcGemmParams& p, int splits, cudaStream_t s) {
         configured = true;
     }
     dim3 grid(p.N / BN, ceil_div(p.M, 128), splits);
-    gemm_tf32x3_kernel<BN, AK, BKM><<<grid, TC_LAUNCH_THREADS, SMEM, s>>>(p);
+    gymrl_launch_pdl(gemm_tf32x3_kernel<BN, AK, BKM>, grid, dim3(TC_LAUNCH_THREADS), SMEM, s, p);
     gymrl_count_launch();
     return GYMRL_OK;
 }

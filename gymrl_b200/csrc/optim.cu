@@ -106,6 +106,8 @@ __global__ void __launch_bounds__(256) clip_adam_kernel(float* __restrict__ para
                                                         float grad_scale, uint32_t* __restrict__ done_counter) {
     __shared__ double scratch[32];
     __shared__ float s_coef;
+    pdl_wait();
+    pdl_launch_dependents();
     const int t = *step + 1;
     double q = 0.0;
     for (int i = threadIdx.x; i < n_partials; i += blockDim.x) q += sumsq_partials[i];
@@ -152,9 +154,8 @@ extern "C" int gymrl_clip_adam_step(float* d_param, const float* d_grad, float* 
     const int threads = 256;
     long long blocks = ceil_div_ll(n, threads);
     if (blocks > GYMRL_NUM_SMS * 4) blocks = GYMRL_NUM_SMS * 4;
-    clip_adam_kernel<<<(int)blocks, threads, 0, as_stream(stream)>>>(d_param, d_grad, d_exp_avg, d_exp_avg_sq, n, d_lr, beta1, beta2, eps,
-                                                                   d_step, d_sumsq_partials, n_partials, max_norm, grad_scale,
-                                                                   d_done_counter);
+    gymrl_launch_pdl(clip_adam_kernel, dim3((int)blocks), dim3(threads), 0, as_stream(stream), d_param, d_grad, d_exp_avg, d_exp_avg_sq, n, d_lr,
+                     beta1, beta2, eps, d_step, d_sumsq_partials, n_partials, max_norm, grad_scale, d_done_counter);
     gymrl_count_launch();
     GYMRL_LAUNCH_CHECK("clip_adam_step");
     return GYMRL_OK;

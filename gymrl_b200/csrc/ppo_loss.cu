@@ -194,6 +194,8 @@ ppo_heads_fused_kernel(const float* __restrict__ h, int ldh, const float* __rest
     __shared__ float s_met[kHeadsWarps][6];
     const int lane = threadIdx.x & 31, wid = threadIdx.x >> 5;
     const int warp = blockIdx.x * kHeadsWarps + wid, nwarps = gridDim.x * kHeadsWarps;
+    pdl_wait();
+    pdl_launch_dependents();
     for (int i = threadIdx.x; i < P; i += blockDim.x) s_acc[i] = 0.f;
     float4 wa[A][NCH], wc[NCH], gwa[A][NCH], gwc[NCH];
     float bav[A];
@@ -338,11 +340,11 @@ extern "C" int gymrl_ppo_heads_fused(const float* d_h, int ldh, const float* d_W
     const size_t smem = (size_t)P * sizeof(float);
     float* partials = (float*)d_workspace;
     if (H == 256)
-        ppo_heads_fused_kernel<2, 4><<<grid, kHeadsWarps * 32, smem, s>>>(d_h, ldh, d_Wa, d_ba, d_Wc, d_bc, d_row_index, d_action, d_logp_old, d_adv,
+        gymrl_launch_pdl(ppo_heads_fused_kernel<2, 4>, dim3(grid), dim3(kHeadsWarps * 32), smem, s, d_h, ldh, d_Wa, d_ba, d_Wc, d_bc, d_row_index, d_action, d_logp_old, d_adv,
                                                                            d_ret, d_entropy_old, d_value_old, d_dh, lddh, act_in, d_lv_out, partials,
                                                                            d_metrics, batch, *cfg);
     else
-        ppo_heads_fused_kernel<1, 4><<<grid, kHeadsWarps * 32, smem, s>>>(d_h, ldh, d_Wa, d_ba, d_Wc, d_bc, d_row_index, d_action, d_logp_old, d_adv,
+        gymrl_launch_pdl(ppo_heads_fused_kernel<1, 4>, dim3(grid), dim3(kHeadsWarps * 32), smem, s, d_h, ldh, d_Wa, d_ba, d_Wc, d_bc, d_row_index, d_action, d_logp_old, d_adv,
                                                                            d_ret, d_entropy_old, d_value_old, d_dh, lddh, act_in, d_lv_out, partials,
                                                                            d_metrics, batch, *cfg);
     if (gymrl_defer_reduce(partials, P, grid, A * H, d_dWa, accumulate)) {

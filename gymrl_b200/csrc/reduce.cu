@@ -13,6 +13,14 @@
 
 void gymrl_count_launch(int n = 1);
 
+#include <cstdlib>
+bool gymrl_pdl_enabled() {
+    // off unless GYMRL_PDL=1: measured neutral on B200 (whole PPO minibatch 205.7 us serialised vs 207.1 us with PDL edges in the
+    // epoch graph — kernel nodes of one graph already launch back to back), so the plain stream order stays the default
+    static const bool on = [] { const char* e = getenv("GYMRL_PDL"); return e && e[0] == '1'; }();
+    return on;
+}
+
 namespace {
 
 constexpr int kMaxSegs = 24;
@@ -38,6 +46,8 @@ thread_local SegTable t_table;
 __global__ void __launch_bounds__(256) reduce_segments_kernel(const SegTable tab, double* __restrict__ sumsq_partials) {
     __shared__ float sm[kGroups][32];
     __shared__ double scratch[32];
+    pdl_wait();
+    pdl_launch_dependents();
     int si = 0;
 #pragma unroll 1
     for (int q = 1; q < tab.nseg; ++q)
@@ -106,7 +116,7 @@ int launch_table(const SegTable& tab_in, double* d_sumsq_partials, int capacity,
     if (n_blocks) *n_blocks = blocks;
     if (blocks == 0) return GYMRL_OK;
     GYMRL_REQUIRE(!d_sumsq_partials || capacity >= blocks, "sum-of-squares partial buffer too small: need %d entries", blocks);
-    reduce_segments_kernel<<<blocks, 256, 0, s>>>(tab, d_sumsq_partials);
+    gymrl_launch_pdl(reduce_segments_kernel, dim3(blocks), dim3(256), 0, s, tab, d_sumsq_partials);
     gymrl_count_launch();
     GYMRL_LAUNCH_CHECK("reduce_segments");
     return GYMRL_OK;
