@@ -125,3 +125,26 @@ def test_sqrt_threshold():
     rng = np.random.default_rng(0)
     xr = np.exp(rng.uniform(-30, 5, 200000)).astype(np.float32)
     assert np.array_equal(np.sqrt(xr) <= slop, xr <= T)
+
+
+# ------------------------------------------------------------------------------------------------ golden provenance
+@pytest.mark.parametrize("gen,name", [("gen_noisy_dqn", "noisy_dqn_update.npz"), ("gen_sac_discrete", "sac_discrete_update.npz"),
+                                      ("gen_ddqn_per", "ddqn_per_update.npz"), ("gen_ddqn_per_duel", "ddqn_per_duel_update.npz")])
+def test_offpolicy_goldens_regenerate_from_the_reference(gen, name, golden, tmp_path, monkeypatch):
+    """The committed fixtures of the §8f rank-2 trainers are what oracle/make_golden_offpolicy.py produces from the reference
+    tree (run here, in the build container; skipped on the GPU box where /root/reference does not exist)."""
+    from oracle import ref_loader
+    if not ref_loader.available():
+        pytest.skip("reference tree not present")
+    import oracle.make_golden_offpolicy as mg
+    monkeypatch.setattr(mg, "OUT", tmp_path)
+    if gen == "gen_ddqn_per":
+        mg.gen_ddqn_per(False)
+    elif gen == "gen_ddqn_per_duel":
+        mg.gen_ddqn_per(True)
+    else:
+        getattr(mg, gen)()
+    new, old = np.load(tmp_path / name), golden(name)
+    assert sorted(new.files) == sorted(old.files)
+    for k in old.files:
+        np.testing.assert_allclose(new[k], old[k], rtol=1e-6, atol=1e-7, err_msg=k)
