@@ -191,3 +191,44 @@ def reward_scaling_stream(r, reset_at, gamma):
         rm.update(R)
         out[t] = np.float32(r[t] / (float(np.asarray(rm.std, np.float64)[0]) + 1e-8))
     return out
+
+
+# ---- discrete SAC (algorithms/sac_cartpole.py:155-221) ------------------------------------------------------
+def _softmax_entropy(logits):
+    """p = softmax(logits), lp = log(p + 1e-8), H = -sum p lp  (Actor.forward :96-99 and the update :166-168, :191-193)."""
+    z = np.asarray(logits, np.float64)
+    e = np.exp(z - z.max(axis=1, keepdims=True))
+    p = e / e.sum(axis=1, keepdims=True)
+    lp = np.log(p + 1e-8)
+    return p, lp, -(p * lp).sum(axis=1)
+
+
+def sac_discrete_target(logits_next, q1t, q2t, reward, done, log_alpha, gamma):
+    """target_q = r + gamma (1 - d) (sum_a p' min(Q1t, Q2t) + alpha H(p'))  (ref :164-176); float64 [B]."""
+    p, _, H = _softmax_entropy(logits_next)
+    mq = (p * np.minimum(np.asarray(q1t, np.float64), np.asarray(q2t, np.float64))).sum(axis=1)
+    return np.asarray(reward, np.float64) + gamma * (1.0 - np.asarray(done, np.float64)) * (mq + np.exp(float(log_alpha)) * H)
+
+
+def sac_discrete_critic(q1, q2, action, y):
+    """mse(Q1(s)[a], y), mse(Q2(s)[a], y) and their gradients wrt the full [B, A] outputs (ref :178-189)."""
+    q1, q2, y = np.asarray(q1, np.float64), np.asarray(q2, np.float64), np.asarray(y, np.float64)
+    B = len(y)
+    rows = np.arange(B)
+    e1, e2 = q1[rows, action] - y, q2[rows, action] - y
+    d1, d2 = np.zeros_like(q1), np.zeros_like(q2)
+    d1[rows, action] = 2.0 * e1 / B
+    d2[rows, action] = 2.0 * e2 / B
+    return dict(loss1=(e1 ** 2).mean(), loss2=(e2 ** 2).mean(), dq1=d1, dq2=d2)
+
+
+def sac_discrete_actor(logits, q1, q2, log_alpha):
+    """actor_loss = mean(-alpha H - sum_a p min(Q1, Q2)) and d/dlogits through softmax and log(p + 1e-8) (ref :191-200);
+    sum_entropy feeds the alpha loss mean(exp(log_alpha) (H - target_entropy)) (ref :202-204)."""
+    p, lp, H = _softmax_entropy(logits)
+    alpha = np.exp(float(log_alpha))
+    m = np.minimum(np.asarray(q1, np.float64), np.asarray(q2, np.float64))
+    B = p.shape[0]
+    g = alpha * (lp + p / (p + 1e-8)) - m                  # dL_i / dp_j
+    dz = p * (g - (p * g).sum(axis=1, keepdims=True)) / B
+    return dict(loss=(-alpha * H - (p * m).sum(axis=1)).mean(), dlogits=dz, sum_entropy=H.sum())

@@ -251,6 +251,39 @@ def test_sac_discrete_update_matches_reference(golden):
             _cmp(net, g, f"{k}{u}_", rtol=3e-4, atol=3e-6)
         np.testing.assert_allclose(float(t.log_alpha.item()), float(g[f"log_alpha{u}"]), rtol=1e-5)
 
+
+@pytest.mark.parametrize("B,A_", [(1, 2), (5, 4), (1777, 2), (4096, 3)])
+def test_sac_discrete_kernels_vs_oracle(B, A_):
+    """gymrl_sac_discrete_target / critic_loss / actor_grad against oracle.algos_np at ragged sizes, with the row gather and
+    padded leading dimensions the trainers use."""
+    from oracle import algos_np as Anp
+    from gymrl_b200 import ops_offpolicy as off
+    rng = np.random.default_rng(B + A_)
+    Btot = B + 300
+    idx = rng.permutation(Btot)[:B].astype(np.int32)
+    z, zn = (rng.standard_normal((B, A_)) * 2).astype(np.float32), (rng.standard_normal((B, A_)) * 2).astype(np.float32)
+    q1, q2, q1t, q2t = (rng.standard_normal((B, A_)).astype(np.float32) for _ in range(4))
+    r, d = rng.standard_normal(Btot).astype(np.float32), (rng.random(Btot) < 0.2).astype(np.float32)
+    act = rng.integers(0, A_, Btot).astype(np.int32)
+    la = torch.tensor([np.log(0.3)], device="cuda", dtype=torch.float32)
+    pad = lambda x: torch.nn.functional.pad(cu(x), (0, 8 - A_))[:, :A_]          # row stride 8: non-trivial leading dimension
+    y = off.sac_discrete_target(pad(zn), pad(q1t), pad(q2t), cu(r), cu(d), la, 0.9, row_index=cu(idx))
+    y_ref = Anp.sac_discrete_target(zn, q1t, q2t, r[idx], d[idx], float(la.item()), 0.9)
+    np.testing.assert_allclose(y.cpu().numpy(), y_ref, rtol=2e-5, atol=2e-6)
+    dq1, dq2 = torch.full((B, 8), float("nan"), device="cuda")[:, :A_], torch.full((B, 8), float("nan"), device="cuda")[:, :A_]
+    acc = torch.zeros(2, device="cuda")
+    off.sac_discrete_critic_loss(pad(q1), pad(q2), cu(act), y, dq1, dq2, row_index=cu(idx), loss_acc=acc)
+    c = Anp.sac_discrete_critic(q1, q2, act[idx], y.cpu().numpy())
+    np.testing.assert_allclose(acc.cpu().numpy(), [c["loss1"], c["loss2"]], rtol=1e-4, atol=1e-6)
+    np.testing.assert_allclose(dq1.cpu().numpy(), c["dq1"], rtol=1e-4, atol=1e-8)
+    np.testing.assert_allclose(dq2.cpu().numpy(), c["dq2"], rtol=1e-4, atol=1e-8)
+    dz = torch.full((B, 8), float("nan"), device="cuda")[:, :A_]
+    acc2 = torch.zeros(2, device="cuda")
+    off.sac_discrete_actor_grad(pad(z), pad(q1), pad(q2), la, dz, acc2)
+    a = Anp.sac_discrete_actor(z, q1, q2, float(la.item()))
+    np.testing.assert_allclose(dz.cpu().numpy(), a["dlogits"], rtol=2e-4, atol=2e-7 / B)
+    np.testing.assert_allclose(acc2.cpu().numpy(), [a["loss"], a["sum_entropy"]], rtol=1e-4, atol=1e-5)
+
 # ------------------------------------------------------------------------------------------------ SAC
 def test_sac_update_matches_reference(golden):
     from gymrl_b200.algorithms import sac_pendulum as S

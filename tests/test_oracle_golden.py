@@ -148,3 +148,44 @@ def test_offpolicy_goldens_regenerate_from_the_reference(gen, name, golden, tmp_
     assert sorted(new.files) == sorted(old.files)
     for k in old.files:
         np.testing.assert_allclose(new[k], old[k], rtol=1e-6, atol=1e-7, err_msg=k)
+
+
+def test_sac_discrete_oracle_matches_torch_autograd():
+    """oracle.algos_np.sac_discrete_* against the reference's own expressions (algorithms/sac_cartpole.py:164-204) evaluated
+    with torch autograd in float64 on the CPU."""
+    import torch
+    rng = np.random.default_rng(3)
+    B, A_ = 257, 3
+    z, zn = rng.standard_normal((B, A_)) * 2, rng.standard_normal((B, A_)) * 2
+    q1, q2, q1t, q2t = (rng.standard_normal((B, A_)) for _ in range(4))
+    r, d, act = rng.standard_normal(B), (rng.random(B) < 0.2).astype(np.float64), rng.integers(0, A_, B)
+    log_alpha, gamma = np.log(0.3), 0.9
+    T = lambda x: torch.tensor(x, dtype=torch.float64)
+    alpha = torch.tensor(log_alpha, dtype=torch.float64).exp()
+    # target (ref :164-176)
+    npb = torch.softmax(T(zn), dim=-1)
+    nlp = torch.log(npb + 1e-8)
+    nH = -(npb * nlp).sum(1, keepdim=True)
+    y_ref = T(r)[:, None] + gamma * (1 - T(d))[:, None] * ((npb * torch.min(T(q1t), T(q2t))).sum(1, keepdim=True) + alpha * nH)
+    y = A.sac_discrete_target(zn, q1t, q2t, r, d, log_alpha, gamma)
+    np.testing.assert_allclose(y, y_ref[:, 0].numpy(), rtol=1e-12, atol=1e-12)
+    # critics (ref :178-189)
+    tq1, tq2 = T(q1).requires_grad_(), T(q2).requires_grad_()
+    l1 = torch.nn.functional.mse_loss(tq1.gather(1, torch.tensor(act)[:, None]), y_ref)
+    l2 = torch.nn.functional.mse_loss(tq2.gather(1, torch.tensor(act)[:, None]), y_ref)
+    (l1 + l2).backward()
+    c = A.sac_discrete_critic(q1, q2, act, y)
+    np.testing.assert_allclose([c["loss1"], c["loss2"]], [l1.item(), l2.item()], rtol=1e-12)
+    np.testing.assert_allclose(c["dq1"], tq1.grad.numpy(), rtol=1e-12, atol=1e-15)
+    np.testing.assert_allclose(c["dq2"], tq2.grad.numpy(), rtol=1e-12, atol=1e-15)
+    # actor (ref :191-200)
+    tz = T(z).requires_grad_()
+    pb = torch.softmax(tz, dim=-1)
+    lp = torch.log(pb + 1e-8)
+    H = -(pb * lp).sum(1, keepdim=True)
+    la = torch.mean(-alpha * H - (pb * torch.min(T(q1), T(q2))).sum(1, keepdim=True))
+    la.backward()
+    a = A.sac_discrete_actor(z, q1, q2, log_alpha)
+    np.testing.assert_allclose(a["loss"], la.item(), rtol=1e-12)
+    np.testing.assert_allclose(a["dlogits"], tz.grad.numpy(), rtol=1e-10, atol=1e-14)
+    np.testing.assert_allclose(a["sum_entropy"], H.sum().item(), rtol=1e-12)
