@@ -1,0 +1,181 @@
+"""The reference's CPU path, timed on this box's host cores — bench.py's `cpu_baseline` / `--impl reference` legs.
+TEST / BENCH INFRASTRUCTURE ONLY (see oracle/__init__.py).
+
+What is timed: one "step" of a worker = the reference's own PPO iteration at its own sizes,
+`PPOTrainer.collect_rollout()` (2048 single-env steps, batch-1 policy forward each) + `PPOTrainer.update()` (fp64 Python-loop
+GAE, 10 epochs x 32 minibatches of 64, clip_grad_norm_ 0.5, Adam).
+
+  kind = "reference": the UNMODIFIED /root/reference/algorithms/ppo_lunarlander.py driven through its public methods on
+                      oracle/gymnasium_shim (only where /root/reference exists, i.e. the build container);
+  kind = "port":      oracle/ref_port.py, the hand port of the same loop over the same C env (what can travel to the GPU box).
+
+Reproducibility (round-1 verdict, weak #5): P worker processes are started ONCE, each pinned with sched_setaffinity to its
+own core (one hardware thread per physical core, inside this process's affinity mask and cgroup CPU quota), torch at 1 thread;
+every step is a barrier-released round in which each worker runs exactly one iteration; value = P x 2048 / slowest worker.
+Rows reported: (a) 1 process / 1 thread, (b) 1 process / torch default threads, (c) P pinned processes (the headline).
+"""
+from __future__ import annotations
+
+import multiprocessing as mp
+import os
+import subprocess
+import time
+from pathlib import Path
+
+UPDATE_FREQ = 2048
+
+
+# ----------------------------------------------------------------------------------------------- host topology
+def _cgroup_quota_cores() -> float | None:
+    try:
+        q, p = Path("/sys/fs/cgroup/cpu.max").read_text().split()
+        if q != "max":
+            return float(q) / float(p)
+    except Exception:
+        pass
+    try:
+        q = int(Path("/sys/fs/cgroup/cpu/cpu.cfs_quota_us").read_text())
+        p = int(Path("/sys/fs/cgroup/cpu/cpu.cfs_period_us").read_text())
+        if q > 0:
+            return q / p
+    except Exception:
+        pass
+    return None
+
+
+def host_info() -> dict:
+    aff = sorted(os.sched_getaffinity(0))
+    # one hardware thread per physical core
+    seen, phys = set(), []
+    for c in aff:
+        try:
+            sib = Path(f"/sys/devices/system/cpu/cpu{c}/topology/thread_siblings_list").read_text().strip()
+        except Exception:
+            sib = str(c)
+        if sib not in seen:
+            seen.add(sib)
+            phys.append(c)
+    model = ""
+    try:
+        for line in subprocess.run(["lscpu"], capture_output=True, text=True).stdout.splitlines():
+            if line.startswith("Model name:"):
+                model = line.split(":", 1)[1].strip()
+                break
+    except Exception:
+        pass
+    quota = _cgroup_quota_cores()
+    usable = len(phys)
+    if quota is not None:
+        usable = max(1, min(usable, int(quota)))
+    return {"nproc": len(aff), "os_cpu_count": os.cpu_count(), "physical_cores_in_mask": len(phys), "cgroup_quota_cores": quota,
+            "model": model, "worker_cores": phys[:usable]}
+
+
+# ----------------------------------------------------------------------------------------------- workers
+def _make_stepper(kind: str, seed: int, threads: int | None):
+    import random
+
+    import numpy as np
+    import torch
+    if threads:
+        torch.set_num_threads(threads)
+    torch.manual_seed(seed)
+    np.random.seed(seed)
+    random.seed(seed)
+    if kind == "reference":
+        import contextlib
+        import io
+
+        from . import gymnasium_shim, ref_loader
+        gymnasium_shim.install()
+        mod = ref_loader.load("algorithms/ppo_lunarlander.py", name=f"ref_cpu_arm_{seed}")
+        cfg = mod.Config()
+        cfg.device = "cpu"
+        with contextlib.redirect_stdout(io.StringIO()):
+            tr = mod.PPOTrainer(cfg)
+
+        def step():
+            nv = tr.collect_rollout()          # ref :198-231 (2048 env steps)
+            tr.update(nv)                      # ref :233-330
+            return cfg.update_freq
+        return step
+    from .ref_port import PortTrainer
+    tr = PortTrainer(seed=seed, update_freq=UPDATE_FREQ)
+    return tr.step
+
+
+def _worker_main(conn, kind, seed, core):
+    if core is not None:
+        try:
+            os.sched_setaffinity(0, {core})
+        except Exception:
+            pass
+    step = _make_stepper(kind, seed, 1)
+    conn.send("ready")
+    while True:
+        msg = conn.recv()
+        if msg == "stop":
+            break
+        t0 = time.perf_counter()
+        n = step()
+        conn.send((n, time.perf_counter() - t0))
+
+
+class WorkerPool:
+    """P pinned single-thread worker processes, created once; run_step() = one barrier-released iteration each."""
+
+    def __init__(self, kind: str, cores: list, seed: int = 0):
+        ctx = mp.get_context("spawn")
+        self.kind, self.cores = kind, list(cores)
+        self.procs, self.conns = [], []
+        for i, c in enumerate(self.cores):
+            a, b = ctx.Pipe()
+            p = ctx.Process(target=_worker_main, args=(b, kind, seed + i, c), daemon=True)
+            p.start()
+            self.procs.append(p); self.conns.append(a)
+        for a in self.conns:
+            assert a.recv() == "ready"
+
+    def run_step(self):
+        for a in self.conns:
+            a.send("go")
+        res = [a.recv() for a in self.conns]
+        steps, slowest = sum(r[0] for r in res), max(r[1] for r in res)
+        return {"env_steps": steps, "seconds": slowest, "value": steps / slowest, "per_worker_s": [round(r[1], 3) for r in res]}
+
+    def close(self):
+        for a in self.conns:
+            try:
+                a.send("stop")
+            except Exception:
+                pass
+        for p in self.procs:
+            p.join(timeout=5)
+            if p.is_alive():
+                p.kill()
+
+
+def pick_kind() -> str:
+    from . import ref_loader
+    return "reference" if ref_loader.available() else "port"
+
+
+def single_process_rows(kind: str, seed: int = 0) -> dict:
+    """Rows (a) and (b) of BASELINE.md §3: one process, 1 thread / torch's default thread count; one iteration each."""
+    import torch
+    default_threads = torch.get_num_threads()
+    out = {}
+    for name, th in (("1proc_1thread", 1), (f"1proc_default_threads({default_threads})", default_threads)):
+        step = _make_stepper(kind, seed, th)
+        t0 = time.perf_counter()
+        n = step()
+        out[name] = round(n / (time.perf_counter() - t0), 1)
+    torch.set_num_threads(default_threads)
+    return out
+
+
+def sample_text(kind: str, P: int) -> str:
+    what = ("the unmodified reference algorithms/ppo_lunarlander.py (collect_rollout + update) on oracle/gymnasium_shim" if kind == "reference"
+            else "oracle/ref_port.py (hand port of the reference's collect_rollout + update; /root/reference is absent on this box)")
+    return (f"{P} pinned single-thread worker processes, each one PPO iteration of {what}: 2048 single-env LunarLander steps + "
+            f"10 epochs x 32 minibatches of 64; env = oracle/lunar_lander.c (our restatement, not gymnasium/Box2D)")

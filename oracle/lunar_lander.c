@@ -1070,6 +1070,20 @@ void ll_step(LLEnv* e, int action, float* obs, float* next_obs, float* reward, u
     else st_to_obs(st, obs);
 }
 
+/* gymnasium single-env semantics (oracle/gymnasium_shim): env.step() under TimeLimit(1000) WITHOUT auto-reset —
+ * the caller calls ll_reset() itself after a done, exactly like the reference scripts do (ppo_lunarlander.py:220-223). */
+void ll_step_single(LLEnv* e, int action, float* obs, float* reward, uint8_t* terminated, uint8_t* truncated) {
+    double st[8];
+    int term;
+    double r = ll_env_step(e, action, st, &term);
+    e->elapsed += 1;
+    e->ep_return += r;
+    st_to_obs(st, obs);
+    *reward = (float)r;
+    *terminated = (uint8_t)term;
+    *truncated = (uint8_t)(e->elapsed >= MAX_EPISODE_STEPS);
+}
+
 void ll_get_state(const LLEnv* e, double* s) {
     int k = 0;
     for (int i = 0; i < CHUNKS; ++i) s[k++] = e->terrain_y[i];

@@ -19,36 +19,41 @@ import time
 import numpy as np
 
 
-def _worker(args):
-    seed, n_rollouts, update_freq = args
-    import torch
-    import torch.nn as nn
-    from torch.distributions import Categorical
+class PortTrainer:
+    """One single-env PPO learner of the reference's shape; step() = collect_rollout + update (one iteration)."""
 
-    from .lunar import LunarLanderVec
-    torch.set_num_threads(1)
-    torch.manual_seed(seed)
-    np.random.seed(seed)
+    def __init__(self, seed: int = 0, update_freq: int = 2048):
+        import torch
+        import torch.nn as nn
 
-    def lin(i, o, std=np.sqrt(2)):
-        l = nn.Linear(i, o)
-        nn.init.orthogonal_(l.weight, gain=std)
-        nn.init.constant_(l.bias, 0)
-        return l
+        from .lunar import LunarLanderVec
+        torch.set_num_threads(1)
+        torch.manual_seed(seed)
+        np.random.seed(seed)
 
-    shared = nn.Sequential(lin(8, 256), nn.Tanh(), lin(256, 256), nn.Tanh())
-    actor = nn.Sequential(lin(256, 256), nn.Tanh(), lin(256, 4, 0.01))
-    critic = nn.Sequential(lin(256, 256), nn.Tanh(), lin(256, 1, 1.0))
-    params = list(shared.parameters()) + list(actor.parameters()) + list(critic.parameters())
-    opt = torch.optim.Adam(params, lr=3e-4, eps=1e-5)
-    env = LunarLanderVec(1, seed=seed, first_env_id=seed)
-    gamma, lam, clip, dual, ent_c, vf_c = 0.99, 0.95, 0.2, 3.0, 0.01, 0.5
-    steps = 0
-    t0 = time.perf_counter()
-    for _ in range(n_rollouts):
+        def lin(i, o, std=np.sqrt(2)):
+            l = nn.Linear(i, o)
+            nn.init.orthogonal_(l.weight, gain=std)
+            nn.init.constant_(l.bias, 0)
+            return l
+
+        self.shared = nn.Sequential(lin(8, 256), nn.Tanh(), lin(256, 256), nn.Tanh())
+        self.actor = nn.Sequential(lin(256, 256), nn.Tanh(), lin(256, 4, 0.01))
+        self.critic = nn.Sequential(lin(256, 256), nn.Tanh(), lin(256, 1, 1.0))
+        self.params = list(self.shared.parameters()) + list(self.actor.parameters()) + list(self.critic.parameters())
+        self.opt = torch.optim.Adam(self.params, lr=3e-4, eps=1e-5)
+        self.env = LunarLanderVec(1, seed=seed, first_env_id=seed)
+        self.update_freq = update_freq
+
+    def step(self) -> int:
+        import torch
+        import torch.nn as nn
+        from torch.distributions import Categorical
+        shared, actor, critic, opt, env, params = self.shared, self.actor, self.critic, self.opt, self.env, self.params
+        gamma, lam, clip, dual, ent_c, vf_c = 0.99, 0.95, 0.2, 3.0, 0.01, 0.5
         S, Aa, LP, V, R, D = [], [], [], [], [], []
         state = env.reset()[0]
-        for _ in range(update_freq):
+        for _ in range(self.update_freq):
             st = torch.tensor(state, dtype=torch.float32).unsqueeze(0)
             with torch.no_grad():
                 f = shared(st)
@@ -58,7 +63,6 @@ def _worker(args):
             obs, _, r, te, tr = env.step(np.array([a.item()], dtype=np.int32))
             S.append(state); Aa.append(a.item()); LP.append(lp); V.append(v); R.append(float(r[0])); D.append(bool(te[0] or tr[0]))
             state = obs[0]
-            steps += 1
         with torch.no_grad():
             nv = critic(shared(torch.tensor(state, dtype=torch.float32).unsqueeze(0))).squeeze().item()
         rew, done, vals = np.array(R), np.array(D, dtype=np.float32), np.array(V + [nv])
@@ -90,8 +94,17 @@ def _worker(args):
                 nn.utils.clip_grad_norm_(params, 0.5)
                 opt.step()
                 _ = (pl.item(), loss.item())  # the reference syncs 5 scalars per minibatch (:309-322)
-    dt = time.perf_counter() - t0
-    return steps, dt
+        return self.update_freq
+
+
+def _worker(args):
+    seed, n_rollouts, update_freq = args
+    tr = PortTrainer(seed, update_freq)
+    steps = 0
+    t0 = time.perf_counter()
+    for _ in range(n_rollouts):
+        steps += tr.step()
+    return steps, time.perf_counter() - t0
 
 
 def run_ppo_port(n_rollouts: int = 1, update_freq: int = 2048, processes: int | None = None, seed: int = 0):
