@@ -92,27 +92,43 @@ def measured_peaks():
 
 
 # ----------------------------------------------------------------------------------------------- reference arm
+def _cpu_arm_rows(n_steps: int, warmup: int, with_single_rows: bool):
+    """The reference's CPU implementation of the path on this box's host cores (oracle/cpu_arm.py): the unmodified reference
+    file on oracle/gymnasium_shim where /root/reference exists (kind "reference"), its hand port elsewhere (kind "port").
+    P pinned single-thread workers created once; every step = one PPO iteration (2048 env steps + full update) per worker."""
+    from oracle import cpu_arm
+    kind = cpu_arm.pick_kind()
+    host = cpu_arm.host_info()
+    cores = host["worker_cores"]
+    pool = cpu_arm.WorkerPool(kind, cores)
+    try:
+        rounds = [pool.run_step() for _ in range(warmup + n_steps)]
+    finally:
+        pool.close()
+    timed = rounds[warmup:]
+    value = sum(r["env_steps"] for r in timed) / sum(r["seconds"] for r in timed)
+    rows = {f"{len(cores)}proc_pinned_1thread_each": round(value, 1)}
+    if with_single_rows:
+        rows.update(cpu_arm.single_process_rows(kind))
+    return {"value": value, "unit": "env-steps/s", "cores": len(cores), "kind": kind, "sample": cpu_arm.sample_text(kind, len(cores)),
+            "rows": rows, "per_core": round(value / len(cores), 1),
+            "host": {k: host[k] for k in ("nproc", "os_cpu_count", "physical_cores_in_mask", "cgroup_quota_cores", "model")},
+            "per_step_values": [round(r["value"], 1) for r in timed]}, timed
+
+
 def run_reference(args, rank, world):
-    """The reference's CPU implementation of the path on this box's host cores (oracle port, see oracle/ref_port.py)."""
     if rank != 0:
         return
-    from oracle.ref_port import run_ppo_port
-    cores = os.cpu_count() or 1
-    procs = max(1, cores // 2)   # physical cores: SMT siblings slow these tiny-MLP workers down (measured 16.6k vs 12.4k steps/s)
-    vals = []
     t0 = time.perf_counter()
-    for _ in range(args.warmup + args.steps):
-        r = run_ppo_port(n_rollouts=1, update_freq=2048, processes=procs)
-        vals.append(r)
-    timed = vals[args.warmup:]
-    v = sum(x["value"] for x in timed) / len(timed)
-    ms = 1000.0 * sum(2048 * procs / x["value"] for x in timed) / len(timed)
+    cpu, timed = _cpu_arm_rows(args.steps, args.warmup, with_single_rows=True)
+    v = cpu["value"]
+    ms = 1000.0 * sum(r["seconds"] for r in timed) / len(timed)
     out = {"metric": "env_steps_per_sec", "value": v, "unit": "env-steps/s", "n_gpus": args.gpus, "steps": args.steps,
            "warmup": args.warmup, "ms_per_step": ms, "higher_is_better": True, "scaling": "weak", "vs_baseline": None,
            "dtype": "f32", "data": "synthetic", "impl": "reference",
-           "config": {"workload": WORKLOAD, "note": "reference path is single-env: each step = every host core runs one 2048-step "
+           "config": {"workload": WORKLOAD, "note": "reference path is single-env: each step = every pinned worker runs one 2048-step "
                       "rollout + full update (10 epochs x 32 minibatches of 64), the reference's own sizes"},
-           "cpu_baseline": {"value": v, "unit": "env-steps/s", "cores": procs, "kind": "port", "sample": timed[0]["sample"]},
+           "cpu_baseline": cpu,
            "e2e": {"value": v, "unit": "env-steps/s", "h2d_bytes_per_step": 0, "d2h_bytes_per_step": 0},
            "gpu_launches": 0, "wall_s": time.perf_counter() - t0}
     print(json.dumps(out), flush=True)
@@ -237,10 +253,7 @@ def run_ours(args, rank, world, local_rank):
                         "note": "the path is compute/latency bound (12.4 MFLOP per env-step), not HBM bound"}
     cpu = None
     if world == 1:
-        from oracle.ref_port import run_ppo_port   # bench's cpu_baseline leg: the oracle is the thing timed here
-        cores = os.cpu_count() or 1
-        r = run_ppo_port(n_rollouts=1, update_freq=2048, processes=max(1, cores // 2))
-        cpu = {"value": r["value"], "unit": "env-steps/s", "cores": r["cores"], "kind": "port", "sample": r["sample"]}
+        cpu, _ = _cpu_arm_rows(2, 1, with_single_rows=False)   # bench's cpu_baseline leg: the oracle is the thing timed here
     out = {"metric": "env_steps_per_sec", "value": value, "unit": "env-steps/s", "n_gpus": world, "steps": args.steps,
            "warmup": args.warmup, "ms_per_step": dev_ms / args.steps, "higher_is_better": True, "scaling": "weak",
            "vs_baseline": None, "dtype": "f32", "data": "synthetic",

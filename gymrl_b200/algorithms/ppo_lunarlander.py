@@ -530,6 +530,16 @@ class PPOTrainer:
             self.episode_rewards.extend([mean_ret] * int(min(total, 100)))
         return mean_ret, total
 
+    def _global_episode_stats(self, avg_reward, total):
+        """The stop criterion must be the same on every rank (a rank that broke out alone would leave the others blocked in the
+        next gradient all-reduce, possibly inside a captured graph): average the ranks' last-100 windows, weighted by how many
+        episodes each window holds, and sum the episode counts.  Identity on one GPU."""
+        if self.world == 1:
+            return avg_reward, total
+        k = float(min(total, 100))
+        s, k_all, tot = gdist.allreduce_scalars([avg_reward * k, k, float(total)], self.device)
+        return (s / k_all if k_all > 0 else 0.0), int(tot)
+
     def train_iteration(self):
         """One pass of the public training loop body (ref train() :336-346): LR anneal (one 8-byte H2D when the
         value changes), rollout, update, metrics + episode statistics read back to the host."""
@@ -550,6 +560,7 @@ class PPOTrainer:
             metrics = self.update(None)
             update_count += 1
             avg_reward, total = self._refresh_episode_rewards()
+            avg_reward, total = self._global_episode_stats(avg_reward, total)
             if total > 0 and self.rank == 0:
                 sps = self.step_count / max(time.time() - t0, 1e-9)
                 print(f"Step: {self.step_count:,} | Updates: {update_count} | Avg Reward: {avg_reward:.1f} | "

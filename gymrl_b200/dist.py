@@ -51,6 +51,20 @@ def global_moments_(sums: torch.Tensor, local_count: int) -> float:
     return float(sums[2].item())
 
 
+def allreduce_scalars(values, device=None):
+    """Sum a short list of host floats over all ranks (float64); identity when not distributed.  Every rank must call it the
+    same number of times — used for decisions that have to be rank-symmetric (e.g. PPOTrainer.train()'s stop criterion: a rank
+    that left the loop alone would leave its peers blocked in the next gradient all-reduce)."""
+    rank, world = info()
+    if world == 1:
+        return [float(v) for v in values]
+    if device is None:
+        device = torch.device("cuda", torch.cuda.current_device()) if dist.get_backend() == "nccl" else torch.device("cpu")
+    t = torch.tensor([float(v) for v in values], dtype=torch.float64, device=device)
+    dist.all_reduce(t, op=dist.ReduceOp.SUM)
+    return t.tolist()
+
+
 def grad_scale() -> float:
     """Gradients are summed across ranks; Adam rescales by 1/world so the step equals the single-GPU step on the
     concatenated minibatch (each rank's loss is a mean over its local minibatch)."""

@@ -156,15 +156,55 @@ class FusedAdam:
         self.sync_lr()
         self.launch(max_norm, clamp, grad_scale)
 
+    # -- checkpoint surface: torch.optim.Adam's own layout, so utils.model.ModelLoader round-trips with reference checkpoints ----
+    def _param_slices(self):
+        """(offset, numel, shape) of every parameter in module.parameters() order — the order torch.optim.Adam numbers them."""
+        by_id = {id(p): n for n, p in self.fp.module.named_parameters()}
+        out = []
+        for p in self.fp.module.parameters():
+            o, shape = self.fp.views[by_id[id(p)]]
+            out.append((o, p.numel(), shape))
+        return out
+
     def state_dict(self):
-        return {"exp_avg": self.exp_avg.clone(), "exp_avg_sq": self.exp_avg_sq.clone(), "step": int(self.step_t.item()),
-                "lr": float(self.param_groups[0]["lr"])}
+        """{state: {i: {step, exp_avg, exp_avg_sq}}, param_groups: [...]} exactly as torch.optim.Adam.state_dict() (ref checkpoints
+        hold `optimizer_state_dict` in this format, utils/model.py:337-366).  `lr` is the current (possibly annealed) value, as in torch."""
+        step = float(self.step_t.item())
+        state = {}
+        for i, (o, k, shape) in enumerate(self._param_slices()):
+            state[i] = {"step": torch.tensor(step), "exp_avg": self.exp_avg[o:o + k].view(shape).clone(),
+                        "exp_avg_sq": self.exp_avg_sq[o:o + k].view(shape).clone()}
+        if step == 0:
+            state = {}   # torch creates per-parameter state lazily at the first step
+        g = {"lr": float(self.param_groups[0]["lr"]), "betas": tuple(self.betas), "eps": self.eps, "weight_decay": 0, "amsgrad": False,
+             "maximize": False, "foreach": None, "capturable": False, "differentiable": False, "fused": None,
+             "decoupled_weight_decay": False, "params": list(range(len(self._param_slices())))}
+        return {"state": state, "param_groups": [g]}
 
     def load_state_dict(self, sd):
-        self.exp_avg.copy_(sd["exp_avg"])
-        self.exp_avg_sq.copy_(sd["exp_avg_sq"])
-        self.step_t.fill_(int(sd["step"]))
-        self.param_groups[0]["lr"] = float(sd["lr"])
+        """Accepts torch.optim.Adam's layout (reference checkpoints) and this class's round-1 private layout."""
+        if "param_groups" in sd:
+            slices = self._param_slices()
+            g = sd["param_groups"][0]
+            assert len(g["params"]) == len(slices), "optimizer state does not match this network's parameter list"
+            self.exp_avg.zero_(); self.exp_avg_sq.zero_()
+            step = 0
+            for j, pid in enumerate(g["params"]):
+                st = sd["state"].get(pid)
+                if st is None:
+                    continue
+                o, k, shape = slices[j]
+                self.exp_avg[o:o + k].copy_(st["exp_avg"].reshape(-1).to(self.exp_avg.device, torch.float32))
+                self.exp_avg_sq[o:o + k].copy_(st["exp_avg_sq"].reshape(-1).to(self.exp_avg.device, torch.float32))
+                step = max(step, int(float(st["step"])))
+            self.step_t.fill_(step)
+            self.param_groups[0]["lr"] = float(g["lr"])
+            # betas / eps stay the constructor's: they are baked into captured graphs and equal the script's own values
+        else:
+            self.exp_avg.copy_(sd["exp_avg"])
+            self.exp_avg_sq.copy_(sd["exp_avg_sq"])
+            self.step_t.fill_(int(sd["step"]))
+            self.param_groups[0]["lr"] = float(sd["lr"])
         self.sync_lr()
 
 

@@ -127,17 +127,23 @@ class ModelLoader:
         os.makedirs(os.path.dirname(cfg.save_path), exist_ok=True)
 
     def save_model(self):
+        from . import install, normalization as _nz
+        install()   # the normalisers pickle as `utils.normalization.*` (the reference's class paths)
         state = {}
         for key, value in self.__dict__.items():
             if key in self._SKIP:
                 continue
-            if hasattr(value, 'state_dict'):
+            if isinstance(value, (_nz.Normalization, _nz.RewardScaling, _nz.RunningMeanStd)):
+                state[key] = value      # a pickled plain attribute, like the reference (its classes have no state_dict)
+            elif hasattr(value, 'state_dict'):
                 state[f'{key}_state_dict'] = value.state_dict()
             else:
                 state[key] = value
         torch.save(state, self.cfg.save_path)
 
     def load_model(self):
+        from . import install
+        install()   # a reference-written checkpoint names `utils.normalization.Normalization`: resolve it to the device class
         checkpoint = torch.load(self.cfg.save_path, map_location=self.cfg.device, weights_only=False)
         for key, value in checkpoint.items():
             if key in self._SKIP:

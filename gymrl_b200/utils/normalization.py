@@ -54,6 +54,21 @@ class RunningMeanStd:
     def load_state_dict(self, sd):
         self.state.copy_(sd["state"])
 
+    # Pickled in the REFERENCE's shape (plain n / mean / S / std NumPy fields, ref :6-10): the reference's ModelLoader stores
+    # `state_norm` / `reward_scaler` as pickled attributes (utils/model.py:343-345), so a checkpoint written here unpickles
+    # into the reference's own classes and one written by the reference unpickles into these.
+    def __getstate__(self):
+        n = self.n
+        return {"n": n, "mean": self.mean, "S": self.S, "std": self.std}
+
+    def __setstate__(self, st):
+        _ffi.require_cuda()
+        mean = np.asarray(st["mean"], dtype=np.float64).reshape(-1)
+        self.shape, self.D = (mean.shape[0] if mean.shape[0] != 1 else 1), mean.shape[0]
+        self.device = torch.device("cuda", torch.cuda.current_device())
+        flat = np.concatenate([[float(st["n"])], mean, np.asarray(st["S"], np.float64).reshape(-1), np.asarray(st["std"], np.float64).reshape(-1)])
+        self.state = torch.as_tensor(flat, dtype=f64).to(self.device)
+
 
 class Normalization:
     def __init__(self, shape, device=None):
@@ -106,6 +121,20 @@ class RewardScaling:
 
     def state_dict(self): return {"state": self.running_ms.state.clone(), "R": self.R.clone()}
 
+    def __getstate__(self):     # the reference's fields (ref :39-43): shape, gamma, running_ms, R (NumPy)
+        return {"shape": self.shape, "gamma": self.gamma, "running_ms": self.running_ms, "R": self.R.cpu().numpy().astype(np.float64)}
+
+    def __setstate__(self, st):
+        self.shape, self.gamma, self.running_ms = st["shape"], st["gamma"], st["running_ms"]
+        self.device = self.running_ms.device
+        self.R = torch.as_tensor(np.asarray(st["R"], np.float64).reshape(-1), dtype=f64).to(self.device)
+        self._reset = torch.zeros(self.R.numel(), device=self.device, dtype=u8)
+
     def load_state_dict(self, sd):
         self.running_ms.state.copy_(sd["state"])
         self.R = sd["R"].clone().to(self.device)
+
+
+# pickle.dump stores classes by (module, qualname): under gymrl_b200.utils.install() these ARE `utils.normalization.*`
+for _c in (RunningMeanStd, Normalization, RewardScaling):
+    _c.__module__ = "utils.normalization"

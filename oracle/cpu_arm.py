@@ -72,7 +72,7 @@ def host_info() -> dict:
 
 
 # ----------------------------------------------------------------------------------------------- workers
-def _make_stepper(kind: str, seed: int, threads: int | None):
+def _make_stepper(kind: str, seed: int, threads: int | None, update_freq: int = UPDATE_FREQ):
     import random
 
     import numpy as np
@@ -91,6 +91,7 @@ def _make_stepper(kind: str, seed: int, threads: int | None):
         mod = ref_loader.load("algorithms/ppo_lunarlander.py", name=f"ref_cpu_arm_{seed}")
         cfg = mod.Config()
         cfg.device = "cpu"
+        cfg.update_freq = update_freq      # the update's cost per collected step does not depend on it (epochs x update_freq/64 minibatches)
         with contextlib.redirect_stdout(io.StringIO()):
             tr = mod.PPOTrainer(cfg)
 
@@ -100,7 +101,7 @@ def _make_stepper(kind: str, seed: int, threads: int | None):
             return cfg.update_freq
         return step
     from .ref_port import PortTrainer
-    tr = PortTrainer(seed=seed, update_freq=UPDATE_FREQ)
+    tr = PortTrainer(seed=seed, update_freq=update_freq)
     return tr.step
 
 
@@ -161,12 +162,14 @@ def pick_kind() -> str:
 
 
 def single_process_rows(kind: str, seed: int = 0) -> dict:
-    """Rows (a) and (b) of BASELINE.md §3: one process, 1 thread / torch's default thread count; one iteration each."""
+    """Rows (a) and (b) of BASELINE.md §3: one process, 1 thread / torch's default thread count; one iteration each of a
+    256-step rollout + its update (same work per env step as the 2048-step iteration, 8x shorter: the default-threads row is
+    slow — intra-op threading hurts these tiny MLPs)."""
     import torch
     default_threads = torch.get_num_threads()
     out = {}
     for name, th in (("1proc_1thread", 1), (f"1proc_default_threads({default_threads})", default_threads)):
-        step = _make_stepper(kind, seed, th)
+        step = _make_stepper(kind, seed, th, update_freq=256)
         t0 = time.perf_counter()
         n = step()
         out[name] = round(n / (time.perf_counter() - t0), 1)

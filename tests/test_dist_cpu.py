@@ -49,7 +49,11 @@ def _worker(rank, world, port, out):
     chk = torch.cat([p.detach().reshape(-1) for p in m.parameters()])
     gathered = [torch.zeros_like(chk) for _ in range(world)]
     dist.all_gather(gathered, chk)
-    out[rank] = dict(first=first, n=n, grad_err=float((g - w2.grad).abs().max()), count=count,
+    # (4) rank-symmetric stop decision: rank 0 alone is "solved"; the pooled last-100 average decides for both
+    avg_r, total_r = (250.0, 120) if rank == 0 else (100.0, 40)
+    k = float(min(total_r, 100))
+    s_, k_all, tot = gd.allreduce_scalars([avg_r * k, k, float(total_r)])
+    out[rank] = dict(pooled_avg=s_ / k_all, pooled_total=int(tot), first=first, n=n, grad_err=float((g - w2.grad).abs().max()), count=count,
                      mean_err=abs(mean - adv_all.mean()), std_err=abs(std - adv_all.std()),
                      replicas_equal=bool(torch.equal(gathered[0], gathered[1])))
     dist.destroy_process_group()
@@ -67,3 +71,4 @@ def test_two_rank_host_logic_gloo():
         assert out[r]["count"] == 2000.0
         assert out[r]["mean_err"] < 1e-12 and out[r]["std_err"] < 1e-12
         assert out[r]["replicas_equal"]
+        assert out[r]["pooled_total"] == 160 and abs(out[r]["pooled_avg"] - (250.0 * 100 + 100.0 * 40) / 140) < 1e-12

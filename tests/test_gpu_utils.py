@@ -177,7 +177,115 @@ def test_runner_train_loop_drives_an_agent(tmp_path, monkeypatch):
     assert ag.cfg.on_policy is True and ag.cfg.use_rnn is False and ag.cfg.n_states == 4 and ag.cfg.n_actions == 2
     assert len(ag.updates) >= 1 and ag.state_norm.running_ms.n > 32
     ckpt = torch.load(ag.cfg.save_path, weights_only=False)
-    assert "net_state_dict" in ckpt and "state_norm_state_dict" in ckpt and ckpt["learn_step"] == ag.learn_step
+    # the normalisers are pickled plain attributes like in the reference (utils/model.py:343-345), not *_state_dict entries
+    assert "net_state_dict" in ckpt and "state_norm" in ckpt and "state_norm_state_dict" not in ckpt and ckpt["learn_step"] == ag.learn_step
     ag.learn_step = -1
     ag.load_model()
     assert ag.learn_step == ckpt["learn_step"]
+
+
+# ----------------------------------------------------------------------------------------------- §8f rank 4: checkpoint wire format
+class _CkptCfg:
+    algo_name, env_name = "PPO", "LunarLander-v3"
+    device = "cuda"
+
+
+def _ckpt_agent(tmp_path, monkeypatch, fused_adam):
+    from gymrl_b200.nn import FlatParams, FusedAdam
+    from gymrl_b200.utils.model import MLP, ModelLoader
+    from gymrl_b200.utils.normalization import Normalization, RewardScaling
+    monkeypatch.chdir(tmp_path)
+
+    class Agent(ModelLoader):
+        def __init__(self, cfg):
+            super().__init__(cfg)
+            self.net = MLP([8, 32, 4]).to("cuda")
+            if fused_adam:
+                self.optimizer = FusedAdam(FlatParams(self.net, device=torch.device("cuda")), lr=3e-4, eps=1e-5)
+            else:
+                self.optimizer = torch.optim.Adam(self.net.parameters(), lr=3e-4, eps=1e-5)
+            self.state_norm = Normalization(shape=(8,))
+            self.reward_scaler = RewardScaling(shape=1, gamma=0.99)
+            self.learn_step = 0
+
+    return Agent(_CkptCfg())
+
+
+@pytest.mark.parametrize("fused_adam", [False, True])
+def test_load_checkpoint_written_by_reference_modelloader(tmp_path, monkeypatch, golden, fused_adam):
+    """tests/golden/ref_checkpoint.pth was written by the UNMODIFIED reference ModelLoader.save_model (oracle/make_golden_checkpoint.py):
+    `state_norm` / `reward_scaler` are pickled reference objects, `optimizer_state_dict` is torch.optim.Adam's layout."""
+    import shutil
+    from pathlib import Path
+    ag = _ckpt_agent(tmp_path, monkeypatch, fused_adam)
+    g = golden("ref_checkpoint_expect.npz")
+    shutil.copy(Path(__file__).parent / "golden" / "ref_checkpoint.pth", ag.cfg.save_path)
+    ag.load_model()
+    assert ag.learn_step == int(g["learn_step"])
+    for k, v in ag.net.state_dict().items():
+        np.testing.assert_array_equal(v.cpu().numpy(), g["w_" + k.replace(".", "_")])
+    np.testing.assert_allclose(ag.net(torch.as_tensor(g["x4"], device="cuda")).detach().cpu().numpy(), g["net_out"], rtol=1e-5, atol=1e-6)
+    # the pickled reference normalisers became device objects with the same statistic, and keep working
+    rm = ag.state_norm.running_ms
+    assert rm.n == int(g["norm_n"])
+    np.testing.assert_array_equal(rm.mean.astype(np.float64), g["norm_mean"])
+    np.testing.assert_allclose(rm.std, g["norm_std"], rtol=1e-15)
+    np.testing.assert_allclose(rm.S, g["norm_S"], rtol=1e-15)
+    np.testing.assert_array_equal(ag.state_norm(g["probe"], update=False), g["probe_normalized"].astype(np.float32))
+    assert ag.reward_scaler.running_ms.n == int(g["rs_n"]) and ag.reward_scaler.gamma == 0.99
+    np.testing.assert_allclose(ag.reward_scaler.R.cpu().numpy(), g["rs_R"].reshape(-1), rtol=1e-15)
+    np.testing.assert_allclose(ag.reward_scaler.running_ms.std, g["rs_std"].reshape(-1), rtol=1e-15)
+    # optimizer state in torch's layout, for torch.optim.Adam and for the flat FusedAdam alike
+    sd = ag.optimizer.state_dict()
+    assert float(sd["state"][0]["step"]) == float(g["adam_step"])
+    np.testing.assert_array_equal(sd["state"][0]["exp_avg"].cpu().numpy(), g["adam_exp_avg0"])
+
+
+def test_checkpoint_written_here_unpickles_as_reference_objects(tmp_path, monkeypatch):
+    """The other direction: a checkpoint saved by gymrl_b200's ModelLoader names only the classes the reference's own file does,
+    and — unpickled WITHOUT this package's classes (stand-ins with no __setstate__, like the reference's) — yields the reference's
+    field layout: state_norm.running_ms.{n, mean, S, std} NumPy arrays, reward_scaler.{shape, gamma, running_ms, R}."""
+    import pickle
+    import zipfile
+    ag = _ckpt_agent(tmp_path, monkeypatch, True)
+    rng = np.random.default_rng(1)
+    for _ in range(17):
+        ag.state_norm(rng.standard_normal(8).astype(np.float32))
+        ag.reward_scaler(float(rng.standard_normal()))
+    ag.learn_step = 9
+    ag.save_model()
+    z = zipfile.ZipFile(ag.cfg.save_path)
+    raw = z.read([n for n in z.namelist() if n.endswith("data.pkl")][0])
+    assert b"gymrl_b200" not in raw                       # no class path of this package inside the file
+
+    class RunningMeanStd: pass
+    class Normalization: pass
+    class RewardScaling: pass
+    standins = {"RunningMeanStd": RunningMeanStd, "Normalization": Normalization, "RewardScaling": RewardScaling}
+
+    class RefSideUnpickler(pickle.Unpickler):
+        def find_class(self, module, name):
+            if module == "utils.normalization":
+                return standins[name]
+            assert module.split(".")[0] in ("torch", "collections", "numpy", "_codecs"), f"unexpected global {module}.{name}"
+            return super().find_class(module, name)
+
+    class _P:   # torch.load's pickle_module protocol
+        Unpickler = RefSideUnpickler
+        load = staticmethod(pickle.load)
+        __name__ = "pickle"
+
+    ck = torch.load(ag.cfg.save_path, map_location="cpu", weights_only=False, pickle_module=_P)
+    assert set(ck) == {"net_state_dict", "optimizer_state_dict", "state_norm", "reward_scaler", "learn_step"}
+    rm = ck["state_norm"].running_ms
+    assert isinstance(ck["state_norm"], Normalization) and isinstance(rm, RunningMeanStd)
+    assert rm.n == 17 and rm.mean.shape == (8,) and rm.mean.dtype == np.float32 and rm.S.dtype == np.float64 and rm.std.shape == (8,)
+    np.testing.assert_array_equal(rm.mean, ag.state_norm.running_ms.mean)
+    rs = ck["reward_scaler"]
+    assert rs.gamma == 0.99 and rs.shape == 1 and rs.running_ms.n == 17 and isinstance(rs.R, np.ndarray)
+    assert set(ck["optimizer_state_dict"]) == {"state", "param_groups"} and ck["learn_step"] == 9
+    # and torch.optim.Adam (what the reference agent holds) accepts the optimizer entry
+    from gymrl_b200.utils.model import MLP
+    ref_net = MLP([8, 32, 4])
+    ref_net.load_state_dict(ck["net_state_dict"])
+    torch.optim.Adam(ref_net.parameters(), lr=1e-3).load_state_dict(ck["optimizer_state_dict"])

@@ -105,3 +105,31 @@ def test_lockstep_graph_mixin_phases_and_host_mirrors(monkeypatch):
     for _ in range(5):
         e.lockstep()
     assert not getattr(e, "_g_lockstep", None) and e.act_count == 5
+
+
+def test_fused_adam_state_dict_is_torch_adam_layout():
+    """FusedAdam.state_dict / load_state_dict speak torch.optim.Adam's {state, param_groups} layout, so
+    utils.model.ModelLoader round-trips `optimizer_state_dict` with reference checkpoints (ref utils/model.py:337-366)."""
+    import torch
+    import torch.nn as nn
+    from gymrl_b200.nn import FlatParams, FusedAdam
+    torch.manual_seed(0)
+    mk = lambda: nn.Sequential(nn.Linear(4, 8), nn.Tanh(), nn.Linear(8, 2))
+    ours, ref = mk(), mk()
+    ref.load_state_dict(ours.state_dict())
+    opt = torch.optim.Adam(ref.parameters(), lr=1e-3, eps=1e-5)
+    for _ in range(3):
+        opt.zero_grad(); ref(torch.randn(5, 4)).sum().backward(); opt.step()
+    fa = FusedAdam(FlatParams(ours, ["2.weight", "0.bias", "0.weight", "2.bias"], device="cpu"), lr=1e-3, eps=1e-5)  # flat order != parameter order
+    assert fa.state_dict()["state"] == {}                      # lazily created, like torch
+    fa.load_state_dict(opt.state_dict())
+    sd, rd = fa.state_dict(), opt.state_dict()
+    assert sd["state"].keys() == rd["state"].keys() and set(sd["param_groups"][0]) == set(rd["param_groups"][0])
+    for i in rd["state"]:
+        assert torch.equal(sd["state"][i]["exp_avg"], rd["state"][i]["exp_avg"])
+        assert torch.equal(sd["state"][i]["exp_avg_sq"], rd["state"][i]["exp_avg_sq"])
+        assert float(sd["state"][i]["step"]) == float(rd["state"][i]["step"]) == 3.0
+    torch.optim.Adam(ref.parameters(), lr=5e-4, eps=1e-5).load_state_dict(sd)       # and torch accepts ours
+    legacy = {"exp_avg": fa.exp_avg.clone(), "exp_avg_sq": fa.exp_avg_sq.clone(), "step": 7, "lr": 1e-4}    # round-1 private layout
+    fa.load_state_dict(legacy)
+    assert int(fa.step_t.item()) == 7 and fa.param_groups[0]["lr"] == 1e-4
