@@ -259,7 +259,7 @@ def run_ours(args, rank, world, local_rank):
            "vs_baseline": None, "dtype": "f32", "data": "synthetic",
            "config": {"workload": WORKLOAD, "envs_per_gpu": N_ENVS, "rollout_steps": T_STEPS, "epochs": N_EPOCHS,
                       "minibatches_per_epoch": N_MB, "minibatch": N_ENVS * T_STEPS // N_MB, "params": 200965,
-                      "parallelism": f"dp{world} (env shards, 1 grad all-reduce / optimizer step)",
+                      "parallelism": f"dp{world} (env shards, 1 gradient sum / optimizer step: " + ("one-shot NVLink peer-memory reduction fused with the clip norm, csrc/comm.cu)" if getattr(tr, "comm", None) is not None else ("ncclAllReduce)" if world > 1 else "none on 1 GPU)")),
                       "l2": "flushed (256 MB write) before every timed step", "cuda_graphs": True},
            "e2e": {"value": e2e_val, "unit": "env-steps/s", "h2d_bytes_per_step": h2d, "d2h_bytes_per_step": d2h,
                    "note": "PPOTrainer.train_iteration(): observations never exist on the host in this design; the per-step "

@@ -67,7 +67,8 @@ class Config:
         self.num_minibatches = None
         self.reset_each_rollout = None
         self.use_cuda_graph = True
-        self.dist_epoch_graph = True   # multi-GPU: capture the per-minibatch NCCL all-reduce inside the epoch graph
+        self.dist_epoch_graph = True   # multi-GPU: capture the per-minibatch gradient reduction inside the epoch graph
+        self.peer_reduce = True        # multi-GPU: one-shot NVLink peer-memory reduction (csrc/comm.cu) instead of ncclAllReduce
         self.fused_heads = True   # heads + loss + heads backward as one kernel where the shape allows (H in {128,256}, 4 actions)
 
 
@@ -253,6 +254,10 @@ class PPOTrainer:
         gdist.broadcast_module_(self.model, self.device)   # identical replicas: rank 0's initialisation everywhere
         self.net = self.model.to_engine(self.device)
         self.optimizer = FusedAdam(self.net.fp, lr=cfg.lr, eps=1e-5)
+        # multi-GPU: the gradient sum is a one-shot NVLink peer-memory reduction fused with the clip's sum of squares
+        # (csrc/comm.cu); None on one GPU, with GYMRL_COMM=nccl, or when peer mappings are unavailable (then ncclAllReduce)
+        self.comm = gdist.make_peer_reducer(self.net.fp.grad.numel()) if getattr(cfg, "peer_reduce", True) else None
+        self.grad_reduced = torch.zeros_like(self.net.fp.grad) if self.comm is not None else None
         self.buffer = RolloutBuffer(T, N, state_dim, self.device)
         self.acts_roll = self._make_acts(N, backward=False)
         self.acts_mb = self._make_acts(self.mb, backward=True)
@@ -408,13 +413,25 @@ class PPOTrainer:
         for w in range(self.n_mb):
             self._minibatch_body(w)
 
+    def _reduce_opt_body(self):
+        """Multi-GPU: sum the flat gradient over the ranks, then clip + Adam with grad_scale = 1 / world."""
+        cfg = self.cfg
+        if self.comm is not None:
+            n = self.comm.allreduce_sumsq(self.net.fp.grad, self.grad_reduced, self.optimizer.sumsq_partials)
+            if cfg.max_grad_norm > 0:
+                self.optimizer.launch_clipped(n, max_norm=cfg.max_grad_norm, grad_scale=1.0 / self.world, grad=self.grad_reduced)
+            else:
+                self.optimizer.launch(grad_scale=1.0 / self.world, grad=self.grad_reduced)
+        else:
+            gdist.allreduce_sum_(self.net.fp.grad)  # ncclAllReduce (sum; Adam rescales by 1/world)
+            self._opt_body()
+
     def _epoch_body_dist(self):
-        """Multi-GPU epoch: per minibatch backward -> the gradient sum-all-reduce -> clip + Adam, all on one stream so the
-        whole epoch (NCCL kernels included) can be one CUDA graph."""
+        """Multi-GPU epoch: per minibatch backward -> the gradient sum over ranks -> clip + Adam, all on one stream so the
+        whole epoch (the peer-memory reduction kernels, or the NCCL kernels) can be one CUDA graph."""
         for w in range(self.n_mb):
             self._fwd_bwd_body(w)
-            gdist.allreduce_sum_(self.net.fp.grad)
-            self._opt_body()
+            self._reduce_opt_body()
 
     def _capture(self, fn, error_mode: str = "global"):
         torch.cuda.synchronize()
@@ -438,12 +455,12 @@ class PPOTrainer:
     def _snapshot(self):
         return {"flat": self.net.fp.flat.clone(), "m": self.optimizer.exp_avg.clone(), "v": self.optimizer.exp_avg_sq.clone(),
                 "step": self.optimizer.step_t.clone(), "ctr_mb": self.ctr_mb.clone(), "ctr_action": self.ctr_action.clone(),
-                "metrics": self.metrics.clone()}
+                "metrics": self.metrics.clone(), "done_ctr": self.optimizer.done_ctr.clone(), "sumsq": self.optimizer.sumsq.clone()}
 
     def _restore(self, s):
         self.net.fp.flat.copy_(s["flat"]); self.optimizer.exp_avg.copy_(s["m"]); self.optimizer.exp_avg_sq.copy_(s["v"])
         self.optimizer.step_t.copy_(s["step"]); self.ctr_mb.copy_(s["ctr_mb"]); self.ctr_action.copy_(s["ctr_action"])
-        self.metrics.copy_(s["metrics"])
+        self.metrics.copy_(s["metrics"]); self.optimizer.done_ctr.copy_(s["done_ctr"]); self.optimizer.sumsq.copy_(s["sumsq"])
 
     def _ensure_update_graphs(self):
         if not self.cfg.use_cuda_graph or self._g_mb is not None or self._g_mb_bwd is not None or self._g_epoch is not None:
@@ -460,7 +477,7 @@ class PPOTrainer:
             self._g_epoch = self._capture(self._epoch_body_dist, error_mode="thread_local")
         else:
             self._g_mb_bwd = self._capture(self._fwd_bwd_body)
-            self._g_opt = self._capture(self._opt_body)
+            self._g_opt = self._capture(self._opt_body) if self.comm is None else None
         self._restore(snap)
 
     def total_launches(self) -> int:
@@ -491,11 +508,14 @@ class PPOTrainer:
                         self._replay(self._g_mb_bwd)
                     else:
                         self._fwd_bwd_body()
-                    gdist.allreduce_sum_(self.net.fp.grad)  # the one collective of the path (sum; Adam rescales by 1/world)
-                    if self._g_opt is not None:
-                        self._replay(self._g_opt)
+                    if self.comm is not None:
+                        self._reduce_opt_body()                 # the one collective of the path, fused with the clip's norm
                     else:
-                        self._opt_body()
+                        gdist.allreduce_sum_(self.net.fp.grad)  # ncclAllReduce (sum; Adam rescales by 1/world)
+                        if self._g_opt is not None:
+                            self._replay(self._g_opt)
+                        else:
+                            self._opt_body()
 
     def update(self, next_value=None, read_metrics: bool = True) -> dict:
         cfg, buf = self.cfg, self.buffer

@@ -39,6 +39,7 @@ SOURCES = {
     "linear_skinny.cu": [],
     "optim.cu": [],
     "reduce.cu": [],
+    "comm.cu": [],
     "replay.cu": [],
     "qlearn.cu": [],
     "mhc.cu": [],

@@ -137,18 +137,20 @@ class FusedAdam:
         self.fp.grad.zero_()
 
     # -- device side (capture-safe) -------------------------------------------------------------------
-    def launch(self, max_norm: float = 0.0, clamp: float = 0.0, grad_scale: float = 1.0):
-        """Enqueue (optional global-norm) + Adam on the current stream; no host sync, no allocation."""
+    def launch(self, max_norm: float = 0.0, clamp: float = 0.0, grad_scale: float = 1.0, grad=None):
+        """Enqueue (optional global-norm) + Adam on the current stream; no host sync, no allocation.  `grad` = an alternative
+        gradient buffer of the flat layout (the peer-reduced gradient of a multi-GPU step)."""
+        grad = self.fp.grad if grad is None else grad
         if max_norm > 0.0:
-            ops.grad_sumsq(self.fp.grad, out=self.sumsq)
-        ops.adam_step(self.fp.flat, self.fp.grad, self.exp_avg, self.exp_avg_sq, self.lr_t, self.step_t,
+            ops.grad_sumsq(grad, out=self.sumsq)
+        ops.adam_step(self.fp.flat, grad, self.exp_avg, self.exp_avg_sq, self.lr_t, self.step_t,
                       beta1=self.betas[0], beta2=self.betas[1], eps=self.eps,
                       sumsq=self.sumsq if max_norm > 0.0 else None, max_norm=max_norm, clamp=clamp, grad_scale=grad_scale)
 
-    def launch_clipped(self, n_partials: int, max_norm: float, grad_scale: float = 1.0):
+    def launch_clipped(self, n_partials: int, max_norm: float, grad_scale: float = 1.0, grad=None):
         """Clip + Adam in one launch, the norm taken from self.sumsq_partials[:n_partials] (filled by
-        ops.reduce_flush(self.sumsq_partials) over *all* of this optimiser's gradients)."""
-        ops.clip_adam_step(self.fp.flat, self.fp.grad, self.exp_avg, self.exp_avg_sq, self.lr_t, self.step_t,
+        ops.reduce_flush(self.sumsq_partials) over *all* of this optimiser's gradients, or by PeerReducer.allreduce_sumsq)."""
+        ops.clip_adam_step(self.fp.flat, self.fp.grad if grad is None else grad, self.exp_avg, self.exp_avg_sq, self.lr_t, self.step_t,
                            sumsq_partials=self.sumsq_partials, n_partials=n_partials, done_counter=self.done_ctr, max_norm=max_norm,
                            beta1=self.betas[0], beta2=self.betas[1], eps=self.eps, grad_scale=grad_scale)
 

@@ -258,6 +258,25 @@ int gymrl_clip_adam_step(float* d_param, const float* d_grad, float* d_exp_avg, 
                          const double* d_lr, float beta1, float beta2, float eps, int32_t* d_step,
                          const double* d_sumsq_partials, int n_partials, float max_norm, float grad_scale,
                          uint32_t* d_done_counter, void* stream);
+/* ---- the one collective of the path (§8b `gymrl_comm_init / gymrl_allreduce_grads`) -----------------------------
+ * The reference has no collective (single process).  The env-sharded engine sums the flat fp32 gradient over the ranks of
+ * one node before every optimizer step.  gymrl_comm_* does that as a ONE-SHOT reduction over NVLink peer memory (cudaIpc
+ * mappings of a staging buffer this library allocates), fused with the sum of squares that clip_grad_norm_
+ * (algorithms/ppo_lunarlander.py:304-306) needs: every rank reads all W staging buffers and adds them in rank order, so all
+ * ranks hold bit-identical sums; gymrl_clip_adam_step(d_reduced, d_sumsq_partials, gymrl_comm_n_partials(), grad_scale = 1/W)
+ * finishes the step.  Host protocol (one process per GPU): create -> exchange every rank's gymrl_comm_get_handle() blob
+ * (gymrl_comm_handle_bytes() bytes each, rank order) with any host-side all-gather -> gymrl_comm_open -> any number of
+ * gymrl_comm_allreduce_sumsq calls, the same sequence on every rank (asynchronous on `stream`, CUDA-graph capturable: the
+ * launch counter lives in device memory).  A peer that never arrives makes the kernel trap after a bounded spin. */
+typedef struct gymrl_comm gymrl_comm;
+int gymrl_comm_create(gymrl_comm** out, int rank, int world, long long n_floats, int n_blocks /* 0 = default */);
+int gymrl_comm_handle_bytes(void);
+int gymrl_comm_get_handle(gymrl_comm* comm, void* handle_out);
+int gymrl_comm_open(gymrl_comm* comm, const void* handles /* world x handle_bytes, rank order */);
+int gymrl_comm_n_partials(const gymrl_comm* comm);
+int gymrl_comm_allreduce_sumsq(gymrl_comm* comm, const float* d_grad, float* d_reduced, double* d_sumsq_partials, void* stream);
+int gymrl_comm_destroy(gymrl_comm* comm);
+
 /* target = tau * source + (1 - tau) * target   (rainbow_dqn_cartpole.py:347-352,
  * sac_pendulum.py:194-199, td3_pendulum.py:150-155); tau = 1 is the hard copy of dqn_cartpole.py:193. */
 int gymrl_polyak(float* d_target, const float* d_source, long long n, float tau, void* stream);

@@ -16,3 +16,5 @@ def test_two_gpu_sharded_ppo_matches_single_gpu():
            "--master-port", "29533", str(ROOT / "tools" / "multigpu_check.py")]
     r = subprocess.run(cmd, capture_output=True, text=True, timeout=600, cwd=str(ROOT))
     assert "MULTIGPU_CHECK PASS" in r.stdout, r.stdout[-3000:] + r.stderr[-3000:]
+    assert "MULTIGPU_GRAPH_CHECK PASS" in r.stdout, r.stdout[-3000:]
+    assert "MULTIGPU_PEER_CHECK PASS" in r.stdout, r.stdout[-3000:]   # one-shot NVLink peer reduction == ncclAllReduce path

@@ -17,8 +17,9 @@ import torch.distributed as dist
 sys.path.insert(0, str(Path(__file__).resolve().parent.parent))
 
 
-def make_trainer(P, n_envs, graph=False, n_mb=1, epochs=1):
+def make_trainer(P, n_envs, graph=False, n_mb=1, epochs=1, peer_reduce=True):
     cfg = P.Config()
+    cfg.peer_reduce = peer_reduce
     cfg.num_envs, cfg.num_steps, cfg.num_minibatches, cfg.num_epochs, cfg.seed, cfg.use_cuda_graph = n_envs, 16, n_mb, epochs, 11, graph
     torch.manual_seed(0)
     return P.PPOTrainer(cfg)
@@ -38,6 +39,59 @@ def graph_vs_eager(P, N):
             assert tr._g_epoch is not None, "the distributed epoch graph was not captured"
         flats.append(tr.net.fp.flat.clone())
     return (flats[0] - flats[1]).abs().max().item()
+
+
+def peer_vs_nccl(P, N):
+    """The one-shot peer-memory reduction (csrc/comm.cu) against ncclAllReduce: same rollout, 2 epochs x 2 minibatches."""
+    flats, used = [], []
+    for peer in (False, True):
+        tr = make_trainer(P, N, graph=False, n_mb=2, epochs=2, peer_reduce=peer)
+        tr.collect_rollout()
+        tr.update(None)
+        used.append(tr.comm is not None)
+        flats.append(tr.net.fp.flat.clone())
+    return (flats[0] - flats[1]).abs().max().item(), used
+
+
+def reduce_latency(n_floats=200968, iters=300):
+    """Device time of one gradient reduction, NCCL vs peer-memory kernel (+ the norm pass NCCL needs afterwards)."""
+    import gymrl_b200.dist as gd
+    from gymrl_b200 import ops
+    g = torch.randn(n_floats, device="cuda")
+    red = torch.zeros_like(g)
+    part = torch.zeros(4096, device="cuda", dtype=torch.float64)
+    sumsq = torch.zeros(1, device="cuda", dtype=torch.float64)
+    comm = gd.make_peer_reducer(n_floats)
+    out = {}
+    e0, e1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
+    for name in ("nccl_allreduce_plus_sumsq", "peer_reduce_sumsq"):
+        if name.startswith("peer") and comm is None:
+            continue
+        def once():
+            if name.startswith("peer"):
+                comm.allreduce_sumsq(g, red, part)
+            else:
+                dist.all_reduce(g, op=dist.ReduceOp.SUM)
+                ops.grad_sumsq(g, out=sumsq)
+        for _ in range(20):
+            once()
+        dist.barrier(); torch.cuda.synchronize()
+        e0.record()
+        for _ in range(iters):
+            once()
+        e1.record()
+        torch.cuda.synchronize()
+        out[name] = e0.elapsed_time(e1) * 1e3 / iters
+    if comm is not None:
+        # correctness on random data: equals the NCCL sum (world = 2: one addition, order-free) and the partials give its norm
+        a = torch.randn(n_floats, device="cuda")
+        ref = a.clone()
+        dist.all_reduce(ref, op=dist.ReduceOp.SUM)
+        n = comm.allreduce_sumsq(a, red, part)
+        torch.cuda.synchronize()
+        out["max_abs_diff_vs_nccl"] = (red - ref).abs().max().item()
+        out["rel_norm_err"] = abs(part[:n].sum().item() - ref.double().pow(2).sum().item()) / ref.double().pow(2).sum().item()
+    return out
 
 
 def main():
@@ -86,6 +140,14 @@ def main():
         print(f"epoch graph (captured all-reduce) vs eager multi-GPU update: max |param diff| {dgraph:.3e}")
         ok = ok and dgraph < 1e-6
         print("MULTIGPU_GRAPH_CHECK", "PASS" if dgraph < 1e-6 else "FAIL")
+    dpeer, used = peer_vs_nccl(P, N)
+    lat = reduce_latency()
+    if rank == 0:
+        print(f"peer-memory reduction vs ncclAllReduce update: max |param diff| {dpeer:.3e} (peer path active: {used[1]}, nccl run: {not used[0]})")
+        print("reduce latency (us per optimizer step, device events):", {k: round(v, 3) if isinstance(v, float) else v for k, v in lat.items()})
+        okp = dpeer < 1e-6 and (not used[1] or (lat.get("max_abs_diff_vs_nccl", 1.0) <= (0.0 if world == 2 else 1e-5) and lat.get("rel_norm_err", 1.0) < 1e-12))
+        print("MULTIGPU_PEER_CHECK", "PASS" if okp else "FAIL")
+        ok = ok and okp
     dist.barrier()
     dist.destroy_process_group()
     sys.exit(0 if ok else 1)
