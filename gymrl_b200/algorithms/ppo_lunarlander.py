@@ -416,7 +416,9 @@ class PPOTrainer:
     def _reduce_opt_body(self):
         """Multi-GPU: sum the flat gradient over the ranks, then clip + Adam with grad_scale = 1 / world."""
         cfg = self.cfg
-        if self.comm is not None:
+        if getattr(cfg, "_profile_skip_reduce", False):     # developer probe (tools/dist_phase_times.py): ranks diverge
+            self._opt_body()
+        elif self.comm is not None:
             n = self.comm.allreduce_sumsq(self.net.fp.grad, self.grad_reduced, self.optimizer.sumsq_partials)
             if cfg.max_grad_norm > 0:
                 self.optimizer.launch_clipped(n, max_norm=cfg.max_grad_norm, grad_scale=1.0 / self.world, grad=self.grad_reduced)

@@ -35,6 +35,7 @@ struct gymrl_comm {
     uint32_t* done = nullptr;           // device: blocks finished in the current launch
     // device-side table of peer base pointers
     uint8_t** d_peer = nullptr;
+    long long* d_dbg = nullptr;         // developer probe: %globaltimer stamps of block 0 (gymrl_debug_comm_stamps)
 };
 
 struct CommLayout {
@@ -68,8 +69,11 @@ __global__ void __launch_bounds__(COMM_THREADS) peer_reduce_sumsq_kernel(const f
                                                                         float* __restrict__ reduced, double* __restrict__ partials,
                                                                         uint8_t* const* __restrict__ peers, int rank, int world,
                                                                         size_t staging_bytes, size_t flags_off,
-                                                                        uint32_t* __restrict__ epoch_ctr, uint32_t* __restrict__ done_ctr) {
+                                                                        uint32_t* __restrict__ epoch_ctr, uint32_t* __restrict__ done_ctr,
+                                                                        long long* __restrict__ dbg) {
     __shared__ double scratch[32];
+#define COMM_STAMP(k) do { if (dbg && blockIdx.x == 0 && threadIdx.x == 0) { long long _v; asm volatile("mov.u64 %0, %%globaltimer;" : "=l"(_v)); dbg[k] = _v; } } while (0)
+    COMM_STAMP(0);
     const int b = blockIdx.x, nb = gridDim.x, t = threadIdx.x;
     const uint32_t e = *epoch_ctr + 1u;             // every block reads it before the last block of this launch advances it
     const int parity = (int)(e & 1u);
@@ -87,8 +91,10 @@ __global__ void __launch_bounds__(COMM_THREADS) peer_reduce_sumsq_kernel(const f
         }
         my_stage[i] = v;
     }
-    __threadfence_system();
+    // bar.sync orders the block's staging writes before thread t's st.release.sys (release is cumulative over what the
+    // releasing thread has observed), so no per-thread system fence is needed
     __syncthreads();
+    COMM_STAMP(1);
     // 2. raise flag[rank][b] in every rank's table, 3. wait for flag[r][b] of every rank r in the local table
     if (t < world) {
         uint32_t* remote = reinterpret_cast<uint32_t*>(peers[t] + flags_off) + (size_t)rank * nb + b;
@@ -102,6 +108,7 @@ __global__ void __launch_bounds__(COMM_THREADS) peer_reduce_sumsq_kernel(const f
         }
     }
     __syncthreads();
+    COMM_STAMP(2);
     // 4. fixed-order sum over ranks + sum of squares of the reduced slice
     double q = 0.0;
     for (int i = t; i < n4; i += COMM_THREADS) {
@@ -127,6 +134,7 @@ __global__ void __launch_bounds__(COMM_THREADS) peer_reduce_sumsq_kernel(const f
         q += (double)acc.x * acc.x + (double)acc.y * acc.y + (double)acc.z * acc.z + (double)acc.w * acc.w;
     }
     q = block_sum(q, scratch);
+    COMM_STAMP(3);
     if (t == 0) {
         partials[b] = q;
         __threadfence();
@@ -139,7 +147,9 @@ __global__ void __launch_bounds__(COMM_THREADS) peer_reduce_sumsq_kernel(const f
 
 extern "C" int gymrl_comm_create(gymrl_comm** out, int rank, int world, long long n_floats, int n_blocks) {
     GYMRL_REQUIRE(out && world >= 1 && world <= COMM_MAX_WORLD && rank >= 0 && rank < world && n_floats > 0, "bad arguments");
-    if (n_blocks <= 0) n_blocks = 128;
+    if (n_blocks <= 0) n_blocks = (int)((n_floats / 4 + COMM_THREADS - 1) / COMM_THREADS);   // one float4 per thread: every peer load of a slice is in flight at once
+    if (n_blocks < 1) n_blocks = 1;
+    if (n_blocks > 1024) n_blocks = 1024;
     GYMRL_REQUIRE(n_blocks <= 1024, "n_blocks too large");
     gymrl_comm* c = new (std::nothrow) gymrl_comm();
     GYMRL_REQUIRE(c, "out of host memory");
@@ -201,9 +211,16 @@ extern "C" int gymrl_comm_allreduce_sumsq(gymrl_comm* c, const float* d_grad, fl
     const CommLayout L = comm_layout(c->n_pad, c->world, c->n_blocks);
     peer_reduce_sumsq_kernel<<<c->n_blocks, COMM_THREADS, 0, as_stream(stream)>>>(d_grad, c->n, c->n_pad, d_reduced, d_sumsq_partials,
                                                                                  c->d_peer, c->rank, c->world, L.staging_bytes,
-                                                                                 L.flags_off, c->epoch, c->done);
+                                                                                 L.flags_off, c->epoch, c->done, c->d_dbg);
     gymrl_count_launch();
     GYMRL_LAUNCH_CHECK("peer_reduce_sumsq");
+    return GYMRL_OK;
+}
+
+// developer probe (not part of the ABI): d_buf[0..3] = %globaltimer (ns) of block 0 at entry / published / peers arrived / reduced
+extern "C" int gymrl_debug_comm_stamps(gymrl_comm* c, long long* d_buf) {
+    if (!c) return GYMRL_EINVAL;
+    c->d_dbg = d_buf;
     return GYMRL_OK;
 }
 
