@@ -25,10 +25,11 @@ class PPOCfg(C.Structure):
     """struct gymrl_ppo_cfg"""
     _fields_ = [("mode", c_int), ("clip_eps_min", c_float), ("clip_eps_max", c_float), ("dual_clip", c_float),
                 ("value_coef", c_float), ("entropy_coef", c_float), ("erc_low", c_float), ("erc_high", c_float),
-                ("vclip_eps_min", c_float), ("vclip_eps_max", c_float), ("d_entropy_coef", c_void_p)]
+                ("vclip_eps_min", c_float), ("vclip_eps_max", c_float), ("d_entropy_coef", c_void_p),
+                ("d_mask_count", c_void_p)]
 
 
-PPO_DUALCLIP, PPO_FULL, PPO_VALUE_CLIP = 0, 1, 4
+PPO_DUALCLIP, PPO_FULL, PPO_VALUE_CLIP, PPO_MASKED_MEAN = 0, 1, 4, 8
 ACT_NONE, ACT_TANH, ACT_RELU = 0, 1, 2
 ENV_CARTPOLE, ENV_PENDULUM, ENV_LUNARLANDER = 0, 1, 2
 ENV_KINDS = {"CartPole-v1": ENV_CARTPOLE, "Pendulum-v1": ENV_PENDULUM, "LunarLander-v3": ENV_LUNARLANDER}
@@ -96,6 +97,9 @@ SIGNATURES = {
     "gymrl_rmsnorm_forward": (c_int, [_P, c_int, c_int, c_int, _P, _P, c_int, c_int, c_int, c_int, c_float, _P]),
     "gymrl_rmsnorm_backward": (c_int, [_P, c_int, c_int, c_int, _P, _P, c_int, _P, c_int, _P, _P, c_size_t, c_int, c_int, c_int,
                                        c_int, c_float, _P]),
+    "gymrl_seq_gather": (c_int, [_P, c_int, _P, c_int, c_int, c_int, _P, c_int, _P]),
+    "gymrl_gru_cell_forward": (c_int, [_P, c_int, _P, c_int, _P, c_int, _P, c_int, _P, c_int, c_int, _P]),
+    "gymrl_gru_cell_backward": (c_int, [_P, c_int, _P, _P, c_int, _P, c_int, _P, c_int, _P, c_int, _P, c_int, c_int, c_int, c_int, _P]),
     "gymrl_counter_add": (c_int, [_P, c_u32, _P]),
     "gymrl_slice_i32": (c_int, [_P, _P, c_int, _P, _P]),
     "gymrl_replay_sample_indices": (c_int, [_P, c_int, _P, c_u64, c_u32, _P, _P]),

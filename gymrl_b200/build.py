@@ -40,6 +40,7 @@ SOURCES = {
     "optim.cu": [],
     "reduce.cu": [],
     "comm.cu": [],
+    "recurrent.cu": [],
     "replay.cu": [],
     "qlearn.cu": [],
     "mhc.cu": [],

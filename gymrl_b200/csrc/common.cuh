@@ -171,6 +171,42 @@ __device__ __forceinline__ T block_sum(T v, T* scratch) {
     if (wid == 0) v = warp_sum(v);
     return v;
 }
+// Deterministic cross-block accumulation (replaces float / double atomicAdd of per-block sums, whose order — and so the last
+// bits of the result — changed from run to run): every block publishes its K partial sums, the last block to arrive (ticket
+// counter) folds all of them in block order (thread-strided, then the fixed block tree) and adds the totals to out[0..K).
+// `v` must be valid in thread 0.  The scratch is one static buffer per translation unit: launches that use it are serialised
+// by the stream they share (the library drives one stream per process).  Call from ALL threads of every block.
+#define GYMRL_FOLD_MAX_BLOCKS 4096
+static __device__ double g_fold_scratch[GYMRL_FOLD_MAX_BLOCKS * 8];
+static __device__ unsigned int g_fold_ticket = 0;
+template <int K, typename OutT>
+__device__ __forceinline__ void ordered_block_accumulate(const double (&v)[K], OutT* out, double* scratch_smem /* >= 32 doubles */) {
+    static_assert(K <= 8, "at most 8 values per block");
+    __shared__ int s_last;
+    const int nb = gridDim.x;
+    if (nb == 1) {
+        if (threadIdx.x == 0)
+            for (int j = 0; j < K; ++j) out[j] = (OutT)((double)out[j] + v[j]);
+        return;
+    }
+    if (threadIdx.x == 0) {
+        for (int j = 0; j < K; ++j) g_fold_scratch[blockIdx.x * K + j] = v[j];
+        __threadfence();
+        const unsigned int t = atomicAdd(&g_fold_ticket, 1u);
+        s_last = (t == (unsigned int)nb - 1u);
+    }
+    __syncthreads();
+    if (!s_last) return;
+    __threadfence();
+    for (int j = 0; j < K; ++j) {
+        double a = 0.0;
+        for (int b = threadIdx.x; b < nb; b += blockDim.x) a += *((volatile double*)&g_fold_scratch[b * K + j]);
+        a = block_sum(a, scratch_smem);
+        if (threadIdx.x == 0) out[j] = (OutT)((double)out[j] + a);
+    }
+    if (threadIdx.x == 0) g_fold_ticket = 0;
+}
+
 // tanh with fp32-grade accuracy (|rel err| < ~5e-7) in ~10 instructions: odd polynomial near 0, 1 - 2/(e^{2|x|}+1) elsewhere.
 // (libdevice tanhf costs ~40 dependent instructions per element, which made the 4-warp epilogue the bottleneck.)
 __device__ __forceinline__ float exp2f_approx(float x) {

@@ -138,10 +138,8 @@ __global__ void sum_sumsq_kernel(const float* __restrict__ x, long long n, doubl
     }
     s = block_sum(s, scratch);
     q = block_sum(q, scratch);
-    if (threadIdx.x == 0) {
-        atomicAdd(&sums[0], s);
-        atomicAdd(&sums[1], q);
-    }
+    const double v[2] = {s, q};
+    ordered_block_accumulate<2>(v, sums, scratch);     // fixed block order: bitwise reproducible moments
 }
 
 extern "C" int gymrl_sum_sumsq(const float* d_x, long long n, double* d_sums, void* stream) {

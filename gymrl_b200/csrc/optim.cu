@@ -32,7 +32,8 @@ __global__ void grad_sumsq_kernel(const float* __restrict__ g, long long n, doub
             q += (double)g[i] * g[i];
     }
     q = block_sum(q, scratch);
-    if (threadIdx.x == 0) atomicAdd(out, q);
+    const double v[1] = {q};
+    ordered_block_accumulate<1>(v, out, scratch);      // fixed block order: bitwise reproducible norm
 }
 
 extern "C" int gymrl_grad_sumsq(const float* d_grad, long long n, double* d_sumsq, void* stream) {

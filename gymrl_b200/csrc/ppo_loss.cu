@@ -31,7 +31,10 @@ struct PpoSample {
 // One sample of the loss and its gradient wrt (logits, V).  `A` may be a compile-time constant at the call site.
 __device__ __forceinline__ void ppo_sample(const float* z, float V, int a, float lpo, float Adv, float R, float ent_old_r,
                                            float val_old_r, const gymrl_ppo_cfg& cfg, float ent_coef, float invB, int A,
-                                           PpoSample& o) {
+                                           PpoSample& o, float invN = -1.0f) {
+    // invN: normaliser of the masked terms (policy / value / entropy / clip_frac) — 1/B for the plain .mean() of ppo_full
+    // (masked rows count as zeros), 1/mask.sum() for ppo_lstm's masked_mean (GYMRL_PPO_MASKED_MEAN)
+    if (invN < 0.0f) invN = invB;
     // loops run to MAX_A with a guard so that every array index is a compile-time constant (arrays stay in registers)
     float ln[MAX_A], p[MAX_A];
     float mx = z[0];
@@ -103,9 +106,9 @@ __device__ __forceinline__ void ppo_sample(const float* z, float V, int a, float
         if (l2 > vterm) { vterm = l2; dv = d2; }
         else if (l2 == vterm) { dv = 0.5f * (dv + d2); }
     }
-    // gradients: L = -obj*mask/B + vc*mask*vterm/B - ec*mask*H/B
-    const float dL_dlp = -(g * ratio) * mask * invB;
-    const float dL_dH = -ent_coef * mask * invB;
+    // gradients: L = -obj*mask/N + vc*mask*vterm/N - ec*mask*H/N   (N = B, or mask.sum() under masked_mean)
+    const float dL_dlp = -(g * ratio) * mask * invN;
+    const float dL_dH = -ent_coef * mask * invN;
 #pragma unroll
     for (int j = 0; j < MAX_A; ++j)
         if (j < A) {
@@ -113,13 +116,40 @@ __device__ __forceinline__ void ppo_sample(const float* z, float V, int a, float
             const float dH = -p[j] * (ln[j] + H);
             o.dlogits[j] = dL_dlp * dlp + dL_dH * dH;
         }
-    o.dvalue = cfg.value_coef * mask * dv * invB;
-    o.m_pol = -obj * mask * invB;
-    o.m_val = cfg.value_coef * mask * vterm * invB;
-    o.m_ent = H * mask * invB;
-    o.m_clip = ((ratio < lo || ratio > hi) ? 1.0f : 0.0f) * mask * invB;
+    o.dvalue = cfg.value_coef * mask * dv * invN;
+    o.m_pol = -obj * mask * invN;
+    o.m_val = cfg.value_coef * mask * vterm * invN;
+    o.m_ent = H * mask * invN;
+    o.m_clip = ((ratio < lo || ratio > hi) ? 1.0f : 0.0f) * mask * invN;
     o.m_kl = (lpo - lp) * invB;
     o.m_erc = (1.0f - mask) * invB;
+}
+
+// mask.sum() of the ERC mask over the minibatch (the denominator of masked_mean): same entropy arithmetic as ppo_sample.
+__global__ void ppo_mask_count_kernel(const float* __restrict__ logits, int ldl, const int32_t* __restrict__ row_index,
+                                      const float* __restrict__ ent_old, float* __restrict__ count, int B, int A, gymrl_ppo_cfg cfg) {
+    __shared__ double dscratch[32];
+    const int i = blockIdx.x * blockDim.x + threadIdx.x;
+    float mask = 0.f;
+    if (i < B) {
+        const int r = row_index ? row_index[i] : i;
+        float mx = logits[(size_t)i * ldl];
+        for (int j = 1; j < A; ++j) mx = fmaxf(mx, logits[(size_t)i * ldl + j]);
+        float p[MAX_A], s = 0.f;
+#pragma unroll
+        for (int j = 0; j < MAX_A; ++j)
+            if (j < A) { p[j] = exp2f_approx((logits[(size_t)i * ldl + j] - mx) * 1.4426950408889634f); s += p[j]; }
+        const float lse = logf(s) + mx, inv_s = 1.0f / s;
+        float H = 0.f;
+#pragma unroll
+        for (int j = 0; j < MAX_A; ++j)
+            if (j < A) { const float pj = p[j] * inv_s; H -= pj * (logits[(size_t)i * ldl + j] - lse); }
+        const float er = H / (ent_old[r] + 1e-8f);
+        mask = (er > 1.0f - cfg.erc_low && er < 1.0f + cfg.erc_high) ? 1.0f : 0.0f;
+    }
+    double m = block_sum((double)mask, dscratch);
+    const double v[1] = {m};
+    ordered_block_accumulate<1>(v, count, dscratch);
 }
 
 __global__ void ppo_loss_kernel(const float* __restrict__ logits, int ldl, const float* __restrict__ value, int ldv,
@@ -132,6 +162,11 @@ __global__ void ppo_loss_kernel(const float* __restrict__ logits, int ldl, const
     __shared__ float scratch[32];
     const int i = blockIdx.x * blockDim.x + threadIdx.x;
     const float invB = 1.0f / (float)B;
+    float invN = invB;
+    if (cfg.mode & GYMRL_PPO_MASKED_MEAN) {     // masked_mean (ppo_lstm :646-655): sum / mask.sum(), 0 when nothing is unmasked
+        const float cnt = *cfg.d_mask_count;
+        invN = cnt > 0.0f ? 1.0f / cnt : 0.0f;
+    }
     const float ent_coef = cfg.d_entropy_coef ? *cfg.d_entropy_coef : cfg.entropy_coef;
     float m_pol = 0.f, m_val = 0.f, m_ent = 0.f, m_clip = 0.f, m_kl = 0.f, m_erc = 0.f;
     if (i < B) {
@@ -142,7 +177,7 @@ __global__ void ppo_loss_kernel(const float* __restrict__ logits, int ldl, const
             if (j < A) z[j] = logits[(size_t)i * ldl + j];
         PpoSample o;
         ppo_sample(z, value[(size_t)i * ldv], action[r], logp_old[r], adv[r], ret[r], ent_old ? ent_old[r] : 0.f,
-                   val_old ? val_old[r] : 0.f, cfg, ent_coef, invB, A, o);
+                   val_old ? val_old[r] : 0.f, cfg, ent_coef, invB, A, o, invN);
 #pragma unroll
         for (int j = 0; j < MAX_A; ++j)
             if (j < A) dlogits[(size_t)i * lddl + j] = o.dlogits[j];
@@ -155,15 +190,10 @@ __global__ void ppo_loss_kernel(const float* __restrict__ logits, int ldl, const
     m_clip = block_sum(m_clip, scratch);
     m_kl = block_sum(m_kl, scratch);
     m_erc = block_sum(m_erc, scratch);
-    if (threadIdx.x == 0 && metrics) {
-        atomicAdd(&metrics[0], m_pol);
-        atomicAdd(&metrics[1], m_val);
-        atomicAdd(&metrics[2], m_ent);
-        atomicAdd(&metrics[3], m_clip);
-        atomicAdd(&metrics[4], m_kl);
-        atomicAdd(&metrics[5], m_erc);
-        atomicAdd(&metrics[6], m_pol + m_val - ent_coef * m_ent);
-        if (blockIdx.x == 0) atomicAdd(&metrics[7], 1.0f);
+    if (metrics) {
+        __shared__ double dscratch[32];
+        const double v[8] = {m_pol, m_val, m_ent, m_clip, m_kl, m_erc, m_pol + m_val - ent_coef * m_ent, blockIdx.x == 0 ? 1.0 : 0.0};
+        ordered_block_accumulate<8>(v, metrics, dscratch);   // fixed block order (reporting only, but reproducible)
     }
 }
 
@@ -299,13 +329,14 @@ ppo_heads_fused_kernel(const float* __restrict__ h, int ldh, const float* __rest
     }
     float* out = partials + (size_t)blockIdx.x * P;
     for (int i = threadIdx.x; i < P; i += blockDim.x) out[i] = s_acc[i];
-    if (threadIdx.x == 0 && metrics) {
+    if (metrics) {
+        __shared__ double dscratch[32];
         float m[6] = {0.f, 0.f, 0.f, 0.f, 0.f, 0.f};
-        for (int w = 0; w < kHeadsWarps; ++w)
-            for (int k = 0; k < 6; ++k) m[k] += s_met[w][k];
-        for (int k = 0; k < 6; ++k) atomicAdd(&metrics[k], m[k]);
-        atomicAdd(&metrics[6], m[0] + m[1] - ent_coef * m[2]);
-        if (blockIdx.x == 0) atomicAdd(&metrics[7], 1.0f);
+        if (threadIdx.x == 0)
+            for (int w = 0; w < kHeadsWarps; ++w)
+                for (int k = 0; k < 6; ++k) m[k] += s_met[w][k];
+        const double v[8] = {m[0], m[1], m[2], m[3], m[4], m[5], m[0] + m[1] - ent_coef * m[2], blockIdx.x == 0 ? 1.0 : 0.0};
+        ordered_block_accumulate<8>(v, metrics, dscratch);   // fixed block order (reporting only, but reproducible)
     }
 }
 
@@ -330,6 +361,7 @@ extern "C" int gymrl_ppo_heads_fused(const float* d_h, int ldh, const float* d_W
     GYMRL_REQUIRE((cfg->mode & 3) <= GYMRL_PPO_FULL, "unknown PPO mode %d", cfg->mode);
     GYMRL_REQUIRE((cfg->mode & 3) != GYMRL_PPO_FULL || d_entropy_old, "GYMRL_PPO_FULL needs d_entropy_old");
     GYMRL_REQUIRE(!(cfg->mode & GYMRL_PPO_VALUE_CLIP) || d_value_old, "VALUE_CLIP needs d_value_old");
+    GYMRL_REQUIRE(!(cfg->mode & GYMRL_PPO_MASKED_MEAN), "MASKED_MEAN needs a pass over the whole minibatch first: use gymrl_ppo_loss");
     const int A = 4;
     const int P = A * H + A + H + 1;
     int grid = ceil_div(batch, kHeadsWarps * 8);           // >= 8 rows per warp so the per-warp set-up amortises
@@ -371,6 +403,13 @@ extern "C" int gymrl_ppo_loss(const float* d_logits, int ld_logits, const float*
     GYMRL_REQUIRE((cfg->mode & 3) <= GYMRL_PPO_FULL, "unknown PPO mode %d", cfg->mode);
     GYMRL_REQUIRE((cfg->mode & 3) != GYMRL_PPO_FULL || d_entropy_old, "GYMRL_PPO_FULL needs d_entropy_old");
     GYMRL_REQUIRE(!(cfg->mode & GYMRL_PPO_VALUE_CLIP) || d_value_old, "VALUE_CLIP needs d_value_old");
+    if (cfg->mode & GYMRL_PPO_MASKED_MEAN) {
+        GYMRL_REQUIRE((cfg->mode & 3) == GYMRL_PPO_FULL && cfg->d_mask_count, "MASKED_MEAN needs GYMRL_PPO_FULL and cfg.d_mask_count");
+        GYMRL_CUDA(cudaMemsetAsync(cfg->d_mask_count, 0, sizeof(float), as_stream(stream)));
+        ppo_mask_count_kernel<<<ceil_div(batch, 256), 256, 0, as_stream(stream)>>>(d_logits, ld_logits, d_row_index, d_entropy_old,
+                                                                                  cfg->d_mask_count, batch, n_actions, *cfg);
+        gymrl_count_launch();
+    }
     ppo_loss_kernel<<<ceil_div(batch, 256), 256, 0, as_stream(stream)>>>(
         d_logits, ld_logits, d_value, ld_value, d_row_index, d_action, d_logp_old, d_adv, d_ret, d_entropy_old, d_value_old,
         d_dlogits, ld_dlogits, d_dvalue, ld_dvalue, d_metrics, batch, n_actions, *cfg);

@@ -233,9 +233,11 @@ __global__ void sac_actor_grad_kernel(const float* __restrict__ x, const float* 
     }
     lsum = block_sum(lsum, scratch);
     float lps = block_sum(lp_i, scratch);
-    if (threadIdx.x == 0 && acc) {
-        atomicAdd(&acc[0], lsum);  // alpha * mean(logpi) part of the actor loss
-        atomicAdd(&acc[1], lps);   // sum(logpi) for the alpha step
+    if (acc) {
+        __shared__ double dscratch[32];
+        // acc[0]: alpha * mean(logpi) part of the actor loss; acc[1]: sum(logpi), which the alpha step consumes -> fixed block order
+        const double v[2] = {lsum, lps};
+        ordered_block_accumulate<2>(v, acc, dscratch);
     }
 }
 

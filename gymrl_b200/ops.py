@@ -202,6 +202,39 @@ def ppo_loss(logits, value, action, logp_old, adv, ret, cfg: _ffi.PPOCfg, *, row
     return dlogits, dvalue, metrics
 
 
+def seq_gather(src, seq_index, seq_len, out=None):
+    """out[b, t] = src.view(S, L, -1)[seq_index[b], t]  (ppo_lstm_lunarlander.py:682-707).  src: [S * L, D] rows."""
+    src2 = src.reshape(src.shape[0], -1)
+    nb, D = seq_index.numel(), src2.shape[1]
+    out = torch.empty(nb * seq_len, D, device=src.device, dtype=f32) if out is None else out
+    check(load().gymrl_seq_gather(ptr(src2, f32), _ld(src2), ptr(seq_index, i32), nb, int(seq_len), D, ptr(out, f32), _ld(out),
+                                  stream_ptr()))
+    return out
+
+
+def gru_cell_forward(gi, gh, h, h_out=None, gates=None, save_gates=True):
+    B, Hd = h.shape
+    h_out = torch.empty(B, Hd, device=h.device, dtype=f32) if h_out is None else h_out
+    if gates is None and save_gates:
+        gates = torch.empty(B, 3 * Hd, device=h.device, dtype=f32)
+    check(load().gymrl_gru_cell_forward(ptr(gi, f32), _ld(gi), ptr(gh, f32), _ld(gh), ptr(h, f32), _ld(h), ptr(h_out, f32), _ld(h_out),
+                                        ptr(gates, f32), B, Hd, stream_ptr()))
+    return h_out, gates
+
+
+def gru_cell_backward(dh_out, gates, gh, h, dgi=None, dgh=None, dh=None, accumulate_dh=False):
+    B, Hd = h.shape
+    dev = h.device
+    dgi = torch.empty(B, 3 * Hd, device=dev, dtype=f32) if dgi is None else dgi
+    dgh = torch.empty(B, 3 * Hd, device=dev, dtype=f32) if dgh is None else dgh
+    dh = torch.empty(B, Hd, device=dev, dtype=f32) if dh is None else dh
+    assert gates.is_contiguous()
+    check(load().gymrl_gru_cell_backward(ptr(dh_out, f32), _ld(dh_out), ptr(gates, f32), ptr(gh, f32), _ld(gh), ptr(h, f32), _ld(h),
+                                         ptr(dgi, f32), _ld(dgi), ptr(dgh, f32), _ld(dgh), ptr(dh, f32), _ld(dh), int(accumulate_dh),
+                                         B, Hd, stream_ptr()))
+    return dgi, dgh, dh
+
+
 def ppo_heads_workspace_bytes(H, A=4) -> int:
     return int(load().gymrl_ppo_heads_workspace_bytes(int(H), int(A)))
 

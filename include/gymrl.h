@@ -153,6 +153,9 @@ int gymrl_normalize_inplace(float* d_x, long long n, const double* d_sums, doubl
 #define GYMRL_PPO_DUALCLIP 0   /* algorithms/ppo_lunarlander.py:278-300                         */
 #define GYMRL_PPO_FULL 1       /* algorithms/ppo_full_lunarlander.py:586-633 (ERC mask, clip-higher) */
 #define GYMRL_PPO_VALUE_CLIP 4 /* flag, OR-ed in: algorithms/ppo_lstm_lunarlander.py:763-771    */
+#define GYMRL_PPO_MASKED_MEAN 8 /* flag (with GYMRL_PPO_FULL): policy / value / entropy / clip_frac are masked_mean()s,
+                                 * sum(x * mask) / mask.sum() and 0 when mask.sum() == 0 (ppo_lstm_lunarlander.py:646-655,
+                                 * :757-771) instead of ppo_full's plain mean over the minibatch; gymrl_ppo_loss only */
 
 typedef struct gymrl_ppo_cfg {
     int mode;            /* GYMRL_PPO_* (| GYMRL_PPO_VALUE_CLIP)                       */
@@ -167,6 +170,7 @@ typedef struct gymrl_ppo_cfg {
     float vclip_eps_max;
     const float* d_entropy_coef; /* nullable device scalar overriding entropy_coef: lets a captured CUDA graph
                                   * follow ppo_full's per-update entropy anneal (:664-666)      */
+    float* d_mask_count;         /* MASKED_MEAN: device float the call fills with mask.sum() of the minibatch */
 } gymrl_ppo_cfg;
 
 /* metrics (device float[8], accumulated with += so zero before the first minibatch):
@@ -425,6 +429,25 @@ int gymrl_ppo_heads_fused(const float* d_h, int ldh, const float* d_Wa, const fl
                           int act_in, float* d_dWa, float* d_dba, float* d_dWc, float* d_dbc, float* d_lv_out, float* d_metrics,
                           void* d_workspace, size_t workspace_bytes, int accumulate, int batch, int H, int n_actions,
                           const gymrl_ppo_cfg* cfg, void* stream);
+
+/* ------------------------------------------------------------------------------------------------
+ * Recurrent PPO / PPG building blocks.
+ * ---------------------------------------------------------------------------------------------- */
+/* Sequence-minibatch gather: out[b][t][:] = src[seq_index[b] * seq_len + t][:], i.e. states.view(S, L, -1)[perm[start:end]]
+ * of algorithms/ppo_lstm_lunarlander.py:682-707 (seq_len 8) for any per-step field of `width` floats. */
+int gymrl_seq_gather(const float* d_src, int ld_src, const int32_t* d_seq_index, int n_seq, int seq_len, int width,
+                     float* d_out, int ld_out, void* stream);
+/* torch.nn.GRU's cell (ppo_rnn_lunarlander.py:124-139 MLPRNN.rnn, ppo_lstm_lunarlander.py:449-492 URNN, ppg_rnn :330-395):
+ * gi = x W_ih^T + b_ih and gh = h W_hh^T + b_hh come from gymrl_linear_forward ([B][3H], gate order r | z | n);
+ *   r = sigmoid(gi_r + gh_r), z = sigmoid(gi_z + gh_z), n = tanh(gi_n + r gh_n), h' = (1 - z) n + z h.
+ * d_gates ([B][3H], nullable in inference) keeps r, z, n for the backward pass. */
+int gymrl_gru_cell_forward(const float* d_gi, int ld_gi, const float* d_gh, int ld_gh, const float* d_h, int ld_h,
+                           float* d_h_out, int ld_out, float* d_gates, int batch, int hidden, void* stream);
+/* Given dL/dh', writes dL/dgi and dL/dgh ([B][3H]) and the direct path of dL/dh (= z dh'; += when accumulate_dh; nullable).
+ * The caller completes BPTT with the dense-layer entry points: dx = dgi W_ih, dh += dgh W_hh, dW_ih += dgi^T x, ... */
+int gymrl_gru_cell_backward(const float* d_dh_out, int ld_dh_out, const float* d_gates, const float* d_gh, int ld_gh,
+                            const float* d_h, int ld_h, float* d_dgi, int ld_dgi, float* d_dgh, int ld_dgh, float* d_dh,
+                            int ld_dh, int accumulate_dh, int batch, int hidden, void* stream);
 
 /* ------------------------------------------------------------------------------------------------
  * ppo_full network glue: manifold hyper-connection stages, RMSNorm, SiLU.

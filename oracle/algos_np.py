@@ -70,7 +70,7 @@ def categorical(logits, noise=None):
 #      ppo_lstm_lunarlander.py:763-771) -----------------------------------------------------------------------
 def ppo_loss_grad(logits, value, action, logp_old, adv, ret, *, mode="dualclip", clip_eps_min=0.2, clip_eps_max=0.2,
                   dual_clip=3.0, value_coef=0.5, entropy_coef=0.01, entropy_old=None, erc_low=0.06, erc_high=0.06,
-                  value_old=None, vclip_eps_min=0.2, vclip_eps_max=0.2):
+                  value_old=None, vclip_eps_min=0.2, vclip_eps_max=0.2, masked_mean=False):
     """float64 restatement with torch's tie conventions (min/max split ties evenly; clamp passes grads on the
     closed interval).  Returns dict(dlogits, dvalue, policy_loss, value_loss, entropy, clip_frac, approx_kl, erc_frac)."""
     z = np.asarray(logits, np.float64); V = np.asarray(value, np.float64)
@@ -113,13 +113,17 @@ def ppo_loss_grad(logits, value, action, logp_old, adv, ret, *, mode="dualclip",
         d2 = 2 * e2 * ((dlt >= -vclip_eps_min) & (dlt <= vclip_eps_max))
         dv = np.where(l2 > vterm, d2, np.where(l2 == vterm, 0.5 * (dv + d2), dv))
         vterm = np.maximum(vterm, l2)
-    dL_dlp = -(g * ratio) * mask / B
-    dL_dH = -entropy_coef * mask / B
+    # masked_mean (ppo_lstm_lunarlander.py:646-655): sum(x * mask) / mask.sum(), 0 when mask.sum() == 0; ppo_full: plain mean
+    Nn = B
+    if masked_mean:
+        Nn = mask.sum() if mask.sum() > 0 else np.inf
+    dL_dlp = -(g * ratio) * mask / Nn
+    dL_dH = -entropy_coef * mask / Nn
     onehot = np.zeros((B, A)); onehot[np.arange(B), a] = 1.0
     dlogits = dL_dlp[:, None] * (onehot - p) + dL_dH[:, None] * (-p * (ln + H[:, None]))
-    dvalue = value_coef * mask * dv / B
-    return dict(dlogits=dlogits, dvalue=dvalue, policy_loss=(-obj * mask).mean(), value_loss=(value_coef * mask * vterm).mean(),
-                entropy=(H * mask).mean(), clip_frac=(((ratio < lo) | (ratio > hi)) * mask).mean(),
+    dvalue = value_coef * mask * dv / Nn
+    return dict(dlogits=dlogits, dvalue=dvalue, policy_loss=(-obj * mask).sum() / Nn, value_loss=(value_coef * mask * vterm).sum() / Nn,
+                entropy=(H * mask).sum() / Nn, clip_frac=(((ratio < lo) | (ratio > hi)) * mask).sum() / Nn,
                 approx_kl=(np.asarray(logp_old, np.float64) - lp).mean(), erc_frac=1.0 - mask.mean())
 
 
@@ -232,3 +236,58 @@ def sac_discrete_actor(logits, q1, q2, log_alpha):
     g = alpha * (lp + p / (p + 1e-8)) - m                  # dL_i / dp_j
     dz = p * (g - (p * g).sum(axis=1, keepdims=True)) / B
     return dict(loss=(-alpha * H - (p * m).sum(axis=1)).mean(), dlogits=dz, sum_entropy=H.sum())
+
+
+# ---- torch.nn.GRU cell (ppo_rnn_lunarlander.py:124-139 MLPRNN.rnn; gate order r | z | n) -----------------------
+def gru_cell_forward(gi, gh, h):
+    """float64: returns (h_new, r, z, n) for gi = x W_ih^T + b_ih, gh = h W_hh^T + b_hh of shape [B, 3H]."""
+    gi, gh, h = (np.asarray(a, np.float64) for a in (gi, gh, h))
+    Hd = h.shape[-1]
+    sig = lambda x: 1.0 / (1.0 + np.exp(-x))
+    r = sig(gi[:, :Hd] + gh[:, :Hd])
+    z = sig(gi[:, Hd:2 * Hd] + gh[:, Hd:2 * Hd])
+    n = np.tanh(gi[:, 2 * Hd:] + r * gh[:, 2 * Hd:])
+    return (1 - z) * n + z * h, r, z, n
+
+
+def gru_cell_backward(dh_new, r, z, n, gh, h):
+    """Returns (dgi, dgh, dh_direct) given dL/dh_new."""
+    Hd = h.shape[-1]
+    dn = dh_new * (1 - z)
+    dz = dh_new * (h - n)
+    dan = dn * (1 - n * n)
+    dr = dan * gh[:, 2 * Hd:]
+    daz, dar = dz * z * (1 - z), dr * r * (1 - r)
+    dgi = np.concatenate([dar, daz, dan], axis=1)
+    dgh = np.concatenate([dar, daz, dan * r], axis=1)
+    return dgi, dgh, dh_new * z
+
+
+def gru_sequence(x, h0, w_ih, w_hh, b_ih, b_hh, dout=None, dhT=None):
+    """x [B, T, I], h0 [B, H]: unrolled GRU forward and (when dout [B, T, H] is given) BPTT, float64.
+    Returns dict(out, hT[, dx, dh0, dw_ih, dw_hh, db_ih, db_hh])."""
+    x, h0, w_ih, w_hh, b_ih, b_hh = (np.asarray(a, np.float64) for a in (x, h0, w_ih, w_hh, b_ih, b_hh))
+    B, T, _ = x.shape
+    hs, saved, h = [], [], h0
+    for t in range(T):
+        gi, gh = x[:, t] @ w_ih.T + b_ih, h @ w_hh.T + b_hh
+        hn, r, z, n = gru_cell_forward(gi, gh, h)
+        saved.append((r, z, n, gh, h))
+        hs.append(hn)
+        h = hn
+    res = {"out": np.stack(hs, axis=1), "hT": h}
+    if dout is None:
+        return res
+    dout = np.asarray(dout, np.float64)
+    dh = np.zeros_like(h0) if dhT is None else np.asarray(dhT, np.float64)
+    dx = np.zeros_like(x)
+    dw_ih, dw_hh, db_ih, db_hh = np.zeros_like(w_ih), np.zeros_like(w_hh), np.zeros_like(b_ih), np.zeros_like(b_hh)
+    for t in reversed(range(T)):
+        r, z, n, gh, hp = saved[t]
+        dgi, dgh, dh_dir = gru_cell_backward(dout[:, t] + dh, r, z, n, gh, hp)
+        dx[:, t] = dgi @ w_ih
+        dw_ih += dgi.T @ x[:, t]; db_ih += dgi.sum(0)
+        dw_hh += dgh.T @ hp; db_hh += dgh.sum(0)
+        dh = dh_dir + dgh @ w_hh
+    res.update(dx=dx, dh0=dh, dw_ih=dw_ih, dw_hh=dw_hh, db_ih=db_ih, db_hh=db_hh)
+    return res

@@ -55,3 +55,9 @@ def trainer_from_golden(g, use_graph, n_mb, seed=0):
     return t
 
 
+
+
+@pytest.fixture(scope="session")
+def ops():
+    from gymrl_b200 import ops as _ops
+    return _ops

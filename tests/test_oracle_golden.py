@@ -189,3 +189,34 @@ def test_sac_discrete_oracle_matches_torch_autograd():
     np.testing.assert_allclose(a["loss"], la.item(), rtol=1e-12)
     np.testing.assert_allclose(a["dlogits"], tz.grad.numpy(), rtol=1e-10, atol=1e-14)
     np.testing.assert_allclose(a["sum_entropy"], H.sum().item(), rtol=1e-12)
+
+
+# ---------------------------------------------------------------- §8f rank 3: masked_mean / value-clip loss, GRU cell
+@pytest.mark.parametrize("tag", ["script_window", "tight_window"])
+def test_oracle_ppo_lstm_masked_mean_value_clip_golden(golden, tag):
+    """oracle ppo_loss_grad(mode=full, masked_mean, value-clip) == autograd of the reference's own update_model expressions
+    (ppo_lstm_lunarlander.py:646-655 masked_mean, :757-771 losses; golden from oracle/make_golden_f3.py)."""
+    g = golden("ppo_lstm_loss.npz")
+    k = lambda n: g[f"{tag}__{n}"]
+    r = A.ppo_loss_grad(k("logits"), k("values"), k("action"), k("logp_old"), k("adv"), k("ret"), mode="full",
+                        clip_eps_min=float(k("clip_eps_min")), clip_eps_max=float(k("clip_eps_max")), dual_clip=float(k("dual_clip")),
+                        value_coef=0.5, entropy_coef=float(k("entropy_coef")), entropy_old=k("entropy_old"),
+                        erc_low=float(k("erc_low")), erc_high=float(k("erc_high")), value_old=k("value_old"),
+                        vclip_eps_min=float(k("clip_eps_min")), vclip_eps_max=float(k("clip_eps_max")), masked_mean=True)
+    np.testing.assert_allclose(r["dlogits"], k("dlogits"), rtol=2e-4, atol=2e-7)
+    np.testing.assert_allclose(r["dvalue"], k("dvalues"), rtol=2e-4, atol=1e-6)
+    if tag == "tight_window":
+        assert 0.2 < r["erc_frac"] < 0.5          # the denominator of masked_mean is not B here
+    # the sequence minibatch of the reference is a gather of whole sequences
+    S, L = int(k("n_seq")), int(k("seq_len"))
+    np.testing.assert_array_equal(k("states").reshape(S, L, -1)[k("perm")], k("s_batch"))
+
+
+def test_oracle_gru_sequence_golden(golden):
+    """oracle gru_sequence (cell forward + BPTT) == torch.nn.GRU of the reference's MLPRNN (ppo_rnn_lunarlander.py:124-139)."""
+    g = golden("gru_mlprnn.npz")
+    r = A.gru_sequence(g["x"], g["h0"], g["w_ih"], g["w_hh"], g["b_ih"], g["b_hh"], dout=g["dout"], dhT=g["dhT"])
+    np.testing.assert_allclose(r["out"], g["out"], rtol=1e-5, atol=1e-6)
+    np.testing.assert_allclose(r["hT"], g["hT"], rtol=1e-5, atol=1e-6)
+    for name in ("dx", "dh0", "dw_ih", "dw_hh", "db_ih", "db_hh"):
+        np.testing.assert_allclose(r[name], g[name], rtol=2e-4, atol=2e-5, err_msg=name)
