@@ -71,6 +71,9 @@ SIGNATURES = {
     "gymrl_reduce_flush": (c_int, [_P, c_int, C.POINTER(c_int), C.POINTER(c_ll), _P]),
     "gymrl_clip_adam_step": (c_int, [_P, _P, _P, _P, c_ll, _P, c_float, c_float, c_float, _P, _P, c_int, c_float, c_float, _P, _P]),
     "gymrl_polyak": (c_int, [_P, _P, c_ll, c_float, _P]),
+    "gymrl_weight_images_register": (c_int, [_P, c_ll, _P, _P, c_int]),
+    "gymrl_weight_images_refresh": (c_int, [_P, _P]),
+    "gymrl_weight_images_unregister": (c_int, [_P]),
     "gymrl_comm_create": (c_int, [_P, c_int, c_int, c_ll, c_int]),
     "gymrl_comm_handle_bytes": (c_int, []),
     "gymrl_comm_get_handle": (c_int, [_P, _P]),

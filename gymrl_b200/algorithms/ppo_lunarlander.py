@@ -134,6 +134,9 @@ class ActorCriticEngine:
         self.gbac = fp.span("actor.0.bias", "critic.0.bias", 1, 2 * H, grad=True).view(2 * H)
         self.gWa2, self.gba2 = fp.g("actor.2.weight"), fp.g("actor.2.bias")
         self.gWc2, self.gbc2 = fp.g("critic.2.weight"), fp.g("critic.2.bias")
+        # the two 256-wide trunk layers are TMA-fed from pre-split tf32 weight images (csrc/wimages.cu, linear_tc.cu ws kernel)
+        if H % 256 == 0:
+            fp.enable_weight_images([("shared.2.weight", "shared.2.weight", H, H), ("actor.0.weight", "critic.0.weight", 2 * H, H)])
         self.workspace = None
         self.ws_layers = None
         self.deferred_reduce = True   # forward_trunk/backward may run inside an ops.reduce_defer_begin() scope
@@ -463,6 +466,7 @@ class PPOTrainer:
         self.net.fp.flat.copy_(s["flat"]); self.optimizer.exp_avg.copy_(s["m"]); self.optimizer.exp_avg_sq.copy_(s["v"])
         self.optimizer.step_t.copy_(s["step"]); self.ctr_mb.copy_(s["ctr_mb"]); self.ctr_action.copy_(s["ctr_action"])
         self.metrics.copy_(s["metrics"]); self.optimizer.done_ctr.copy_(s["done_ctr"]); self.optimizer.sumsq.copy_(s["sumsq"])
+        self.net.fp.refresh_weight_images()    # the parameters were written behind the library's back
 
     def _ensure_update_graphs(self):
         if not self.cfg.use_cuda_graph or self._g_mb is not None or self._g_mb_bwd is not None or self._g_epoch is not None:

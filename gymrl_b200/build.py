@@ -41,6 +41,7 @@ SOURCES = {
     "reduce.cu": [],
     "comm.cu": [],
     "recurrent.cu": [],
+    "wimages.cu": [],
     "replay.cu": [],
     "qlearn.cu": [],
     "mhc.cu": [],

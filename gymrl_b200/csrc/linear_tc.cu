@@ -343,6 +343,7 @@ __global__ void __launch_bounds__(TC_LAUNCH_THREADS, 1) gemm_tf32x3_kernel(const
                 TC_STAMP(8 + kb * 8 + 0);
                 mbar_wait(&bar_full[s], (uint32_t)(use & 1));
                 TC_STAMP(8 + kb * 8 + 1);
+                asm volatile("fence.proxy.async.shared::cta;" ::: "memory");   // the producers' st.shared -> visible to the tensor core
                 asm volatile("tcgen05.fence::after_thread_sync;" ::: "memory");
                 const uint32_t st = smem_u32(smem + (size_t)s * STAGE_BYTES);
                 const uint32_t ah = st, al = st + A_BYTES, bh = st + 2 * A_BYTES, bl = st + 2 * A_BYTES + B_BYTES;
@@ -390,7 +391,8 @@ __global__ void __launch_bounds__(TC_LAUNCH_THREADS, 1) gemm_tf32x3_kernel(const
                     csum.x += va[i].x; csum.y += va[i].y; csum.z += va[i].z; csum.w += va[i].w;
                 }
             }
-            asm volatile("fence.proxy.async.shared::cta;" ::: "memory");   // generic-proxy smem writes -> visible to the tensor core
+            // (the generic -> async proxy fence is executed by the MMA lane after it has acquired bar_full: here it would compile to
+            //  MEMBAR.ALL.CTA and wait for this warp's prefetched global loads, i.e. cost a memory round trip per slab)
             mbar_arrive(&bar_full[s]);
             TC_STAMP(8 + kb * 8 + 2);
         };
@@ -584,6 +586,7 @@ __global__ void __launch_bounds__(TC_LAUNCH_THREADS, 1) gemm_tf32x3_ts_kernel(co
             int s = 0, ph = 0;
             for (int kb = 0; kb < nslab; ++kb) {
                 mbar_wait(&bar_full[s], (uint32_t)ph);
+                asm volatile("fence.proxy.async.shared::cta;" ::: "memory");
                 asm volatile("tcgen05.fence::after_thread_sync;" ::: "memory");
                 const uint32_t st = smem_u32(smem + (size_t)s * STAGE_BYTES);
                 const uint32_t bh = st, bl = st + B_BYTES;
@@ -636,8 +639,7 @@ __global__ void __launch_bounds__(TC_LAUNCH_THREADS, 1) gemm_tf32x3_ts_kernel(co
             }
             asm volatile("tcgen05.wait::st.sync.aligned;" ::: "memory");
             asm volatile("tcgen05.fence::before_thread_sync;" ::: "memory");
-            asm volatile("fence.proxy.async.shared::cta;" ::: "memory");
-            mbar_arrive(&bar_full[s]);
+            mbar_arrive(&bar_full[s]);     // proxy fence: MMA lane (see the SS kernel)
             if (++s == NST) { s = 0; ph ^= 1; }
         };
 
@@ -707,6 +709,464 @@ static int launch_tc_ts(const TcGemmParams& p, int splits, cudaStream_t s) {
     return GYMRL_OK;
 }
 
+
+// =====================================================================================================================
+// Warp-specialised persistent variant ("ws"): TMA-fed weights, register-split activations, 2-CTA MMA, overlapped epilogue.
+//
+// What bounded the kernels above (ncu + per-CTA timelines, profiles/r1_tc_gemm_ncu_full_v12_summary.md): (1) the 128 B/clk
+// shared-memory port — per 32-k slab the converters write 96 KB of hi/lo images and the tensor core reads 144 KB (BN = 256);
+// (2) 45 % of a CTA's life is prologue + epilogue with the tensor pipe idle.  This variant
+//   * pairs two CTAs on one 256 x 256 tile (tcgen05.mma.cta_group::2): each CTA stages its own 128 A rows and HALF of B, so per
+//     slab a CTA writes 64 KB and its tensor core reads 96 KB -> 1250 clk of port time against 1536 clk of MMA;
+//   * takes B (a WEIGHT matrix) from pre-split hi/lo images (wimages.cu) with one 3-D TMA box per stage
+//     (cp.async.bulk.tensor, SWIZZLE_128B = the UMMA K-major layout, [hi | lo] adjacent), so only A — 1/3 of the old
+//     conversion work — passes through registers, on 4 producer warps instead of 8;
+//   * is persistent (one CTA pair per SM pair, static round-robin over tiles) with TWO accumulators in TMEM (2 x 256 columns)
+//     and 8 dedicated epilogue warps: the epilogue of tile i (tcgen05.ld -> smem transpose -> bias / act -> coalesced stores)
+//     runs while the MMAs of tile i + 1 are issued.
+// Roles (15 warps): 0-3 A producers | 4 TMA | 5 MMA issue (leader CTA only) | 6 relay (proxy fence) | 7-14 epilogue.
+// mbarriers: full[s] (producers' elected lanes + TMA expect_tx -> MMA; lives in the leader CTA, the peer arrives remotely),
+// free[s] (tcgen05.commit multicast to both CTAs -> producers / TMA), acc_full[b] (commit multicast -> epilogue),
+// acc_empty[b] (epilogue warps of both CTAs -> MMA).  All waits are bounded (trap on timeout).
+// =====================================================================================================================
+#include <cuda.h>   // CUtensorMap (types only: the encoder is fetched through cudaGetDriverEntryPoint, no libcuda link)
+
+namespace ws {
+constexpr int BM = 128, BN = 256;
+constexpr int PROD_WARPS = 4, EPI_WARPS = 8;
+constexpr int TMA_WARP = 4, MMA_WARP = 5, RELAY_WARP = 6, EPI_WARP0 = 7;
+constexpr int THREADS = (EPI_WARP0 + EPI_WARPS) * 32;   // 448
+constexpr int PROD_THREADS = PROD_WARPS * 32;           // 128
+constexpr int A_PASSES = BM * 8 / PROD_THREADS;         // float4 per producer thread per slab (8)
+
+template <int NCTA>
+struct Cfg {
+    static constexpr int B_ROWS = BN / NCTA;                           // B rows (output columns) this CTA stages
+    static constexpr uint32_t A_BYTES = BM * 128;                      // one image of one 32-k slab
+    static constexpr uint32_t B_BYTES = B_ROWS * 128;
+    static constexpr uint32_t STAGE_BYTES = 2 * A_BYTES + 2 * B_BYTES;   // 64 KB (pair) / 96 KB (single CTA)
+    static constexpr int NST = NCTA == 2 ? 3 : 2;
+    static constexpr uint32_t EPI_SCRATCH = EPI_WARPS * 4096;
+    static constexpr size_t SMEM = (size_t)NST * STAGE_BYTES + EPI_SCRATCH + 1024;
+};
+
+__device__ __forceinline__ uint32_t cluster_ctarank() {
+    uint32_t r;
+    asm volatile("mov.u32 %0, %%cluster_ctarank;" : "=r"(r));
+    return r;
+}
+__device__ __forceinline__ void cluster_sync_all() {
+    asm volatile("barrier.cluster.arrive.release.aligned;" ::: "memory");
+    asm volatile("barrier.cluster.wait.acquire.aligned;" ::: "memory");
+}
+// address of the same shared-memory object in CTA `rank` of the cluster (shared::cluster window)
+__device__ __forceinline__ uint32_t mapa_u32(uint32_t local_addr, uint32_t rank) {
+    uint32_t r;
+    asm volatile("mapa.shared::cluster.u32 %0, %1, %2;" : "=r"(r) : "r"(local_addr), "r"(rank));
+    return r;
+}
+// Arrive on a barrier addressed in the shared::cluster window (own CTA or the leader).  Deliberately WITHOUT .release.cluster:
+// ptxas implements that qualifier as MEMBAR.ALL.GPU, which waits for every outstanding global load of the thread — it serialised
+// the producers' prefetch (measured 1.26 us per slab instead of the tensor pipe's 0.78 us).  What the consumer needs is ordered
+// by other means: the staged bytes are made visible to the async proxy by fence.proxy.async in every writing thread (completed
+// before the __syncwarp that precedes the elected arrive), exactly as in CUTLASS' ClusterBarrier::arrive(cta_id).
+__device__ __forceinline__ void mbar_arrive_cluster(uint32_t cluster_addr) {
+    asm volatile("mbarrier.arrive.shared::cluster.b64 _, [%0];" ::"r"(cluster_addr) : "memory");
+}
+__device__ __forceinline__ void mbar_arrive_expect_tx(uint64_t* bar, uint32_t bytes) {
+    asm volatile("mbarrier.arrive.expect_tx.shared::cta.b64 _, [%0], %1;" ::"r"(smem_u32(bar)), "r"(bytes) : "memory");
+}
+template <int NCTA>
+__device__ __forceinline__ void mbar_wait_ws(uint64_t* bar, uint32_t parity) {
+    const uint32_t addr = smem_u32(bar);
+    for (uint32_t it = 0; it < (1u << 26); ++it) {
+        uint32_t done;
+        asm volatile("{\n.reg .pred p;\nmbarrier.try_wait.parity.shared::cta.b64 p, [%1], %2;\nselp.b32 %0, 1, 0, p;\n}\n"
+                     : "=r"(done) : "r"(addr), "r"(parity) : "memory");
+        if (done) return;
+    }
+    __trap();
+}
+template <int NCTA>
+__device__ __forceinline__ void umma_tf32_ws(uint32_t tmem_d, uint64_t desc_a, uint64_t desc_b, uint32_t idesc, uint32_t accumulate) {
+    if (NCTA == 2)
+        asm volatile("{\n.reg .pred p;\nsetp.ne.b32 p, %4, 0;\ntcgen05.mma.cta_group::2.kind::tf32 [%0], %1, %2, %3, p;\n}\n"
+                     ::"r"(tmem_d), "l"(desc_a), "l"(desc_b), "r"(idesc), "r"(accumulate) : "memory");
+    else
+        asm volatile("{\n.reg .pred p;\nsetp.ne.b32 p, %4, 0;\ntcgen05.mma.cta_group::1.kind::tf32 [%0], %1, %2, %3, p;\n}\n"
+                     ::"r"(tmem_d), "l"(desc_a), "l"(desc_b), "r"(idesc), "r"(accumulate) : "memory");
+}
+// tcgen05.commit: the barrier at this shared-memory offset receives one arrival once every MMA issued so far has retired —
+// in both CTAs of the pair for NCTA == 2 (multicast mask 0b11)
+template <int NCTA>
+__device__ __forceinline__ void umma_commit_ws(uint64_t* bar) {
+    if (NCTA == 2)
+        asm volatile("tcgen05.commit.cta_group::2.mbarrier::arrive::one.shared::cluster.multicast::cluster.b64 [%0], %1;"
+                     ::"r"(smem_u32(bar)), "h"((uint16_t)3) : "memory");
+    else
+        asm volatile("tcgen05.commit.cta_group::1.mbarrier::arrive::one.shared::cluster.b64 [%0];" ::"r"(smem_u32(bar)) : "memory");
+}
+// One 3-D box {32 k, B_ROWS rows, 2 images} of the weight images -> this CTA's stage; the bytes are accounted on the LEADER
+// CTA's full barrier (mbar_cluster_addr), as the MMA that consumes both CTAs' stages is issued there.
+template <int NCTA>
+__device__ __forceinline__ void tma_load_b(uint32_t smem_dst, const CUtensorMap* map, int k0, int row0, uint32_t mbar_cluster_addr) {
+    if (NCTA == 2)
+        asm volatile("cp.async.bulk.tensor.3d.cta_group::2.shared::cluster.global.mbarrier::complete_tx::bytes [%0], [%1, {%2, %3, %4}], [%5];"
+                     ::"r"(smem_dst), "l"(reinterpret_cast<uint64_t>(map)), "r"(k0), "r"(row0), "r"(0), "r"(mbar_cluster_addr) : "memory");
+    else
+        asm volatile("cp.async.bulk.tensor.3d.shared::cluster.global.mbarrier::complete_tx::bytes [%0], [%1, {%2, %3, %4}], [%5];"
+                     ::"r"(smem_dst), "l"(reinterpret_cast<uint64_t>(map)), "r"(k0), "r"(row0), "r"(0), "r"(mbar_cluster_addr) : "memory");
+}
+}  // namespace ws
+
+template <int NCTA>
+__global__ void __launch_bounds__(ws::THREADS, 1) gemm3x_ws_kernel(const TcGemmParams p, const __grid_constant__ CUtensorMap tmap_b,
+                                                                   int tiles_m, int tiles_n) {
+    const int dbg_flags = p.bn_max;   // developer probe (GYMRL_TC_WS_DBG): 1 = producers skip their st.shared, 2 = only the hi*hi MMA, 4 = no TMA
+    using C = ws::Cfg<NCTA>;
+    constexpr int NST = C::NST;
+    constexpr int BM = ws::BM, BN = ws::BN;
+    extern __shared__ __align__(1024) uint8_t smem_raw[];
+    uint8_t* smem = reinterpret_cast<uint8_t*>((reinterpret_cast<uintptr_t>(smem_raw) + 1023) & ~(uintptr_t)1023);
+    __shared__ __align__(8) uint64_t bar_full[NST];
+    __shared__ __align__(8) uint64_t bar_free[NST];
+    __shared__ __align__(8) uint64_t bar_acc_full[2];
+    __shared__ __align__(8) uint64_t bar_acc_empty[2];
+    __shared__ __align__(8) uint64_t bar_staged[NST];   // this CTA's producers -> its relay lane, which fences and arrives on the leader's full[s]
+    __shared__ uint32_t tmem_base_s;
+
+    const int t = threadIdx.x, warp = t >> 5, lane = t & 31;
+    const uint32_t rank = NCTA == 2 ? ws::cluster_ctarank() : 0u;
+    const bool leader = rank == 0;
+    const int cluster_id = blockIdx.x / NCTA, n_clusters = gridDim.x / NCTA;
+    const int n_tiles = tiles_m * tiles_n;
+    const int nslab = p.K / 32;
+    const uint32_t smem_base = smem_u32(smem);
+    // developer probe (tools/ws_cta_times.py): 32 %globaltimer slots per CTA
+    long long* const wdbg = g_tc_cta_dbg ? g_tc_cta_dbg + 32ll * blockIdx.x : nullptr;
+#define WS_STAMP(slot) do { if (wdbg) wdbg[(slot)] = globaltimer_ns(); } while (0)
+    if (t == 0) { WS_STAMP(0); if (wdbg) { uint32_t smid; asm volatile("mov.u32 %0, %%smid;" : "=r"(smid)); wdbg[3] = smid; } }
+
+    if (t == 0) {
+#pragma unroll
+        for (int s = 0; s < NST; ++s) {
+            // leader: the relay lane of every CTA of the pair + the expect_tx arrival of the TMA lane
+            mbar_init(&bar_full[s], NCTA + 1);
+            mbar_init(&bar_free[s], 1);
+            mbar_init(&bar_staged[s], ws::PROD_WARPS);
+        }
+        mbar_init(&bar_acc_full[0], 1); mbar_init(&bar_acc_full[1], 1);
+        mbar_init(&bar_acc_empty[0], NCTA * ws::EPI_WARPS); mbar_init(&bar_acc_empty[1], NCTA * ws::EPI_WARPS);
+        asm volatile("fence.mbarrier_init.release.cluster;" ::: "memory");
+    }
+    if (warp == ws::MMA_WARP) {   // the same warp of both CTAs allocates (and later frees) all 512 TMEM columns: two accumulators
+        if (NCTA == 2) {
+            asm volatile("tcgen05.alloc.cta_group::2.sync.aligned.shared::cta.b32 [%0], %1;" ::"r"(smem_u32(&tmem_base_s)), "n"(512) : "memory");
+            asm volatile("tcgen05.relinquish_alloc_permit.cta_group::2.sync.aligned;" ::: "memory");
+        } else {
+            asm volatile("tcgen05.alloc.cta_group::1.sync.aligned.shared::cta.b32 [%0], %1;" ::"r"(smem_u32(&tmem_base_s)), "n"(512) : "memory");
+            asm volatile("tcgen05.relinquish_alloc_permit.cta_group::1.sync.aligned;" ::: "memory");
+        }
+    }
+    if (warp == ws::TMA_WARP && lane == 0) asm volatile("prefetch.tensormap [%0];" ::"l"(reinterpret_cast<uint64_t>(&tmap_b)) : "memory");
+    asm volatile("tcgen05.fence::before_thread_sync;" ::: "memory");
+    if (NCTA == 2) ws::cluster_sync_all(); else __syncthreads();
+    asm volatile("tcgen05.fence::after_thread_sync;" ::: "memory");
+    const uint32_t tmem_d = tmem_base_s;
+    pdl_wait();
+    pdl_launch_dependents();
+    if (t == 0) WS_STAMP(1);
+
+    // barrier addresses in the LEADER CTA, for the remote arrivals of the peer
+    uint32_t full_leader[NST], acc_empty_leader[2];
+#pragma unroll
+    for (int s = 0; s < NST; ++s) full_leader[s] = NCTA == 2 ? ws::mapa_u32(smem_u32(&bar_full[s]), 0u) : smem_u32(&bar_full[s]);
+#pragma unroll
+    for (int b = 0; b < 2; ++b) acc_empty_leader[b] = NCTA == 2 ? ws::mapa_u32(smem_u32(&bar_acc_empty[b]), 0u) : smem_u32(&bar_acc_empty[b]);
+
+    if (warp < ws::PROD_WARPS) {
+        // ===== A producers: global fp32 -> registers -> hi / lo tf32 images (K-major SWIZZLE_128B atoms) =====
+        const int r0 = t >> 3, c = t & 7;
+        const uint32_t soff = (uint32_t)(r0 >> 3) * 1024u + (uint32_t)(r0 & 7) * 128u + (uint32_t)((c ^ (r0 & 7)) << 4);
+        const float* ptr[ws::A_PASSES];
+        int l_tile = cluster_id, l_kb = 0;           // loader position (runs ahead of the consumer position)
+        auto set_tile = [&](int tile) {
+            const int m0 = ((tile / tiles_n) * NCTA + (int)rank) * BM;
+#pragma unroll
+            for (int i = 0; i < ws::A_PASSES; ++i) {
+                const int m = min(m0 + r0 + (ws::PROD_THREADS / 8) * i, p.M - 1);   // clamped: those rows are never stored
+                ptr[i] = p.A + (long long)m * p.lda + c * 4;
+            }
+        };
+        auto load = [&](float4 (&v)[ws::A_PASSES]) {
+            if (l_kb == 0) set_tile(l_tile);
+#pragma unroll
+            for (int i = 0; i < ws::A_PASSES; ++i) {
+                v[i] = __ldg(reinterpret_cast<const float4*>(ptr[i]));
+                ptr[i] += 32;
+            }
+            if (++l_kb == nslab) { l_kb = 0; l_tile += n_clusters; }
+        };
+        uint32_t it = 0;
+        auto consume = [&](const float4 (&v)[ws::A_PASSES]) {
+            const uint32_t s = it % NST, ph = (it / NST) & 1u;
+            ws::mbar_wait_ws<NCTA>(&bar_free[s], ph ^ 1u);       // the MMAs that read this stage have retired (passes on first use)
+            const uint32_t st = smem_base + s * C::STAGE_BYTES;
+            if (t == 0 && it == 0) { if (wdbg) wdbg[8] = (long long)(__float_as_uint(v[0].x) & 0) + globaltimer_ns(); }   // first operands arrived
+#pragma unroll
+            for (int i = 0; i < ws::A_PASSES; ++i) {
+                uint4 hi, lo;
+                split4(v[i], hi, lo);
+                if (!(dbg_flags & 1) || hi.x == 0x12345u) {
+                    sts128(st + soff + 2048u * i, hi);                 // 16 rows per pass = two 8-row atoms
+                    sts128(st + C::A_BYTES + soff + 2048u * i, lo);
+                }
+            }
+            // No fence.proxy.async here: it compiles to MEMBAR.ALL.CTA + FENCE.VIEW.ASYNC, and the membar waits for the warp's
+            // outstanding global loads — the prefetched slabs — so every slab cost a full memory round trip (1.1-1.3 us measured,
+            // also in the round-1 kernels).  The generic -> async proxy fence is executed by the relay lane, which has no loads in
+            // flight, after it has acquired this barrier; it then arrives on the leader's full[s].
+            __syncwarp();
+            if (lane == 0) mbar_arrive(&bar_staged[s]);
+            if (t == 0) { if (it == 0) WS_STAMP(9); if ((int)it == nslab - 1) WS_STAMP(10); if ((int)it == 2 * nslab - 1) WS_STAMP(11); }
+            ++it;
+        };
+        const int my_tiles = cluster_id < n_tiles ? (n_tiles - cluster_id + n_clusters - 1) / n_clusters : 0;
+        const long long total = (long long)my_tiles * nslab;
+        // two register sets: the loads of slab g + 1 are in flight while slab g is converted (a third set was measured: no gain —
+        // once the proxy fence left these warps the producers sustain 0.7 us per slab, the tensor pipe 1.0-1.1 us)
+        float4 v0[ws::A_PASSES], v1[ws::A_PASSES];
+        if (total > 0) load(v0);
+        for (long long g = 0; g < total; g += 2) {
+            if (g + 1 < total) load(v1);
+            consume(v0);
+            if (g + 1 < total) {
+                if (g + 2 < total) load(v0);
+                consume(v1);
+            }
+        }
+    } else if (warp == ws::TMA_WARP) {
+        // ===== TMA: one 3-D box {32 k, B_ROWS, hi|lo} of the weight images per stage =====
+        if (lane == 0) {
+            uint32_t it = 0;
+            for (int tile = cluster_id; tile < n_tiles; tile += n_clusters) {
+                const int row0 = (tile % tiles_n) * BN + (int)rank * C::B_ROWS;
+                for (int kb = 0; kb < nslab; ++kb, ++it) {
+                    const uint32_t s = it % NST, ph = (it / NST) & 1u;
+                    ws::mbar_wait_ws<NCTA>(&bar_free[s], ph ^ 1u);
+                    if (dbg_flags & 4) { if (leader) mbar_arrive(&bar_full[s]); continue; }
+                    if (leader) ws::mbar_arrive_expect_tx(&bar_full[s], (uint32_t)NCTA * 2u * C::B_BYTES);
+                    ws::tma_load_b<NCTA>(smem_base + s * C::STAGE_BYTES + 2 * C::A_BYTES, &tmap_b, kb * 32, row0, full_leader[s]);
+                    if (it == 0) WS_STAMP(16);
+                    if ((int)it == nslab - 1) WS_STAMP(17);
+                }
+            }
+        }
+        __syncwarp();    // reconverge before the (aligned) cluster barrier at the end
+    } else if (warp == ws::MMA_WARP) {
+        // ===== MMA issue: one lane of the leader CTA drives the tensor cores of both CTAs =====
+        if (leader && lane == 0) {
+            constexpr uint32_t IDESC = (1u << 4) | (2u << 7) | (2u << 10) | ((uint32_t)(BN >> 3) << 17) | ((uint32_t)((BM * NCTA) >> 4) << 24);
+            uint32_t it = 0, acc_it = 0;
+            for (int tile = cluster_id; tile < n_tiles; tile += n_clusters, ++acc_it) {
+                const uint32_t b = acc_it & 1u, aph = (acc_it >> 1) & 1u;
+                ws::mbar_wait_ws<NCTA>(&bar_acc_empty[b], aph ^ 1u);      // the epilogue has drained this accumulator
+                asm volatile("tcgen05.fence::after_thread_sync;" ::: "memory");
+                const uint32_t d = tmem_d + b * (uint32_t)BN;
+                for (int kb = 0; kb < nslab; ++kb, ++it) {
+                    const uint32_t s = it % NST, ph = (it / NST) & 1u;
+                    ws::mbar_wait_ws<NCTA>(&bar_full[s], ph);
+                    if (it == 0) WS_STAMP(4);
+                    if ((int)it == nslab) WS_STAMP(6);
+                    asm volatile("tcgen05.fence::after_thread_sync;" ::: "memory");
+                    const uint32_t st = smem_base + s * C::STAGE_BYTES;
+                    const uint32_t ah = st, al = st + C::A_BYTES, bh = st + 2 * C::A_BYTES, bl = bh + C::B_BYTES;
+#pragma unroll
+                    for (int j = 0; j < 4; ++j) {
+                        const uint64_t dah = make_desc(ah + j * 32, 16, 1024), dal = make_desc(al + j * 32, 16, 1024);
+                        const uint64_t dbh = make_desc(bh + j * 32, 16, 1024), dbl = make_desc(bl + j * 32, 16, 1024);
+                        if (!(dbg_flags & 2)) {
+                            ws::umma_tf32_ws<NCTA>(d, dal, dbh, IDESC, (kb | j) ? 1u : 0u);
+                            ws::umma_tf32_ws<NCTA>(d, dah, dbl, IDESC, 1u);
+                            ws::umma_tf32_ws<NCTA>(d, dah, dbh, IDESC, 1u);
+                        } else {
+                            ws::umma_tf32_ws<NCTA>(d, dah, dbh, IDESC, (kb | j) ? 1u : 0u);
+                        }
+                    }
+                    ws::umma_commit_ws<NCTA>(&bar_free[s]);
+                }
+                ws::umma_commit_ws<NCTA>(&bar_acc_full[b]);
+                if (acc_it == 0) WS_STAMP(5);
+                if (acc_it == 1) WS_STAMP(7);
+            }
+        }
+        __syncwarp();
+    } else if (warp == ws::RELAY_WARP) {
+        // ===== relay: wait for this CTA's producers, make their st.shared visible to this SM's async proxy (tensor core), then
+        // arrive on the LEADER's full barrier (for the peer CTA: remotely; the leader's MMA makes this SM read this CTA's stage)
+        if (lane == 0) {
+            uint32_t it = 0;
+            for (int tile = cluster_id; tile < n_tiles; tile += n_clusters)
+                for (int kb = 0; kb < nslab; ++kb, ++it) {
+                    const uint32_t s = it % NST, ph = (it / NST) & 1u;
+                    ws::mbar_wait_ws<NCTA>(&bar_staged[s], ph);
+                    asm volatile("fence.proxy.async.shared::cta;" ::: "memory");
+                    ws::mbar_arrive_cluster(full_leader[s]);
+                }
+        }
+        __syncwarp();
+    } else {
+        // ===== epilogue warps: TMEM -> registers -> smem transpose -> bias / act / act' -> coalesced global =====
+        const int ew = warp - ws::EPI_WARP0;
+        const int lane_q = warp & 3, col_half = ew >> 2;     // a warp reaches TMEM lanes 32 * (warp id % 4) .. + 31 only
+        uint32_t acc_it = 0;
+        for (int tile = cluster_id; tile < n_tiles; tile += n_clusters, ++acc_it) {
+            const uint32_t b = acc_it & 1u, aph = (acc_it >> 1) & 1u;
+            const int m0 = ((tile / tiles_n) * NCTA + (int)rank) * BM, n0 = (tile % tiles_n) * BN;
+            ws::mbar_wait_ws<NCTA>(&bar_acc_full[b], aph);
+            if (ew == 0 && lane == 0 && acc_it < 2) WS_STAMP(12 + 2 * acc_it);
+            asm volatile("tcgen05.fence::after_thread_sync;" ::: "memory");
+            EpiArgs ea;
+            ea.scr = smem_base + NST * C::STAGE_BYTES + (uint32_t)ew * 4096u;
+            ea.tmem_row = tmem_d + b * (uint32_t)BN + ((uint32_t)(lane_q * 32) << 16);
+            ea.lane = lane;
+            ea.c_begin = col_half * (BN / 2); ea.c_end = (col_half + 1) * (BN / 2);
+            ea.m_base = m0 + lane_q * 32; ea.n0 = n0; ea.C = p.C; ea.have_acc = true; ea.dbg = nullptr;
+            if (p.H == nullptr) {
+                if (p.act == GYMRL_ACT_TANH) epilogue_chunks<EPI_TANH>(p, ea);
+                else if (p.act == GYMRL_ACT_RELU) epilogue_chunks<EPI_RELU>(p, ea);
+                else epilogue_chunks<EPI_PLAIN>(p, ea);
+            } else if (p.act == GYMRL_ACT_NONE && p.act_in == GYMRL_ACT_TANH) {
+                epilogue_chunks<EPI_DTANH>(p, ea);
+            } else if (p.act == GYMRL_ACT_NONE && p.act_in == GYMRL_ACT_RELU) {
+                epilogue_chunks<EPI_DRELU>(p, ea);
+            } else {
+                epilogue_chunks<EPI_GENERIC>(p, ea);
+            }
+            asm volatile("tcgen05.fence::before_thread_sync;" ::: "memory");
+            __syncwarp();
+            if (lane == 0) ws::mbar_arrive_cluster(acc_empty_leader[b]);
+            if (ew == 0 && lane == 0 && acc_it < 2) WS_STAMP(13 + 2 * acc_it);
+        }
+    }
+    asm volatile("tcgen05.fence::before_thread_sync;" ::: "memory");
+    if (NCTA == 2) ws::cluster_sync_all(); else __syncthreads();
+    if (t == 0) WS_STAMP(2);
+    if (warp == ws::MMA_WARP) {
+        if (NCTA == 2) asm volatile("tcgen05.dealloc.cta_group::2.sync.aligned.b32 %0, %1;" ::"r"(tmem_d), "n"(512) : "memory");
+        else asm volatile("tcgen05.dealloc.cta_group::1.sync.aligned.b32 %0, %1;" ::"r"(tmem_d), "n"(512) : "memory");
+    }
+}
+
+// ---- ws host side -----------------------------------------------------------------------------------------------
+#include "wimages.cuh"
+typedef CUresult (*PFN_encodeTiled)(CUtensorMap*, CUtensorMapDataType, cuuint32_t, void*, const cuuint64_t*, const cuuint64_t*,
+                                    const cuuint32_t*, const cuuint32_t*, CUtensorMapInterleave, CUtensorMapSwizzle,
+                                    CUtensorMapL2promotion, CUtensorMapFloatOOBfill);
+static PFN_encodeTiled get_encode_tiled() {
+    static PFN_encodeTiled fn = [] {
+        void* f = nullptr;
+        cudaDriverEntryPointQueryResult q;
+        if (cudaGetDriverEntryPoint("cuTensorMapEncodeTiled", &f, cudaEnableDefault, &q) != cudaSuccess || q != cudaDriverEntryPointSuccess) f = nullptr;
+        return reinterpret_cast<PFN_encodeTiled>(f);
+    }();
+    return fn;
+}
+
+// 0 = off, 1 = single-CTA tiles (debug / A-B), 2 = CTA pairs (default)
+static int ws_mode() {
+    static const int m = [] { const char* e = getenv("GYMRL_TC_WS"); return e ? atoi(e) : 2; }();
+    return m;
+}
+
+static unsigned long long g_ws_launches = 0;
+extern "C" unsigned long long gymrl_debug_ws_launches(void) { return g_ws_launches; }   // developer probe (tests: the ws path really ran)
+
+template <int NCTA>
+static int launch_ws(const TcGemmParams& p, const float* b_hi, long long img_stride, int b_rows_total, cudaStream_t s) {
+    using C = ws::Cfg<NCTA>;
+    PFN_encodeTiled enc = get_encode_tiled();
+    if (!enc) GYMRL_FAIL(GYMRL_ECUDA, "cuTensorMapEncodeTiled is not available from this driver");
+    CUtensorMap map;
+    const cuuint64_t dims[3] = {(cuuint64_t)p.K, (cuuint64_t)b_rows_total, 2};
+    const cuuint64_t strides[2] = {(cuuint64_t)p.K * sizeof(float), (cuuint64_t)img_stride * sizeof(float)};
+    const cuuint32_t box[3] = {32, (cuuint32_t)C::B_ROWS, 2};
+    const cuuint32_t estr[3] = {1, 1, 1};
+    const CUresult r = enc(&map, CU_TENSOR_MAP_DATA_TYPE_FLOAT32, 3, const_cast<float*>(b_hi), dims, strides, box, estr,
+                           CU_TENSOR_MAP_INTERLEAVE_NONE, CU_TENSOR_MAP_SWIZZLE_128B, CU_TENSOR_MAP_L2_PROMOTION_L2_128B,
+                           CU_TENSOR_MAP_FLOAT_OOB_FILL_NONE);
+    if (r != CUDA_SUCCESS) GYMRL_FAIL(GYMRL_ECUDA, "cuTensorMapEncodeTiled failed (%d)", (int)r);
+    static bool configured = false;
+    if (!configured) {
+        cudaError_t e = cudaFuncSetAttribute(gemm3x_ws_kernel<NCTA>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)C::SMEM);
+        if (e != cudaSuccess) GYMRL_FAIL(GYMRL_ECUDA, "cudaFuncSetAttribute(smem=%zu) failed: %s", C::SMEM, cudaGetErrorString(e));
+        configured = true;
+    }
+    const int tiles_m = ceil_div(p.M, ws::BM * NCTA), tiles_n = p.N / ws::BN;
+    const int n_tiles = tiles_m * tiles_n;
+    cudaLaunchConfig_t cfg;
+    memset(&cfg, 0, sizeof(cfg));
+    cfg.blockDim = dim3(ws::THREADS); cfg.dynamicSmemBytes = C::SMEM; cfg.stream = s;
+    cudaLaunchAttribute attr[2];
+    int na = 0;
+    if (NCTA == 2) {
+        attr[na].id = cudaLaunchAttributeClusterDimension;
+        attr[na].val.clusterDim.x = 2; attr[na].val.clusterDim.y = 1; attr[na].val.clusterDim.z = 1;
+        ++na;
+    }
+    // persistent grid = the number of clusters that can be CO-RESIDENT (not SMs / 2: a GPC with an odd number of usable TPC slots
+    // leaves SMs that cannot host a pair, and a cluster that does not fit waits for a whole wave of persistent CTAs to finish)
+    static int max_clusters = 0;
+    if (max_clusters == 0) {
+        cfg.gridDim = dim3(GYMRL_NUM_SMS / NCTA * NCTA);
+        cfg.attrs = attr; cfg.numAttrs = na;
+        int n = 0;
+        if (NCTA == 2 && cudaOccupancyMaxActiveClusters(&n, gemm3x_ws_kernel<NCTA>, &cfg) == cudaSuccess && n > 0) max_clusters = n;
+        else max_clusters = GYMRL_NUM_SMS / NCTA;
+        (void)cudaGetLastError();
+        if (getenv("GYMRL_TC_VERBOSE")) fprintf(stderr, "[gymrl] gemm3x_ws_kernel<%d>: %d co-resident clusters\n", NCTA, max_clusters);
+    }
+    int clusters = max_clusters < n_tiles ? max_clusters : n_tiles;
+    cfg.gridDim = dim3(clusters * NCTA);
+    if (gymrl_pdl_enabled()) {
+        attr[na].id = cudaLaunchAttributeProgrammaticStreamSerialization;
+        attr[na].val.programmaticStreamSerializationAllowed = 1;
+        ++na;
+    }
+    cfg.attrs = attr; cfg.numAttrs = na;
+    TcGemmParams pk = p;
+    static const int dbg = [] { const char* e = getenv("GYMRL_TC_WS_DBG"); return e ? atoi(e) : 0; }();
+    pk.bn_max = dbg;
+    cudaError_t e = cudaLaunchKernelEx(&cfg, gemm3x_ws_kernel<NCTA>, pk, map, tiles_m, tiles_n);
+    if (e != cudaSuccess) GYMRL_FAIL(GYMRL_ECUDA, "launch of gemm3x_ws_kernel<%d> failed: %s", NCTA, cudaGetErrorString(e));
+    gymrl_count_launch();
+    ++g_ws_launches;
+    return GYMRL_OK;
+}
+
+// The warp-specialised kernel takes the GEMM when B is a registered weight matrix (pre-split images exist), A is K-major and
+// ungathered, the output is at least 256 columns wide in whole tiles and there are enough tiles to occupy the chip.
+static bool ws_try_launch(const TcGemmParams& p, bool a_kmajor, bool b_kmajor, int splits, cudaStream_t s, int* rc) {
+    const int mode = ws_mode();
+    if (mode == 0 || !a_kmajor || splits != 1 || p.a_rows || p.b_rows || p.N % ws::BN != 0 || p.K % 32 != 0 || p.K < 64) return false;
+    if (p.ldb != (b_kmajor ? p.K : p.N)) return false;
+    const int ncta = mode == 1 ? 1 : 2;
+    const long long tiles = (long long)ceil_div(p.M, ws::BM * ncta) * (p.N / ws::BN);
+    // Measured (tools/ws_gemm_bench.py, M = 16384, in a CUDA graph): with >= 2 tiles per CTA pair the overlapped epilogue wins
+    // (N = 512 forward: 32.3 us vs 35.9 us); with a single tile per pair nothing overlaps and the one-tile-per-CTA kernel's
+    // shorter set-up wins (N = 256: 20.9 vs 19.6 us).  GYMRL_TC_WS_MIN_TILES overrides the threshold (A/B runs).
+    const char* mt_env = getenv("GYMRL_TC_WS_MIN_TILES");     // read per call: the test-suite flips it inside one process
+    const long long min_tiles = mt_env ? atoll(mt_env) : 0ll;
+    const long long need = min_tiles > 0 ? min_tiles : (ncta == 2 ? 100 : 200);
+    if (tiles < need) return false;
+    const float* hi = nullptr;
+    long long stride = 0;
+    // forward: B = W [N][K];  backward-input: B = W [K][N] read as W^T [N][K] from the transposed images
+    if (!(b_kmajor ? wimg_lookup(p.B, p.N, p.K, false, &hi, &stride) : wimg_lookup(p.B, p.K, p.N, true, &hi, &stride))) return false;
+    *rc = ncta == 2 ? launch_ws<2>(p, hi, stride, p.N, s) : launch_ws<1>(p, hi, stride, p.N, s);
+    return true;
+}
+
 // ---- host side ------------------------------------------------------------------------------------------
 template <int BN, bool AK, bool BKM>
 static int launch_tc(const TcGemmParams& p, int splits, cudaStream_t s) {
@@ -736,6 +1196,10 @@ bool tc_gemm_supported(const TcGemmParams& p, bool a_kmajor, bool b_kmajor) {
 }
 
 int tc_gemm_launch(const TcGemmParams& p, bool a_kmajor, bool b_kmajor, int splits, cudaStream_t s) {
+    {
+        int rc = GYMRL_OK;
+        if (ws_try_launch(p, a_kmajor, b_kmajor, splits, s, &rc)) return rc;
+    }
     // widest tile that still gives (nearly) every SM a CTA: the rollout's M = 4096 forward would otherwise run 32 CTAs
     // on 148 SMs.  (tc_gemm_supported guarantees N % 64 == 0.)
     const long long mt = (long long)ceil_div(p.M, 128) * splits;

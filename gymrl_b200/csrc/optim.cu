@@ -11,6 +11,7 @@
 //  - gymrl_polyak: target <- tau*source + (1-tau)*target.
 //  - gymrl_random_permutation: bijective mixing network + cycle walking (no sort, O(1) per index).
 #include "common.cuh"
+#include "wimages.cuh"
 
 void gymrl_count_launch(int n = 1);
 
@@ -94,6 +95,7 @@ extern "C" int gymrl_adam_step(float* d_param, const float* d_grad, float* d_exp
     adam_post_kernel<<<1, 1, 0, s>>>(d_step, const_cast<double*>(d_sumsq));
     gymrl_count_launch(2);
     GYMRL_LAUNCH_CHECK("adam_step");
+    wimg_refresh_if_registered(d_param, s);     // pre-split tf32 images of the weights follow every parameter write
     return GYMRL_OK;
 }
 
@@ -159,6 +161,7 @@ extern "C" int gymrl_clip_adam_step(float* d_param, const float* d_grad, float* 
                      beta1, beta2, eps, d_step, d_sumsq_partials, n_partials, max_norm, grad_scale, d_done_counter);
     gymrl_count_launch();
     GYMRL_LAUNCH_CHECK("clip_adam_step");
+    wimg_refresh_if_registered(d_param, as_stream(stream));
     return GYMRL_OK;
 }
 
@@ -176,6 +179,7 @@ extern "C" int gymrl_polyak(float* d_target, const float* d_source, long long n,
     polyak_kernel<<<(int)blocks, threads, 0, as_stream(stream)>>>(d_target, d_source, n, tau);
     gymrl_count_launch();
     GYMRL_LAUNCH_CHECK("polyak");
+    wimg_refresh_if_registered(d_target, as_stream(stream));
     return GYMRL_OK;
 }
 

@@ -56,6 +56,33 @@ class FlatParams:
         self.module = module
         self.flat, self.grad, self.views = flatten_module(module, order, device)
 
+    # -- pre-split tf32 weight images (TMA operand of the warp-specialised GEMM, csrc/wimages.cu) ---------------------------------
+    def enable_weight_images(self, matrices):
+        """matrices: [(first_name, last_name, rows, cols)] spans of consecutive parameters that are used as one [rows, cols] GEMM
+        operand (a single parameter: first == last).  The library keeps the images current on every optimiser step / Polyak
+        update of this buffer; refresh_views() and refresh_weight_images() cover host-side writes."""
+        mats = []
+        for first, last, rows, cols in matrices:
+            o0 = self.views[first][0]
+            o1, shape1 = self.views[last]
+            n1 = 1
+            for s_ in shape1:
+                n1 *= s_
+            assert o1 + n1 - o0 == rows * cols and o0 % 4 == 0, f"{first}..{last} is not a contiguous, 16-byte aligned [{rows}, {cols}] matrix"
+            mats.append((o0, rows, cols))
+        self._wimages = ops.weight_images_register(self.flat, mats)
+
+    def refresh_weight_images(self):
+        if getattr(self, "_wimages", None) is not None:
+            ops.weight_images_refresh(self.flat)
+
+    def __del__(self):
+        try:
+            if getattr(self, "_wimages", None) is not None:
+                ops.weight_images_unregister(self.flat)
+        except Exception:
+            pass
+
     def p(self, name: str) -> torch.Tensor:
         o, shape = self.views[name]
         k = 1
@@ -105,6 +132,7 @@ class FlatParams:
                 self.flat[o:o + k].copy_(p.data.reshape(-1))
                 p.data = self.flat[o:o + k].view(shape)
             p.grad = self.grad[o:o + k].view(shape)
+        self.refresh_weight_images()
 
 
 class FusedAdam:

@@ -202,6 +202,27 @@ def ppo_loss(logits, value, action, logp_old, adv, ret, cfg: _ffi.PPOCfg, *, row
     return dlogits, dvalue, metrics
 
 
+def weight_images_register(flat, mats):
+    """Allocate and register pre-split tf32 images for the weight matrices `mats` = [(offset, rows, cols), ...] of the flat
+    parameter buffer (csrc/wimages.cu): dense layers on those matrices then run the TMA-fed warp-specialised tensor-core GEMM.
+    Returns the image tensor (keep it alive as long as the registration)."""
+    import ctypes as C_
+    n = flat.numel()
+    images = torch.empty(4 * n, device=flat.device, dtype=f32)
+    arr = (C_.c_int * (3 * len(mats)))(*[int(v) for m in mats for v in m])
+    check(load().gymrl_weight_images_register(ptr(flat, f32), n, ptr(images, f32), arr, len(mats)))
+    check(load().gymrl_weight_images_refresh(ptr(flat, f32), stream_ptr()))
+    return images
+
+
+def weight_images_refresh(flat):
+    check(load().gymrl_weight_images_refresh(ptr(flat, f32), stream_ptr()))
+
+
+def weight_images_unregister(flat):
+    load().gymrl_weight_images_unregister(ptr(flat, f32))
+
+
 def seq_gather(src, seq_index, seq_len, out=None):
     """out[b, t] = src.view(S, L, -1)[seq_index[b], t]  (ppo_lstm_lunarlander.py:682-707).  src: [S * L, D] rows."""
     src2 = src.reshape(src.shape[0], -1)

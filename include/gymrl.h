@@ -281,6 +281,17 @@ int gymrl_comm_n_partials(const gymrl_comm* comm);
 int gymrl_comm_allreduce_sumsq(gymrl_comm* comm, const float* d_grad, float* d_reduced, double* d_sumsq_partials, void* stream);
 int gymrl_comm_destroy(gymrl_comm* comm);
 
+/* Pre-split tf32 images of weight matrices (csrc/wimages.cu): the TMA-fed B operand of the warp-specialised tensor-core GEMM.
+ * d_images: 4 * n_floats floats [hi | lo | hi^T | lo^T]; mats: host int[n_mats][3] = {offset, rows, cols} of the matrices
+ * (torch.nn.Linear [out][in] layout, offsets multiples of 4) whose dense layers should take that path.  After registration
+ * gymrl_linear_forward / gymrl_linear_backward_input recognise those matrices by address + shape; gymrl_adam_step,
+ * gymrl_clip_adam_step and gymrl_polyak re-split the images of a registered buffer after writing it.  Call
+ * gymrl_weight_images_refresh after any other write to the parameters (initialisation, load_state_dict, broadcast) and
+ * gymrl_weight_images_unregister before freeing the buffer. */
+int gymrl_weight_images_register(const float* d_flat, long long n_floats, float* d_images, const int* mats, int n_mats);
+int gymrl_weight_images_refresh(const float* d_flat, void* stream);
+int gymrl_weight_images_unregister(const float* d_flat);
+
 /* target = tau * source + (1 - tau) * target   (rainbow_dqn_cartpole.py:347-352,
  * sac_pendulum.py:194-199, td3_pendulum.py:150-155); tau = 1 is the hard copy of dqn_cartpole.py:193. */
 int gymrl_polyak(float* d_target, const float* d_source, long long n, float tau, void* stream);
