@@ -48,9 +48,11 @@ SIGNATURES = {
     "gymrl_env_get_state": (c_int, [_P, _P, _P]),
     "gymrl_env_set_state": (c_int, [_P, _P, _P]),
     "gymrl_env_set_profile": (c_int, [_P, _P]),
+    "gymrl_env_overflow_count": (c_int, [_P, _P, _P]),
     "gymrl_env_episode_stats": (c_int, [_P, c_int, _P, _P, _P, _P]),
     "gymrl_sample_categorical": (c_int, [_P, c_int, _P, _P, _P, _P, _P, c_int, _P, c_int, c_int, c_u64, c_u64, c_u32, _P, c_int, _P]),
     "gymrl_select_eps_greedy": (c_int, [_P, c_int, _P, c_int, c_int, c_float, c_u64, c_u64, c_u32, _P, _P]),
+    "gymrl_select_eps_greedy_dev": (c_int, [_P, c_int, _P, c_int, c_int, _P, c_u64, c_u64, c_u32, _P, _P]),
     "gymrl_sample_tanh_gaussian": (c_int, [_P, _P, c_int, _P, _P, _P, _P, c_int, c_int, c_float, c_float, c_float,
                                            c_u64, c_u64, c_u32, _P, c_int, _P]),
     "gymrl_add_gaussian_noise_clip": (c_int, [_P, _P, _P, c_int, c_int, c_float, c_float, c_float, c_u64, c_u64, c_u32, _P, _P]),

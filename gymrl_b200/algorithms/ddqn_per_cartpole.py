@@ -22,6 +22,7 @@ import torch
 import torch.nn as nn
 
 from .. import _ffi, ops, ops_offpolicy as off
+from ..graphs import HostScheduledLockstep
 from ..mlp import Chain
 from ..nn import FlatParams, FusedAdam
 
@@ -53,6 +54,7 @@ class Config:
         # ---- engine extras ----
         self.num_envs = 1
         self.max_locksteps = None
+        self.use_cuda_graph = True   # lockstep(): act -> env step -> store -> update as ONE captured graph
         self.target_sync_updates = 200
 
 
@@ -132,10 +134,15 @@ class PrioritizedReplayBuffer:
         t = lambda x, dt: torch.as_tensor(np.asarray(x), device=dev).to(dt)
         self.store(t(s, f32).reshape(1, -1), t([a], i32).reshape(1, 1), t([r], f32), t(s2, f32).reshape(1, -1), t([bool(d)], u8))
 
-    def sample(self, batch_size: int = None, uniforms=None, seed=0, draw=0, draw_base=None):
-        """Returns (data indices [B] int32, IS weights [B] float32) — device tensors; beta advances per call (ref :130)."""
+    def advance_beta(self):
+        """beta += beta_increment per sample() call (ref :125-130): host value -> device slot (outside any captured graph)."""
         self.cfg.beta = min(1.0, self.cfg.beta + self.cfg.beta_increment)
         self.beta_t.fill_(self.cfg.beta)
+
+    def sample(self, batch_size: int = None, uniforms=None, seed=0, draw=0, draw_base=None, advance_beta=True):
+        """Returns (data indices [B] int32, IS weights [B] float32) — device tensors; beta advances per call (ref :130)."""
+        if advance_beta:
+            self.advance_beta()
         self.tree.sample(int(batch_size or self.cfg.batch_size), self.ring.state, self.beta_t, uniforms=uniforms, out_idx=self.batch_index,
                          out_w=self.is_weight, seed=seed, draw=draw, draw_base=draw_base)
         return self.batch_index, self.is_weight
@@ -148,7 +155,7 @@ class PrioritizedReplayBuffer:
         return len(self.ring)
 
 
-class DDQNPERTrainer:
+class DDQNPERTrainer(HostScheduledLockstep):
     NET = QNetwork
 
     def __init__(self, config: Config):
@@ -176,6 +183,12 @@ class DDQNPERTrainer:
         self.loss_acc = torch.zeros(2, device=dev, dtype=f32)
         self.action = torch.zeros(N, device=dev, dtype=i32)
         self.done = torch.zeros(N, device=dev, dtype=u8)
+        self.cur = torch.zeros(N, D, device=dev, dtype=f32)
+        self.eps_t = torch.zeros(1, device=dev, dtype=f32)        # host-scheduled epsilon in a device slot
+        self.ctr_act = torch.zeros(1, device=dev, dtype=i32)      # device mirrors of sample_count / update_count
+        self.ctr_upd = torch.zeros(1, device=dev, dtype=i32)
+        self.graph_launches = 0
+        self._episodes_synced = 0
         self.epsilon = cfg.epsilon_start
         self.sample_count = 0
         self.update_count = 0
@@ -197,7 +210,10 @@ class DDQNPERTrainer:
         """Vector select_action: one epsilon (decayed once per call, ref :180-186) for the whole lockstep."""
         eps = 0.0 if deterministic else self.get_epsilon()
         q = self.q_act.forward(obs, self.N)
-        return ops.select_eps_greedy(self._greedy_columns(q), eps, seed=self.seed, draw=self.sample_count, action=self.action)
+        a = ops.select_eps_greedy(self._greedy_columns(q), eps, seed=self.seed, draw=1, draw_base=self.ctr_act, action=self.action)
+        if not deterministic:
+            ops.counter_add(self.ctr_act, 1)
+        return a
 
     @torch.no_grad()
     def select_action(self, state: np.ndarray, deterministic: bool = False) -> int:
@@ -209,12 +225,20 @@ class DDQNPERTrainer:
 
     def update(self, uniforms=None) -> float:
         """One update (ref :206-247).  `uniforms` [B] float64 lets the parity test feed the reference's random.uniform draws."""
-        cfg, B, A, mem = self.cfg, int(self.cfg.batch_size), self.action_dim, self.memory
-        if len(mem) < B:
+        if len(self.memory) < int(self.cfg.batch_size):
             return 0.0
         self.update_count += 1
+        self.memory.advance_beta()
+        self.optimizer.sync_lr()
+        self._update_device(uniforms)
+        return self.loss_acc[0]
+
+    def _update_device(self, uniforms=None):
+        """Device side of update(), capture-safe: PER beta and the learning rate sit in device slots, the stratified draws
+        come from a device counter."""
+        cfg, B, A, mem = self.cfg, int(self.cfg.batch_size), self.action_dim, self.memory
         ring = mem.ring
-        idx, w = mem.sample(B, uniforms=uniforms, seed=self.seed, draw=self.update_count)
+        idx, w = mem.sample(B, uniforms=uniforms, seed=self.seed, draw=1, draw_base=self.ctr_upd, advance_beta=False)
         q = self.q_upd.forward(ring.obs, B, row_index=idx)
         qo = self.q_nxt.forward(ring.next_obs, B, row_index=idx)
         qt = self.q_tgt.forward(ring.next_obs, B, row_index=idx)
@@ -226,33 +250,66 @@ class DDQNPERTrainer:
                      td_error=self.td, loss_acc=self.loss_acc)
         mem.update_priorities(idx, self.td)                      # ref :236-237 (before the optimizer step)
         self.q_upd.backward(ring.obs, B, row_index=idx)
-        self.optimizer.step(clamp=1.0)                           # param.grad.clamp_(-1, 1) then Adam (ref :241-245)
-        return self.loss_acc[0]
+        self.optimizer.launch(clamp=1.0)                         # param.grad.clamp_(-1, 1) then Adam (ref :241-245)
+        ops.counter_add(self.ctr_upd, 1)
+
+    # ---------------------------------------------------------------- one lockstep (ref train() loop body)
+    def _lockstep_ready(self) -> bool:
+        return len(self.memory) + self.N >= int(self.cfg.batch_size)
+
+    def _before_lockstep(self):
+        self.eps_t.fill_(float(self.get_epsilon()))
+        if self._lockstep_ready():
+            self.memory.advance_beta()                           # beta += beta_increment per sample() call (ref :125-130)
+        self.optimizer.sync_lr()
+
+    def _lockstep_body(self):
+        mem, cur = self.memory, self.cur
+        q = self.q_act.forward(cur, self.N)
+        ops.select_eps_greedy(self._greedy_columns(q), self.eps_t, seed=self.seed, draw=1, draw_base=self.ctr_act, action=self.action)
+        ops.counter_add(self.ctr_act, 1)
+        obs, r, te, tr, nobs = self.env.step(self.action, done=self.done)
+        mem.store(cur, self.action.view(-1, 1), r, nobs, self.done)
+        if len(mem) >= int(self.cfg.batch_size):
+            self._update_device()
+        cur.copy_(obs)
+
+    def _host_mirrors(self):
+        return self.memory.ring._size_host
+
+    def _set_host_mirrors(self, m):
+        self.memory.ring._size_host = m
+
+    def _advance_host_mirrors(self):
+        ring = self.memory.ring
+        ring._size_host = min(ring.capacity, ring._size_host + self.N)
+
+    def _after_lockstep(self):
+        cfg = self.cfg
+        if len(self.memory) >= int(cfg.batch_size):
+            self.update_count += 1
+        if self.N > 1:
+            if self.update_count and self.update_count % cfg.target_sync_updates == 0:
+                self.sync_target()
+        elif bool(self.done.item()):
+            self._episodes_synced += 1
+            if self._episodes_synced % cfg.target_update_freq == 0:
+                self.sync_target()
 
     def sync_target(self):
         ops.polyak(self.fp_t.flat, self.fp.flat, 1.0)
 
     def train(self):
         print("Starting training...")
-        cfg, env, mem = self.cfg, self.env, self.memory
-        cur = env.reset().clone()
+        cfg, env = self.cfg, self.env
+        env.reset(out=self.cur)
         max_lock = cfg.max_locksteps or int(cfg.max_episodes * 500 / self.N)
         last_total, t0 = 0, time.time()
         for step in range(max_lock):
-            a = self.act(cur)
-            obs, r, te, tr, nobs = env.step(a, done=self.done)
-            mem.store(cur, a.view(-1, 1), r, nobs, self.done)
-            self.update()
-            cur.copy_(obs)
-            if self.N > 1 and self.update_count and self.update_count % cfg.target_sync_updates == 0:
-                self.sync_target()
+            self.lockstep()
             if self.N == 1 or step % 50 == 49:
                 avg, _, total = env.episode_stats(100)
                 if total != last_total:
-                    if self.N == 1:
-                        for e in range(last_total, total):
-                            if (e + 1) % cfg.target_update_freq == 0:
-                                self.sync_target()
                     self.episode_rewards.extend([avg] * min(total - last_total, 100))
                     last_total = total
                     if self.N > 1 or total % 10 == 0:

@@ -20,6 +20,7 @@ import torch
 import torch.nn as nn
 
 from .. import _ffi, ops, ops_offpolicy as off
+from ..graphs import HostScheduledLockstep
 from ..mlp import Chain
 from ..nn import FlatParams, FusedAdam, layer_init
 
@@ -46,6 +47,7 @@ class Config:
         self.num_envs = 1
         self.target_sync_updates = 128
         self.max_locksteps = None      # stop criterion for vectorised runs (default: max_episodes * max_steps / num_envs)
+        self.use_cuda_graph = True     # lockstep(): act -> env step -> store -> update as ONE captured graph per lockstep
 
 
 class QNetwork(nn.Module):
@@ -80,7 +82,7 @@ class ReplayBuffer(off.ReplayRing):
                 self.next_obs[idx].cpu().numpy(), self.done[idx].cpu().numpy().astype(bool))
 
 
-class DQNTrainer:
+class DQNTrainer(HostScheduledLockstep):
     def __init__(self, config: Config):
         _ffi.require_cuda()
         self.cfg = cfg = config
@@ -104,6 +106,12 @@ class DQNTrainer:
         self.loss_acc = torch.zeros(2, device=self.device, dtype=f32)
         self.action = torch.zeros(N, device=self.device, dtype=i32)
         self.done = torch.zeros(N, device=self.device, dtype=u8)
+        self.cur = torch.zeros(N, D, device=self.device, dtype=f32)           # current observations of the lockstep
+        self.eps_t = torch.zeros(1, device=self.device, dtype=f32)            # host-scheduled epsilon in a device slot
+        self.ctr_act = torch.zeros(1, device=self.device, dtype=i32)          # device mirrors of sample_count / update_count
+        self.ctr_upd = torch.zeros(1, device=self.device, dtype=i32)
+        self.graph_launches = 0
+        self._episodes_synced = 0
         self.epsilon = cfg.epsilon_start
         self.sample_count = 0
         self.update_count = 0
@@ -122,7 +130,10 @@ class DQNTrainer:
         """Vector select_action: one epsilon (decayed once per call, ref :117-122) for the whole lockstep."""
         eps = 0.0 if deterministic else self.get_epsilon()
         q = self.q_act.forward(obs, self.N)
-        return ops.select_eps_greedy(q, eps, seed=self.seed, draw=self.sample_count, action=self.action)
+        a = ops.select_eps_greedy(q, eps, seed=self.seed, draw=1, draw_base=self.ctr_act, action=self.action)
+        if not deterministic:
+            ops.counter_add(self.ctr_act, 1)
+        return a
 
     @torch.no_grad()
     def select_action(self, state: np.ndarray, deterministic: bool = False) -> int:
@@ -135,19 +146,65 @@ class DQNTrainer:
         return int(self.act(obs, deterministic).item())
 
     def update(self, idx: torch.Tensor = None) -> float:
-        cfg, B, mem = self.cfg, int(self.cfg.batch_size), self.memory
-        if len(mem) < B:
+        if len(self.memory) < int(self.cfg.batch_size):
             return 0.0
         self.update_count += 1
+        self.optimizer.sync_lr()
+        self._update_device(idx)
+        return self.loss_acc[0]                  # device scalar; .item() only when the caller wants it
+
+    def _update_device(self, idx: torch.Tensor = None):
+        """The device side of update() (ref :135-168), capture-safe: the sampling draw comes from a device counter."""
+        cfg, B, mem = self.cfg, int(self.cfg.batch_size), self.memory
         if idx is None:
-            idx = mem.sample_indices(B, seed=self.seed, draw=self.update_count, out=self.idx)
+            idx = mem.sample_indices(B, seed=self.seed, draw=1, draw_base=self.ctr_upd, out=self.idx)
         q = self.q_upd.forward(mem.obs, B, row_index=idx)
         qn = self.q_tgt.forward(mem.next_obs, B, row_index=idx)
         self.loss_acc.zero_()
         off.dqn_loss(q, qn, mem.action, mem.reward, mem.done, cfg.gamma, row_index=idx, dq=self.q_upd.dout, loss_acc=self.loss_acc)
         self.q_upd.backward(mem.obs, B, row_index=idx)
-        self.optimizer.step(clamp=1.0)           # param.grad.clamp_(-1, 1) then Adam (ref :161-166)
-        return self.loss_acc[0]                  # device scalar; .item() only when the caller wants it
+        self.optimizer.launch(clamp=1.0)         # param.grad.clamp_(-1, 1) then Adam (ref :161-166)
+        ops.counter_add(self.ctr_upd, 1)
+
+    # ---------------------------------------------------------------- one lockstep (ref train() loop body :178-191)
+    def _lockstep_ready(self) -> bool:
+        return len(self.memory) + self.N >= int(self.cfg.batch_size)
+
+    def _before_lockstep(self):
+        self.eps_t.fill_(float(self.get_epsilon()))      # one decay per select_action call (ref :117-122)
+        self.optimizer.sync_lr()
+
+    def _lockstep_body(self):
+        mem, cur = self.memory, self.cur
+        q = self.q_act.forward(cur, self.N)
+        ops.select_eps_greedy(q, self.eps_t, seed=self.seed, draw=1, draw_base=self.ctr_act, action=self.action)
+        ops.counter_add(self.ctr_act, 1)
+        obs, r, te, tr, nobs = self.env.step(self.action, done=self.done)
+        mem.store(cur, self.action.view(-1, 1), r, nobs, self.done)
+        if len(mem) >= int(self.cfg.batch_size):
+            self._update_device()
+        cur.copy_(obs)
+
+    def _host_mirrors(self):
+        return self.memory._size_host
+
+    def _set_host_mirrors(self, m):
+        self.memory._size_host = m
+
+    def _advance_host_mirrors(self):
+        self.memory._size_host = min(self.memory.capacity, self.memory._size_host + self.N)
+
+    def _after_lockstep(self):
+        cfg = self.cfg
+        if len(self.memory) >= int(cfg.batch_size):
+            self.update_count += 1
+        if self.N > 1:
+            if self.update_count and self.update_count % cfg.target_sync_updates == 0:
+                self.sync_target()
+        elif bool(self.done.item()):      # reference schedule: hard sync every `target_update_freq` finished episodes (ref :193-194)
+            self._episodes_synced += 1
+            if self._episodes_synced % cfg.target_update_freq == 0:
+                self.sync_target()
 
     def sync_target(self):
         ops.polyak(self.fp_t.flat, self.fp.flat, 1.0)
@@ -158,26 +215,15 @@ class DQNTrainer:
 
     def train(self):
         print("Starting training...")
-        cfg, env, mem = self.cfg, self.env, self.memory
-        obs = env.reset()
-        cur = obs.clone()
+        cfg, env = self.cfg, self.env
+        env.reset(out=self.cur)
         max_lock = cfg.max_locksteps or int(cfg.max_episodes * cfg.max_steps / self.N)
         last_total, t0 = 0, time.time()
         for step in range(max_lock):
-            a = self.act(cur)
-            obs, r, te, tr, nobs = env.step(a, done=self.done)
-            mem.store(cur, a.view(-1, 1), r, nobs, self.done)
-            self.update()
-            cur.copy_(obs)
-            if self.N > 1 and self.update_count and self.update_count % cfg.target_sync_updates == 0:
-                self.sync_target()
+            self.lockstep()
             if self.N == 1 or step % 50 == 49:
                 avg, total = self._episode_stats()
                 if total != last_total:
-                    if self.N == 1:
-                        for e in range(last_total, total):
-                            if (e + 1) % cfg.target_update_freq == 0:
-                                self.sync_target()
                     self.episode_rewards.extend([avg] * min(total - last_total, 100))
                     last_total = total
                     if self.N > 1 or total % 10 == 0:

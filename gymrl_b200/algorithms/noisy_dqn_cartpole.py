@@ -21,6 +21,7 @@ import torch
 import torch.nn as nn
 
 from .. import _ffi, ops, ops_offpolicy as off
+from ..graphs import HostScheduledLockstep
 from ..mlp import Chain
 from ..nn import FlatParams, FusedAdam
 from .rainbow_dqn_cartpole import NoisyLinear
@@ -46,6 +47,7 @@ class Config:
         # ---- engine extras ----
         self.num_envs = 1
         self.max_locksteps = None
+        self.use_cuda_graph = True   # lockstep(): act -> env step -> store -> update as ONE captured graph
 
 
 class NoisyDuelingQNetwork(nn.Module):
@@ -134,7 +136,7 @@ class NoisyDuelingEngine:
             off.noisy_backward(dW, db, e_in, e_out, G(n + ".weight_mu"), G(n + ".weight_sigma"), G(n + ".bias_mu"), G(n + ".bias_sigma"))
 
 
-class NoisyDQNTrainer:
+class NoisyDQNTrainer(HostScheduledLockstep):
     def __init__(self, config: Config):
         _ffi.require_cuda()
         self.cfg = cfg = config
@@ -162,6 +164,8 @@ class NoisyDQNTrainer:
         self.action = torch.zeros(N, device=dev, dtype=i32)
         self.done = torch.zeros(N, device=dev, dtype=u8)
         self.ctr_upd = torch.zeros(1, device=dev, dtype=i32)
+        self.cur = torch.zeros(N, D, device=dev, dtype=f32)
+        self.graph_launches = 0
         self.learn_step = 0
         self.episode_rewards = deque(maxlen=100)
         print(f"Device: {dev}")
@@ -183,9 +187,16 @@ class NoisyDQNTrainer:
 
     def update(self, idx: torch.Tensor = None, xi_cur=None, xi_next=None) -> dict:
         """One update (ref :206-253).  idx / xi_* let the parity test feed the reference's own sample and noise draws."""
-        cfg, B, A, mem = self.cfg, int(self.cfg.batch_size), self.action_dim, self.memory
-        if len(mem) < B:
+        if len(self.memory) < int(self.cfg.batch_size):
             return {}
+        self.optimizer.sync_lr()
+        self._update_device(idx, xi_cur, xi_next)
+        self._after_update()
+        return {"loss": self.loss_acc[0]}
+
+    def _update_device(self, idx=None, xi_cur=None, xi_next=None):
+        """Device side of update(), capture-safe (sampling and noise draws come from device counters)."""
+        cfg, B, A, mem = self.cfg, int(self.cfg.batch_size), self.action_dim, self.memory
         if idx is None:
             idx = mem.sample_indices(B, seed=self.seed, draw=1, draw_base=self.ctr_upd, out=self.idx)
         q = self.net_upd.forward(mem.obs, B, row_index=idx, noisy=True, xi=xi_cur)            # ref :229 (first noise draw)
@@ -196,25 +207,52 @@ class NoisyDQNTrainer:
                      qnext_online=qo[:, :A], vnext_online=qo[:, A:], row_index=idx, dq=self.net_upd.dout[:, :A],
                      dv=self.net_upd.dout[:, A:], td_error=self.td, loss_acc=self.loss_acc)
         self.net_upd.backward(mem.obs, B, row_index=idx)
-        self.optimizer.step()
+        self.optimizer.launch()
         ops.counter_add(self.ctr_upd, 1)
+
+    def _after_update(self):
         self.learn_step += 1
-        if self.learn_step % cfg.target_update_freq == 0:
+        if self.learn_step % self.cfg.target_update_freq == 0:
             ops.polyak(self.fp_t.flat, self.fp.flat, 1.0)     # hard sync (ref :248-249); buffers (epsilon) are not parameters
-        return {"loss": self.loss_acc[0]}
+
+    # ---------------------------------------------------------------- one lockstep (ref train() loop body :255-270)
+    def _lockstep_ready(self) -> bool:
+        return len(self.memory) + self.N >= int(self.cfg.batch_size)
+
+    def _before_lockstep(self):
+        self.optimizer.sync_lr()
+
+    def _lockstep_body(self):
+        mem, cur = self.memory, self.cur
+        out = self.net_act.forward(cur, self.N, noisy=True)
+        ops.select_eps_greedy(out[:, :self.action_dim], 0.0, action=self.action)
+        obs, r, te, tr, nobs = self.env.step(self.action, done=self.done)
+        mem.store(cur, self.action.view(-1, 1), r, nobs, self.done)   # done = terminated or truncated (ref :263-265)
+        if len(mem) >= int(self.cfg.batch_size):
+            self._update_device()
+        cur.copy_(obs)
+
+    def _host_mirrors(self):
+        return self.memory._size_host
+
+    def _set_host_mirrors(self, m):
+        self.memory._size_host = m
+
+    def _advance_host_mirrors(self):
+        self.memory._size_host = min(self.memory.capacity, self.memory._size_host + self.N)
+
+    def _after_lockstep(self):
+        if len(self.memory) >= int(self.cfg.batch_size):
+            self._after_update()
 
     def train(self):
         print("Starting training...")
-        cfg, env, mem = self.cfg, self.env, self.memory
-        cur = env.reset().clone()
+        cfg, env = self.cfg, self.env
+        env.reset(out=self.cur)
         max_lock = cfg.max_locksteps or int(cfg.max_episodes * 500 / self.N)
         t0, last_total = time.time(), 0
         for step in range(max_lock):
-            a = self.act(cur)
-            obs, r, te, tr, nobs = env.step(a, done=self.done)
-            mem.store(cur, a.view(-1, 1), r, nobs, self.done)   # done = terminated or truncated (ref :263-265)
-            self.update()
-            cur.copy_(obs)
+            self.lockstep()
             if step % 100 == 99:
                 avg, _, total = env.episode_stats(100)
                 if total != last_total:

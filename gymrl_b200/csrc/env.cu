@@ -273,7 +273,7 @@ extern "C" int gymrl_env_create(gymrl_env** out, int kind, int n_envs, uint64_t 
     ENV_ALLOC(e->ep_return, n * sizeof(double));
     ENV_ALLOC(e->ring_ret, GYMRL_EP_RING * sizeof(float));
     ENV_ALLOC(e->ring_len, GYMRL_EP_RING * sizeof(int32_t));
-    ENV_ALLOC(e->ring_count, sizeof(unsigned long long));
+    ENV_ALLOC(e->ring_count, 2 * sizeof(unsigned long long));   // [0] finished episodes, [1] LunarLander dropped-manifold events
     if (kind == GYMRL_ENV_LUNARLANDER) {
         int rc = lunar_alloc(e);
         if (rc != GYMRL_OK) { gymrl_env_destroy(e); return rc; }
@@ -354,6 +354,16 @@ extern "C" int gymrl_env_set_profile(gymrl_env* e, long long* d_prof) {
     GYMRL_REQUIRE(e != nullptr, "env is NULL");
     GYMRL_REQUIRE(e->kind == GYMRL_ENV_LUNARLANDER || d_prof == nullptr, "profile counters exist for LunarLander only");
     e->prof = d_prof;
+    return GYMRL_OK;
+}
+
+extern "C" int gymrl_env_overflow_count(gymrl_env* e, uint64_t* count, void* stream) {
+    GYMRL_REQUIRE(e != nullptr && count != nullptr, "NULL argument");
+    unsigned long long c = 0;
+    cudaStream_t s = as_stream(stream);
+    GYMRL_CUDA(cudaMemcpyAsync(&c, e->ring_count + 1, sizeof(c), cudaMemcpyDeviceToHost, s));
+    GYMRL_CUDA(cudaStreamSynchronize(s));
+    *count = c;
     return GYMRL_OK;
 }
 

@@ -85,10 +85,12 @@ extern "C" int gymrl_sample_categorical(const float* d_logits, int ld_logits, co
 }
 
 __global__ void eps_greedy_kernel(const float* __restrict__ q, int ld, int32_t* __restrict__ action, int n, int A,
-                                  float eps, uint64_t seed, uint64_t first_id, uint32_t draw, const uint32_t* __restrict__ draw_base) {
+                                  float eps, uint64_t seed, uint64_t first_id, uint32_t draw, const uint32_t* __restrict__ draw_base,
+                                  const float* __restrict__ eps_dev) {
     const int i = blockIdx.x * blockDim.x + threadIdx.x;
     if (i >= n) return;
     if (draw_base) draw += *draw_base;
+    if (eps_dev) eps = *eps_dev;     // host-scheduled epsilon in a device slot: a captured lockstep graph follows the decay
     const u32x4 r = philox_draw(seed, first_id + i, draw, PHILOX_ACTION);
     int a;
     if (u01_f32(r.x) < eps) {
@@ -110,9 +112,20 @@ extern "C" int gymrl_select_eps_greedy(const float* d_q, int ld_q, int32_t* d_ac
     GYMRL_REQUIRE(d_q && d_action, "NULL q/action");
     GYMRL_REQUIRE(n > 0 && n_actions > 0 && ld_q >= n_actions, "bad shape");
     eps_greedy_kernel<<<ceil_div(n, 128), 128, 0, as_stream(stream)>>>(d_q, ld_q, d_action, n, n_actions, eps, seed,
-                                                                      first_id, draw, d_draw_base);
+                                                                      first_id, draw, d_draw_base, nullptr);
     gymrl_count_launch();
     GYMRL_LAUNCH_CHECK("eps_greedy");
+    return GYMRL_OK;
+}
+
+extern "C" int gymrl_select_eps_greedy_dev(const float* d_q, int ld_q, int32_t* d_action, int n, int n_actions, const float* d_eps,
+                                           uint64_t seed, uint64_t first_id, uint32_t draw, const uint32_t* d_draw_base, void* stream) {
+    GYMRL_REQUIRE(d_q && d_action && d_eps, "NULL q/action/eps");
+    GYMRL_REQUIRE(n > 0 && n_actions > 0 && ld_q >= n_actions, "bad shape");
+    eps_greedy_kernel<<<ceil_div(n, 128), 128, 0, as_stream(stream)>>>(d_q, ld_q, d_action, n, n_actions, 0.0f, seed,
+                                                                      first_id, draw, d_draw_base, d_eps);
+    gymrl_count_launch();
+    GYMRL_LAUNCH_CHECK("eps_greedy_dev");
     return GYMRL_OK;
 }
 

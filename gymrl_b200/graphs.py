@@ -55,3 +55,34 @@ class LockstepGraphs:
         # host mirrors of the counters the device body advanced
         self.act_count, self.total_updates = mirrors[0] + 1, mirrors[1] + 1
         mem._size_host = min(mem.capacity, mirrors[2] + self.N)
+
+
+class HostScheduledLockstep:
+    """Mixin for the value-based off-policy trainers (DQN, NoisyNet DQN, DDQN + PER): `lockstep()` = act -> env step -> store ->
+    update as ONE captured CUDA graph, with the host-side schedules around it:
+
+        _lockstep_ready()   -> True once the body is capture-safe (replay holds a batch)
+        _before_lockstep()  -> write host-scheduled scalars (epsilon, PER beta, learning rate) into their device slots
+        _lockstep_body()    -> the device work (every per-step-varying value read from device memory)
+        _after_lockstep()   -> host mirrors of the device counters + host-scheduled follow-ups (hard target sync)
+        _host_mirrors() / _set_host_mirrors(m)  -> counters the body advances on the host while it is being recorded
+    """
+
+    def lockstep(self):
+        if not getattr(self.cfg, "use_cuda_graph", True) or not self._lockstep_ready():
+            self._before_lockstep()
+            self._lockstep_body()
+            self._after_lockstep()
+            return
+        self._before_lockstep()
+        g = self.__dict__.get("_g_lockstep")
+        if g is None:
+            self._lockstep_body()                       # this lockstep, eagerly (also the warm-up) ...
+            m = self._host_mirrors()
+            self._g_lockstep = capture(self._lockstep_body, warmup=False)    # ... then record one without running it
+            self._set_host_mirrors(m)
+        else:
+            g.replay()
+            self.graph_launches = getattr(self, "graph_launches", 0) + g.n_kernels
+            self._advance_host_mirrors()
+        self._after_lockstep()

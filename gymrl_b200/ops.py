@@ -98,6 +98,12 @@ class VecEnv:
         self._prof = buf
         check(load().gymrl_env_set_profile(self._h, ptr(buf, torch.int64) if buf is not None else None))
 
+    def overflow_count(self) -> int:
+        """LunarLander: touching manifolds dropped because all 8 contact slots of an env copy were taken (see gymrl.h)."""
+        c = C.c_uint64()
+        check(load().gymrl_env_overflow_count(self._h, C.byref(c), stream_ptr()))
+        return int(c.value)
+
     def episode_stats(self, last_k: int = 100) -> Tuple[float, float, int]:
         mr, ml, te = C.c_double(), C.c_double(), C.c_uint64()
         check(load().gymrl_env_episode_stats(self._h, int(last_k), C.byref(mr), C.byref(ml), C.byref(te), stream_ptr()))
@@ -123,8 +129,13 @@ def sample_categorical(logits, noise=None, *, seed=0, first_id=0, draw=0, draw_b
 
 
 def select_eps_greedy(q, eps, *, seed=0, first_id=0, draw=0, draw_base=None, action=None):
+    """eps: a Python float, or a device float32 tensor of one element (read by the kernel: capture-safe schedules)."""
     n, a = q.shape
     action = torch.empty(n, device=q.device, dtype=i32) if action is None else action
+    if torch.is_tensor(eps):
+        check(load().gymrl_select_eps_greedy_dev(ptr(q, f32), _ld(q), ptr(action, i32), n, a, ptr(eps, f32), seed, first_id, draw,
+                                                 ptr(draw_base, i32), stream_ptr()))
+        return action
     check(load().gymrl_select_eps_greedy(ptr(q, f32), _ld(q), ptr(action, i32), n, a, float(eps), seed, first_id, draw,
                                          ptr(draw_base, i32), stream_ptr()))
     return action

@@ -122,8 +122,18 @@ class ReplayBuffer_on_policy_v2:
 
 
 class ReplayBuffer_off_policy:
+    """Uniform replay (reference :105-135: object ring + np.random.choice(size, B, replace=False)) as a device SoA ring.
+
+    store(transitions) takes the reference's tuple (s, a, r, s', done ...) for ONE env copy, or the same fields with a leading
+    [N] axis for N lockstep copies (N = cfg.num_envs when set, else inferred from the first store's state against
+    cfg.state_shape).  Every field keeps its per-item shape: sample() returns [B] for scalars, [B, 1] for 1-element vectors
+    (e.g. Pendulum actions, like torch.tensor(np.array(...)) in the reference), [B, C, H, W] for image states.
+    Writes go through gymrl_replay_store with the ring cursor in device memory; sampling is the O(B) keyed-bijection prefix
+    of gymrl_replay_sample_indices (without replacement) into a preallocated index buffer."""
+
     def __init__(self, cfg):
         _ffi.require_cuda()
+        self.cfg = cfg
         self.capacity, self.batch_size = int(cfg.memory_capacity), int(cfg.batch_size)
         self.device = _dev(cfg)
         self.seed = int(getattr(cfg, "seed", 0) or 0)
@@ -131,21 +141,39 @@ class ReplayBuffer_off_policy:
 
     def clear(self):
         self.fields = None
+        self.item_shapes = None
         self.pointer, self.is_full = 0, False
         self._draw = 0
+        self.state = torch.zeros(2, device=self.device, dtype=torch.int32)        # {cursor, size} on the device
+        self._idx = torch.zeros(self.batch_size, device=self.device, dtype=torch.int32)
 
-    def _alloc(self, row):
-        self.fields = [torch.zeros((self.capacity,) + tuple(x.shape[1:]), device=self.device, dtype=f32) for x in row]
+    def _infer_n(self, first):
+        """(n, batched): how many transitions this store() carries and whether the fields have a leading [n] axis."""
+        n = int(getattr(self.cfg, "num_envs", 0) or 0)
+        shape = tuple(first.shape) if torch.is_tensor(first) else tuple(np.shape(first))
+        if n > 1:
+            assert shape[:1] == (n,), f"expected a leading [{n}] axis (cfg.num_envs), got {shape}"
+            return n, True
+        st = getattr(self.cfg, "state_shape", None)
+        if st is not None and shape != tuple(st) and shape[1:] == tuple(st):
+            return shape[0], True
+        return 1, False
 
     def store(self, transitions):
-        row = [_row(x, self.device) for x in transitions]
-        n = row[0].shape[0] if row[0].dim() >= 2 else 1     # state [D] = one env copy, [N, D] = N lockstep copies
-        row = [x.reshape(n, -1) for x in row]
+        n, batched = self._infer_n(transitions[0])
+        rows = [x.to(self.device, f32) if torch.is_tensor(x) else torch.as_tensor(np.asarray(x, dtype=np.float32), device=self.device)
+                for x in transitions]
         if self.fields is None:
-            self._alloc(row)
-        idx = (self.pointer + torch.arange(n, device=self.device)) % self.capacity
-        for f, x in zip(self.fields, row):
-            f[idx] = x
+            self.item_shapes = [tuple(t.shape[1:]) if batched else tuple(t.shape) for t in rows]
+            self.fields = [torch.zeros(self.capacity, max(1, int(np.prod(sh, dtype=np.int64))), device=self.device, dtype=f32)
+                           for sh in self.item_shapes]
+        L, sp = _ffi.load(), _ffi.stream_ptr()
+        for f, t in zip(self.fields, rows):
+            src = t.reshape(n, -1).contiguous()
+            assert src.shape[1] == f.shape[1], "field width changed between stores"
+            _ffi.check(L.gymrl_replay_store(_ffi.ptr(f, f32), _ffi.ptr(src, f32), n, f.shape[1], 0, self.capacity,
+                                            _ffi.ptr(self.state, torch.int32), sp))
+        _ffi.check(L.gymrl_replay_advance(_ffi.ptr(self.state, torch.int32), n, self.capacity, sp))
         if self.pointer + n >= self.capacity:
             self.is_full = True
         self.pointer = (self.pointer + n) % self.capacity
@@ -156,14 +184,11 @@ class ReplayBuffer_off_policy:
     def sample(self):
         size = self.size()
         b = min(self.batch_size, size)
-        perm = ops.random_permutation(size, seed=self.seed, draw=self._draw, device=self.device)   # without replacement
+        _ffi.check(_ffi.load().gymrl_replay_sample_indices(_ffi.ptr(self._idx, torch.int32), b, _ffi.ptr(self.state, torch.int32),
+                                                           self.seed, self._draw, None, _ffi.stream_ptr()))
         self._draw += 1
-        idx = perm[:b].long()
-        out = []
-        for f in self.fields:
-            x = f[idx]
-            out.append(x.squeeze(-1) if x.shape[-1] == 1 else x)
-        return iter(out)
+        idx = self._idx[:b].long()
+        return iter([torch.index_select(f, 0, idx).reshape((b,) + sh) for f, sh in zip(self.fields, self.item_shapes)])
 
 
 class Queue:

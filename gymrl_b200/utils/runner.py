@@ -103,7 +103,97 @@ def _episode_seed():
     return int(np.random.randint(1, 2 ** 31 - 1))
 
 
+def train_vec(agent, cfg, env=None):
+    """train() for cfg.num_envs = N lockstep env copies on the device (the runner loop, vectorised).
+
+    Same loop as the reference's (utils/runner.py:81-166) with every per-step quantity a device tensor of N rows:
+      * env        gymrl_b200.ops.VecEnv (auto-reset; the TRUE next observation is what the buffer sees, like the reference's
+                   next_state; the observation after an episode end seeds that copy's next episode);
+      * state_norm one running statistic over all copies (batch-merged Welford update per lockstep); the first observation of a
+                   new episode updates it only at N = 1 (a masked batch update does not exist) — the one documented difference;
+      * reward_scaler one discounted-return accumulator R per copy, reset where that copy's episode ended (ref :107);
+      * memory.store((s, a, r, done, dw, logp, v, v')) with [N] rows per call; agent.update() whenever memory.size() >= batch_size.
+    The agent's choose_action takes a [N, D] device tensor and returns ([N] actions, [N] log-probs, [N] values) (on-policy) or [N]
+    actions (off-policy).  At N = 1 the sequence of operations is train()'s.  Stops after cfg.train_eps finished episodes."""
+    from .. import ops
+    N = int(cfg.num_envs)
+    seed = int(getattr(cfg, "seed", 0) or 0)
+    env = env or ops.VecEnv(cfg.env_name, N, seed=seed)
+    cfg.state_shape = (env.obs_dim,)
+    cfg.n_states = env.obs_dim
+    if env.n_actions:
+        cfg.n_actions = env.n_actions
+    cfg.max_steps = env.max_episode_steps
+    dev = torch.device("cuda", torch.cuda.current_device())
+    if not hasattr(agent, "state_norm"):
+        agent.state_norm = Normalization(shape=(env.obs_dim,))
+    if not hasattr(agent, "reward_scaler"):
+        agent.reward_scaler = RewardScaling(shape=1, gamma=cfg.gamma, num_envs=N)
+    mem = agent.memory
+    cfg.on_policy = isinstance(mem, ReplayBuffer_on_policy)
+    cfg.use_rnn = False
+    stamp = time.strftime("%Y%m%d-%H%M%S")
+    writer = SummaryWriter(f'./exp/{cfg.algo_name}_{cfg.env_name.replace("/", "-")}_{stamp}')
+    logger.info(f'Start training: {N} lockstep env copies')
+    obs = env.reset()
+    state = agent.state_norm(obs)
+    agent.reward_scaler.reset()
+    if cfg.on_policy:
+        action, log_prob, value = agent.choose_action(state)
+    else:
+        action = agent.choose_action(state)
+    last_total, step = 0, 0
+    max_lock = int(getattr(cfg, "max_locksteps", 0) or (cfg.train_eps * cfg.max_steps))
+    while step < max_lock:
+        step += 1
+        a_dev = action if torch.is_tensor(action) else torch.as_tensor(np.asarray(action), device=dev)
+        obs, reward, terminated, truncated, next_obs = env.step(a_dev.to(torch.int32) if env.n_actions else a_dev.float().reshape(N, -1))
+        done = (terminated | truncated)
+        reward = agent.reward_scaler(reward)
+        next_state = agent.state_norm(next_obs)                      # the true s' (updates the statistic, ref :126)
+        if cfg.on_policy:
+            nxt_action, nxt_log_prob, nxt_value = agent.choose_action(next_state)
+            mem.store((state, action, reward, done, terminated, log_prob, value, nxt_value))
+        else:
+            mem.store((state, action, reward, next_state, done))
+            nxt_action = agent.choose_action(next_state)
+        # copies whose episode ended continue from their reset observation (ref :111-113 at the next episode start)
+        fresh = agent.state_norm(obs, update=(N == 1 and bool(done.any())))
+        dmask = done.bool()
+        if bool(dmask.any()):
+            agent.reward_scaler.reset(done)
+            if cfg.on_policy:
+                f_action, f_log_prob, f_value = agent.choose_action(fresh)
+                nxt_action = torch.where(dmask, f_action, nxt_action)
+                nxt_log_prob = torch.where(dmask, f_log_prob, nxt_log_prob)
+                nxt_value = torch.where(dmask, f_value, nxt_value)
+            else:
+                f_action = agent.choose_action(fresh)
+                nxt_action = torch.where(dmask.reshape((N,) + (1,) * (f_action.dim() - 1)), f_action, nxt_action)
+            next_state = torch.where(dmask[:, None], fresh, next_state)
+        state, action = next_state, nxt_action
+        if cfg.on_policy:
+            log_prob, value = nxt_log_prob, nxt_value
+        if mem.size() >= cfg.batch_size:
+            log_monitors(writer, agent.update(), agent, 'train', agent.learn_step)
+        if step % 50 == 0 or step == max_lock:
+            avg, _, total = env.episode_stats(100)
+            if total != last_total:
+                last_total = total
+                log_monitors(writer, {'reward': avg}, agent, 'train', total)
+                logger.info(f'Episodes:{total}/{cfg.train_eps}  Avg(100) reward:{avg:.1f}  locksteps:{step}')
+            if total >= cfg.train_eps:
+                break
+    logger.info('Finish training!')
+    if hasattr(agent, "save_model"):
+        agent.save_model()
+    writer.close()
+    return env
+
+
 def train(env, agent, cfg):
+    if int(getattr(cfg, "num_envs", 1) or 1) > 1:
+        return train_vec(agent, cfg)        # N lockstep copies on the device; `env` (the 1-copy view) is not used
     logger.info('Start training!')
     if cfg.load_model:
         agent.load_model()

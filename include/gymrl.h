@@ -80,6 +80,10 @@ int gymrl_env_set_state(gymrl_env* env, const double* d_state, void* stream);
  * subsequent step with {step cycles, collide, constraint setup, velocity iterations, position iterations (cycles),
  * touching manifolds, position iterations run, work slot}.  NULL switches it off (the default). */
 int gymrl_env_set_profile(gymrl_env* env, long long* d_prof);
+/* LunarLander keeps at most 8 touching manifolds per env copy (the device solver's contact slots; Box2D's contact list is
+ * unbounded).  A ninth is dropped — in the CUDA env and in the CPU oracle alike — and counted here: the number of such events
+ * since the env was created (synchronises the stream; 0 for the other envs).  Convergence runs report it (observed: 0). */
+int gymrl_env_overflow_count(gymrl_env* env, uint64_t* count, void* stream);
 /* Mean return/length over the last `last_k` finished episodes (all envs).  SYNCHRONOUS (one small
  * D2H) — call at log time only.  Replaces the deque(maxlen=100) bookkeeping at
  * algorithms/ppo_lunarlander.py:172,219-221. */
@@ -107,6 +111,10 @@ int gymrl_sample_categorical(const float* d_logits, int ld_logits, const float* 
 int gymrl_select_eps_greedy(const float* d_q, int ld_q, int32_t* d_action, int n, int n_actions,
                             float eps, uint64_t seed, uint64_t first_id, uint32_t draw,
                             const uint32_t* d_draw_base, void* stream);
+/* Same, with epsilon read from a device float: the host writes the decayed value (dqn_cartpole.py:117-122) into the slot
+ * before replaying a captured lockstep graph. */
+int gymrl_select_eps_greedy_dev(const float* d_q, int ld_q, int32_t* d_action, int n, int n_actions, const float* d_eps,
+                                uint64_t seed, uint64_t first_id, uint32_t draw, const uint32_t* d_draw_base, void* stream);
 /* tanh-Gaussian policy (Actor.sample / get_action, algorithms/sac_pendulum.py:76-98):
  * x = mean + exp(clamp(log_std)) * xi; a = tanh(x) * bound;
  * logp = sum_j [ N(x; mean, std).log_prob - log(bound * (1 - tanh(x)^2) + 1e-6) ].

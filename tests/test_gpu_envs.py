@@ -203,3 +203,21 @@ def test_cartpole_pendulum_full_size_properties():
         assert (r <= 0).all() and (te == 0).all()
         n_trunc += int(tr.sum())
     assert n_trunc == 4096  # every env hits the 200-step TimeLimit exactly once
+
+
+def test_lunarlander_reports_dropped_manifolds():
+    """The device solver keeps 8 contact slots per env copy; a ninth touching manifold is dropped (as in the CPU oracle) and
+    COUNTED (gymrl_env_overflow_count) instead of vanishing silently.  2048 copies x 300 random-action steps (many crash
+    landings): the counter reads back and, with 3 bodies over 10 terrain edges, stays at 0."""
+    import torch
+    from gymrl_b200 import ops
+    env = ops.VecEnv("LunarLander-v3", 2048, seed=11)
+    env.reset()
+    g = torch.Generator(device="cuda").manual_seed(0)
+    for _ in range(300):
+        env.step(torch.randint(0, 4, (2048,), device="cuda", dtype=torch.int32, generator=g), want_next_obs=False)
+    n = env.overflow_count()
+    _, _, total = env.episode_stats(100)
+    assert isinstance(n, int) and total > 1000
+    assert n == 0, f"{n} touching manifolds were dropped in {total} episodes"
+    assert ops.VecEnv("CartPole-v1", 4).overflow_count() == 0

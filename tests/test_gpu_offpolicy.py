@@ -369,15 +369,16 @@ def test_offpolicy_trainers_run_vectorised(algo):
     assert len(r) == 4 and all(np.isfinite(r))
 
 
-@pytest.mark.parametrize("algo", ["rainbow", "sac", "td3", "ddpg", "sac_discrete"])
+@pytest.mark.parametrize("algo", ["rainbow", "sac", "td3", "ddpg", "sac_discrete", "dqn", "noisy_dqn", "ddqn_per", "ddqn_per_duel"])
 def test_graph_lockstep_equals_eager_lockstep(algo):
     """train()'s captured lockstep (act -> env step -> store -> update as one CUDA graph, RNG draw counters / PER beta /
     learning rate in device scalars) leaves the same parameters, replay contents and env stream as the eager lockstep."""
     import importlib
     name = {"rainbow": "rainbow_dqn_cartpole", "sac": "sac_pendulum", "td3": "td3_pendulum", "ddpg": "ddpg_pendulum",
-            "sac_discrete": "sac_cartpole"}[algo]
+            "sac_discrete": "sac_cartpole", "dqn": "dqn_cartpole", "noisy_dqn": "noisy_dqn_cartpole", "ddqn_per": "ddqn_per_cartpole",
+            "ddqn_per_duel": "ddqn_per_duel_cartpole"}[algo]
     M = importlib.import_module(f"gymrl_b200.algorithms.{name}")
-    cls = [getattr(M, k) for k in dir(M) if k.endswith("Trainer")][0]
+    cls = [getattr(M, k) for k in dir(M) if k.endswith("Trainer") and getattr(M, k).__module__ == M.__name__][0]
     res = []
     for use_graph in (False, True):
         cfg = M.Config()

@@ -100,6 +100,38 @@ def test_off_policy_buffer_semantics():
     assert len(rr) == 16 and len(set(rr.tolist())) == 16 and rr.min() >= 70   # the ring kept the newest 50
 
 
+def test_off_policy_buffer_keeps_item_shapes_and_vector_stores():
+    """1-element action vectors come back as [B, 1] like the reference's torch.tensor(np.array(...)), image-shaped
+    states keep their shape (a [C, H, W] state is ONE transition, not C env copies), and N lockstep copies store in one call."""
+    from gymrl_b200.utils.buffer import ReplayBuffer_off_policy
+    cfg = _cfg(memory_capacity=64, batch_size=8)
+    cfg.state_shape = (3,)
+    buf = ReplayBuffer_off_policy(cfg)
+    for i in range(12):                                   # Pendulum-like: action shape (1,)
+        buf.store((np.full(3, i, np.float32), np.array([0.5 * i], np.float32), -float(i), np.full(3, i + 1, np.float32), False))
+    s, a, r, s2, d = buf.sample()
+    assert s.shape == (8, 3) and a.shape == (8, 1) and r.shape == (8,) and d.shape == (8,)
+    np.testing.assert_allclose(torch.cat([s, a], 1)[:, 3].cpu().numpy(), -0.5 * r.cpu().numpy())      # the reference idiom works
+    cfg2 = _cfg(memory_capacity=16, batch_size=4)
+    cfg2.state_shape = (2, 4, 4)
+    img = ReplayBuffer_off_policy(cfg2)
+    for i in range(5):
+        img.store((np.full((2, 4, 4), i, np.float32), i, 1.0, np.full((2, 4, 4), i + 1, np.float32), False))
+    s, a, r, s2, d = img.sample()
+    assert img.size() == 5 and s.shape == (4, 2, 4, 4) and a.shape == (4,)
+    assert (s.reshape(4, -1).std(dim=1) == 0).all()       # every sampled state is one stored image, not a mix
+    cfg3 = _cfg(memory_capacity=100, batch_size=32)
+    cfg3.state_shape, cfg3.num_envs = (4,), 16
+    vec = ReplayBuffer_off_policy(cfg3)
+    for t in range(5):                                    # 16 env copies per store, device tensors accepted
+        st = torch.full((16, 4), float(t), device="cuda") + torch.arange(16, device="cuda")[:, None] * 0.01
+        vec.store((st, torch.zeros(16, device="cuda"), torch.full((16,), float(t), device="cuda"), st + 1, torch.zeros(16, device="cuda")))
+    assert vec.size() == 80
+    s, a, r, s2, d = vec.sample()
+    assert s.shape == (32, 4) and r.shape == (32,) and len({(float(x[0]), float(y)) for x, y in zip(s.cpu(), r.cpu())}) == 32
+    np.testing.assert_allclose(np.floor(s[:, 0].cpu().numpy() + 1e-6), r.cpu().numpy())
+
+
 def test_gym_view_matches_oracle_env():
     from gymrl_b200.utils import env as E
     env = E.make("CartPole-v1")
@@ -289,3 +321,52 @@ def test_checkpoint_written_here_unpickles_as_reference_objects(tmp_path, monkey
     ref_net = MLP([8, 32, 4])
     ref_net.load_state_dict(ck["net_state_dict"])
     torch.optim.Adam(ref_net.parameters(), lr=1e-3).load_state_dict(ck["optimizer_state_dict"])
+
+
+def test_runner_train_vectorised(tmp_path, monkeypatch):
+    """utils.runner.train with cfg.num_envs = 64: the reference's loop over N lockstep copies on the device — device normalisers
+    (one RewardScaling accumulator per copy), [N]-row buffer stores, one update() per filled buffer, episode accounting."""
+    monkeypatch.chdir(tmp_path)
+    from gymrl_b200.utils import runner as R
+    from gymrl_b200.utils.buffer import ReplayBuffer_on_policy
+    from gymrl_b200.utils.model import MLP, ModelLoader
+
+    class Config(R.BasicConfig):
+        def __init__(self):
+            super().__init__()
+            self.env_name, self.algo_name = "CartPole-v1", "TestVecPPO"
+            self.num_envs, self.train_eps, self.batch_size, self.seed = 64, 200, 2048, 1
+            self.n_states, self.n_actions = 4, 2          # make_env is not needed for the device env
+
+    class Agent(ModelLoader):
+        def __init__(self, cfg):
+            super().__init__(cfg)
+            self.net = MLP([cfg.n_states, 16, cfg.n_actions + 1]).to("cuda")
+            self.memory = ReplayBuffer_on_policy(cfg)
+            self.learn_step, self.updates = 0, []
+
+        @torch.no_grad()
+        def choose_action(self, state):
+            out = self.net(state)
+            dist = torch.distributions.Categorical(logits=out[:, :-1])
+            a = dist.sample()
+            return a, dist.log_prob(a), out[:, -1]
+
+        def update(self):
+            s, a, logp, adv, v_target = self.memory.sample()
+            assert s.shape[0] == a.shape[0] == adv.shape[0] >= self.cfg.batch_size and torch.isfinite(adv).all()
+            assert s.shape[0] % 64 == 0
+            self.updates.append(s.shape[0])
+            self.memory.clear()
+            self.learn_step += 1
+            return {"adv_mean": float(adv.mean())}
+
+    cfg = Config()
+    ag = Agent(cfg)
+    env = R.train(None, ag, cfg)
+    assert cfg.on_policy is True and len(ag.updates) >= 1 and all(u == 2048 for u in ag.updates)
+    avg, _, total = env.episode_stats(100)
+    assert total >= 200 and 8.0 < avg < 200.0                       # a random CartPole policy lasts ~20 steps
+    assert ag.state_norm.running_ms.n >= 2048 and ag.reward_scaler.R.numel() == 64
+    ckpt = torch.load(cfg.save_path, weights_only=False)
+    assert "net_state_dict" in ckpt and "state_norm" in ckpt

@@ -175,3 +175,32 @@ def test_reference_ppo_lunarlander_runs():
 def test_reference_other_scripts_run(script, steps):
     r = run_reference.run(script, steps=steps, seed=0)
     assert r["steps"] == steps and r["episodes"] >= 1 and all(math.isfinite(x) for x in r["returns"])
+
+
+@needs_ref
+@pytest.mark.parametrize("script,agent_cls", [("legacy/LunarLander(PPO).py", "PPO"), ("legacy/CartPole(NDQN).py", "DQN")])
+def test_legacy_scripts_import_against_our_utils_surface(script, agent_cls):
+    """The two in-scope `utils` consumers execute their module bodies UNCHANGED against gymrl_b200.utils.install():
+    every name they take from `utils.model / utils.buffer / utils.runner` resolves, their Config(BasicConfig) builds, and their agent
+    classes carry the protocol utils.runner.train drives (choose_action / evaluate / update, ModelLoader save/load).  Running
+    BenchMark.train needs the device env, i.e. a GPU, and /root/reference is not on the GPU box — tests/test_gpu_utils.py drives the
+    same loop there with agents of this shape."""
+    import runpy
+    import sys
+    saved = {k: sys.modules.get(k) for k in ("utils", "utils.buffer", "utils.model", "utils.normalization", "utils.runner")}
+    try:
+        import gymrl_b200.utils as U
+        U.install()
+        ns = runpy.run_path(str(ref_loader.REFERENCE_ROOT / script), run_name="legacy_under_test")
+        cfg = ns["Config"]()
+        assert cfg.env_name in ("LunarLander-v3", "CartPole-v1") and hasattr(cfg, "batch_size") and hasattr(cfg, "gamma")
+        agent = ns[agent_cls]
+        for m in ("choose_action", "evaluate", "update", "save_model", "load_model"):
+            assert callable(getattr(agent, m)), m
+        assert ns["BenchMark"].train.__module__ == "gymrl_b200.utils.runner"
+    finally:
+        for k, v in saved.items():
+            if v is None:
+                sys.modules.pop(k, None)
+            else:
+                sys.modules[k] = v

@@ -57,6 +57,7 @@ def ppo(budget_s=90.0, seed=0, num_envs=4096, num_steps=128, num_minibatches=32,
     return {"algo": "ppo_lunarlander", "config": f"{num_envs} envs x {num_steps} steps, {cfg.num_epochs} epochs x {num_minibatches} minibatches, lr {cfg.lr}",
             "criterion": f"avg100 >= {target} (ref ppo_lunarlander.py:361)", "solved_at_step": solved_at, "train_wall_s": round(wall, 2),
             "final_avg100": curve[-1][1] if curve else None, "eval_mean_256_deterministic": round(float(np.mean(ev)), 2),
+            "dropped_manifold_events": tr.env.overflow_count(),
             "eval_frac_ge_200": round(float(np.mean(np.asarray(ev) >= 200.0)), 3),
             "curve_columns": ["env_steps", "avg100", "episodes", "approx_kl", "entropy", "value_loss"], "curve": curve}
 
@@ -104,24 +105,8 @@ def dqn(budget_s=60.0, seed=0, num_envs=64, batch_size=256, target_sync_updates=
         cfg.epsilon_decay = epsilon_decay
     with contextlib.redirect_stdout(io.StringIO()):
         tr = D.DQNTrainer(cfg)
-    obs = tr.env.reset()
-    cur = obs.clone()
-    state = {"episodes_synced": 0}
-
-    def lockstep():
-        a = tr.act(cur)
-        o, r, te, trc, nobs = tr.env.step(a, done=tr.done)
-        tr.memory.store(cur, a.view(-1, 1), r, nobs, tr.done)
-        tr.update()
-        cur.copy_(o)
-        if tr.N > 1:
-            if tr.update_count and tr.update_count % cfg.target_sync_updates == 0:
-                tr.sync_target()
-        else:   # reference schedule: hard sync every `target_update_freq` finished episodes (ref :193-194)
-            if bool(tr.done.item()):
-                state["episodes_synced"] += 1
-                if state["episodes_synced"] % cfg.target_update_freq == 0:
-                    tr.sync_target()
+    tr.env.reset(out=tr.cur)
+    lockstep = tr.lockstep       # act -> env step -> store -> update (+ the hard target sync schedule), one CUDA graph per lockstep
 
     return _offpolicy(tr, "dqn_cartpole", f"{num_envs} envs, B={batch_size}, target sync every {target_sync_updates} updates" if num_envs > 1
                       else "1 env, reference schedule", "avg100 >= 495 (ref dqn_cartpole.py:207)", 495.0, budget_s,
