@@ -114,14 +114,14 @@ __global__ void __launch_bounds__(COMM_THREADS) peer_reduce_sumsq_kernel(const f
     for (int i = t; i < n4; i += COMM_THREADS) {
         float4 acc = make_float4(0.f, 0.f, 0.f, 0.f);
 #pragma unroll 1
-        for (int r0 = 0; r0 < world; r0 += 4) {      // up to four peer loads in flight
-            float4 v[4];
+        for (int r0 = 0; r0 < world; r0 += 8) {      // up to eight peer loads in flight: one NVLink round trip for a whole node
+            float4 v[8];
 #pragma unroll
-            for (int j = 0; j < 4; ++j)
+            for (int j = 0; j < 8; ++j)
                 if (r0 + j < world)
                     v[j] = ld_cv4(reinterpret_cast<const float4*>(peers[r0 + j] + (size_t)parity * staging_bytes) + (lo >> 2) + i);
 #pragma unroll
-            for (int j = 0; j < 4; ++j)
+            for (int j = 0; j < 8; ++j)
                 if (r0 + j < world) { acc.x += v[j].x; acc.y += v[j].y; acc.z += v[j].z; acc.w += v[j].w; }
         }
         const long long g0 = lo + 4ll * i;

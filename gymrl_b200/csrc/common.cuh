@@ -198,12 +198,28 @@ __device__ __forceinline__ void ordered_block_accumulate(const double (&v)[K], O
     __syncthreads();
     if (!s_last) return;
     __threadfence();
+    // all K values in one pass: thread-strided partial sums over the blocks (fixed order), one warp tree each, then the warps in
+    // order — two block barriers in total (a block_sum per value cost ~1 us each in the last block of the fused-heads kernel)
+    double a[K];
+#pragma unroll
+    for (int j = 0; j < K; ++j) a[j] = 0.0;
+    for (int b = threadIdx.x; b < nb; b += blockDim.x)
+#pragma unroll
+        for (int j = 0; j < K; ++j) a[j] += *((volatile double*)&g_fold_scratch[b * K + j]);
+    __shared__ double s_part[32][K];
+    const int lane = threadIdx.x & 31, wid = threadIdx.x >> 5, nw = (blockDim.x + 31) >> 5;
+#pragma unroll
     for (int j = 0; j < K; ++j) {
-        double a = 0.0;
-        for (int b = threadIdx.x; b < nb; b += blockDim.x) a += *((volatile double*)&g_fold_scratch[b * K + j]);
-        a = block_sum(a, scratch_smem);
-        if (threadIdx.x == 0) out[j] = (OutT)((double)out[j] + a);
+        a[j] = warp_sum(a[j]);
+        if (lane == 0) s_part[wid][j] = a[j];
     }
+    __syncthreads();
+    if (threadIdx.x < K) {
+        double t = 0.0;
+        for (int w = 0; w < nw; ++w) t += s_part[w][threadIdx.x];
+        out[threadIdx.x] = (OutT)((double)out[threadIdx.x] + t);
+    }
+    (void)scratch_smem;
     if (threadIdx.x == 0) g_fold_ticket = 0;
 }
 

@@ -18,3 +18,4 @@ def test_two_gpu_sharded_ppo_matches_single_gpu():
     assert "MULTIGPU_CHECK PASS" in r.stdout, r.stdout[-3000:] + r.stderr[-3000:]
     assert "MULTIGPU_GRAPH_CHECK PASS" in r.stdout, r.stdout[-3000:]
     assert "MULTIGPU_PEER_CHECK PASS" in r.stdout, r.stdout[-3000:]   # one-shot NVLink peer reduction == ncclAllReduce path
+    assert "MULTIGPU_DETERMINISM_CHECK PASS" in r.stdout, r.stdout[-3000:]

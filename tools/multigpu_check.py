@@ -53,6 +53,19 @@ def peer_vs_nccl(P, N):
     return (flats[0] - flats[1]).abs().max().item(), used
 
 
+def run_twice(P, N):
+    """Two runs of the same seeded multi-GPU iterations (peer reduction, epoch graph) leave bit-identical parameters: the
+    reduction adds the ranks in rank order and every other cross-block sum folds in a fixed order."""
+    flats = []
+    for _ in range(2):
+        tr = make_trainer(P, N, graph=True, n_mb=2, epochs=2)
+        for _ in range(2):
+            tr.collect_rollout()
+            tr.update(None)
+        flats.append(tr.net.fp.flat.clone())
+    return bool(torch.equal(flats[0], flats[1]))
+
+
 def reduce_latency(n_floats=200968, iters=300):
     """Device time of one gradient reduction, NCCL vs peer-memory kernel (+ the norm pass NCCL needs afterwards)."""
     import gymrl_b200.dist as gd
@@ -141,6 +154,11 @@ def main():
         ok = ok and dgraph < 1e-6
         print("MULTIGPU_GRAPH_CHECK", "PASS" if dgraph < 1e-6 else "FAIL")
     dpeer, used = peer_vs_nccl(P, N)
+    same2 = torch.tensor([float(run_twice(P, N))], device="cuda")
+    dist.all_reduce(same2, op=dist.ReduceOp.MIN)
+    if rank == 0:
+        print("MULTIGPU_DETERMINISM_CHECK", "PASS" if same2.item() >= 1 else "FAIL", "(two seeded runs, bitwise equal parameters on every rank)")
+        ok = ok and same2.item() >= 1
     lat = reduce_latency()
     if rank == 0:
         print(f"peer-memory reduction vs ncclAllReduce update: max |param diff| {dpeer:.3e} (peer path active: {used[1]}, nccl run: {not used[0]})")
