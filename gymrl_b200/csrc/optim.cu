@@ -106,7 +106,7 @@ __global__ void __launch_bounds__(256) clip_adam_kernel(float* __restrict__ para
                                                         float* __restrict__ v, long long n, const double* __restrict__ lr, float beta1,
                                                         float beta2, float eps, int32_t* __restrict__ step,
                                                         const double* __restrict__ sumsq_partials, int n_partials, float max_norm,
-                                                        float grad_scale, uint32_t* __restrict__ done_counter) {
+                                                        float grad_scale, uint32_t* __restrict__ done_counter, const WImgDev wimg) {
     __shared__ double scratch[32];
     __shared__ float s_coef;
     pdl_wait();
@@ -132,9 +132,11 @@ __global__ void __launch_bounds__(256) clip_adam_kernel(float* __restrict__ para
         mi = mi + w1 * (g - mi);
         vi = vi * beta2 + (w2 * g) * g;
         const float denom = sqrtf(vi) / bc2_sqrt + eps;
-        param[i] = param[i] + (step_size * mi) / denom;
+        const float pn = param[i] + (step_size * mi) / denom;
+        param[i] = pn;
         m[i] = mi;
         v[i] = vi;
+        if (wimg.images && i < wimg.n) wimg_store(wimg, i, pn);   // pre-split tf32 images of the weights follow the write, same pass
     }
     // every block read *step before it got here, so the last one to arrive may advance it
     __syncthreads();
@@ -157,11 +159,11 @@ extern "C" int gymrl_clip_adam_step(float* d_param, const float* d_grad, float* 
     const int threads = 256;
     long long blocks = ceil_div_ll(n, threads);
     if (blocks > GYMRL_NUM_SMS * 4) blocks = GYMRL_NUM_SMS * 4;
+    const WImgDev wimg = wimg_device_view(d_param);     // registered buffer: the images are re-split inside the Adam pass
     gymrl_launch_pdl(clip_adam_kernel, dim3((int)blocks), dim3(threads), 0, as_stream(stream), d_param, d_grad, d_exp_avg, d_exp_avg_sq, n, d_lr,
-                     beta1, beta2, eps, d_step, d_sumsq_partials, n_partials, max_norm, grad_scale, d_done_counter);
+                     beta1, beta2, eps, d_step, d_sumsq_partials, n_partials, max_norm, grad_scale, d_done_counter, wimg);
     gymrl_count_launch();
     GYMRL_LAUNCH_CHECK("clip_adam_step");
-    wimg_refresh_if_registered(d_param, as_stream(stream));
     return GYMRL_OK;
 }
 

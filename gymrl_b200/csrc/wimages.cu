@@ -31,34 +31,16 @@ struct WSet {
 std::vector<WSet> g_sets;
 std::mutex g_mu;
 
-__device__ __forceinline__ uint32_t to_tf32_rn(float x) { return (__float_as_uint(x) + 0x1000u) & 0xffffe000u; }
-
-__global__ void wimg_refresh_kernel(const float* __restrict__ flat, float* __restrict__ img, long long n, const int* __restrict__ mats,
-                                    int n_mats) {
+__global__ void wimg_refresh_kernel(const float* __restrict__ flat, WImgDev w) {
     const long long i = (long long)blockIdx.x * blockDim.x + threadIdx.x;
-    if (i >= n) return;
-    const float x = flat[i];
-    const uint32_t hi = to_tf32_rn(x);
-    const uint32_t lo = to_tf32_rn(x - __uint_as_float(hi));
-    uint32_t* im = reinterpret_cast<uint32_t*>(img);
-    im[i] = hi;
-    im[n + i] = lo;
-    for (int m = 0; m < n_mats; ++m) {
-        const long long off = mats[3 * m];
-        const int rows = mats[3 * m + 1], cols = mats[3 * m + 2];
-        const long long j = i - off;
-        if (j >= 0 && j < (long long)rows * cols) {
-            const int r = (int)(j / cols), c = (int)(j - (long long)r * cols);
-            const long long t = off + (long long)c * rows + r;
-            im[2 * n + t] = hi;
-            im[3 * n + t] = lo;
-            break;
-        }
-    }
+    if (i >= w.n) return;
+    wimg_store(w, i, flat[i]);
 }
 
 int refresh_set(const WSet& s, cudaStream_t st) {
-    wimg_refresh_kernel<<<(int)ceil_div_ll(s.n, 256), 256, 0, st>>>(s.flat, s.images, s.n, s.d_mats, s.n_mats);
+    WImgDev w;
+    w.images = s.images; w.mats = s.d_mats; w.n_mats = s.n_mats; w.n = s.n;
+    wimg_refresh_kernel<<<(int)ceil_div_ll(s.n, 256), 256, 0, st>>>(s.flat, w);
     gymrl_count_launch();
     GYMRL_LAUNCH_CHECK("weight_images_refresh");
     return GYMRL_OK;
@@ -81,6 +63,15 @@ bool wimg_lookup(const float* w, int rows, int cols, bool transposed, const floa
         return false;
     }
     return false;
+}
+
+WImgDev wimg_device_view(const float* d_param_base) {
+    WImgDev w;
+    w.images = nullptr; w.mats = nullptr; w.n_mats = 0; w.n = 0;
+    std::lock_guard<std::mutex> lk(g_mu);
+    for (const WSet& s : g_sets)
+        if (s.flat == d_param_base) { w.images = s.images; w.mats = s.d_mats; w.n_mats = s.n_mats; w.n = s.n; break; }
+    return w;
 }
 
 void wimg_refresh_if_registered(const float* d_param_base, cudaStream_t st) {
