@@ -946,19 +946,47 @@ __global__ void __launch_bounds__(ws::THREADS, 1) gemm3x_ws_kernel(const TcGemmP
             }
         }
     } else if (warp == ws::TMA_WARP) {
-        // ===== TMA: one 3-D box {32 k, B_ROWS, hi|lo} of the weight images per stage =====
-        if (lane == 0) {
+        // ===== TMA: one 3-D box {32 k, B_ROWS, hi|lo} of the weight images per stage (lane 0); all 32 lanes also pull the A
+        // slabs the producers will read PF slabs later into L2 (prefetch.global.L2, four 128 B row pieces per lane and slab): with
+        // L2-cold activations the producers' one-slab-ahead register prefetch (~1 us) barely covers the HBM latency =====
+        {
+            constexpr int PF = 4;
+            int pf_tile = cluster_id, pf_kb = 0;
+            auto pf_issue = [&]() {
+                if (pf_tile < n_tiles) {
+                    const int m0 = ((pf_tile / tiles_n) * NCTA + (int)rank) * BM;
+#pragma unroll
+                    for (int i = 0; i < 4; ++i) {
+                        const int m = min(m0 + lane * 4 + i, p.M - 1);
+                        asm volatile("prefetch.global.L2 [%0];" ::"l"(p.A + (long long)m * p.lda + pf_kb * 32));
+                    }
+                    if (++pf_kb == nslab) { pf_kb = 0; pf_tile += n_clusters; }
+                }
+            };
+            const bool do_pf = !(dbg_flags & 8);
+            if (do_pf) {
+                // the first slabs are fetched by the producers themselves at kernel start: begin one slab past them
+                for (int i = 0; i < 2 && pf_tile < n_tiles; ++i) { if (++pf_kb == nslab) { pf_kb = 0; pf_tile += n_clusters; } }
+#pragma unroll 1
+                for (int i = 0; i < PF; ++i) pf_issue();
+            }
             uint32_t it = 0;
             for (int tile = cluster_id; tile < n_tiles; tile += n_clusters) {
                 const int row0 = (tile % tiles_n) * BN + (int)rank * C::B_ROWS;
                 for (int kb = 0; kb < nslab; ++kb, ++it) {
-                    const uint32_t s = it % NST, ph = (it / NST) & 1u;
-                    ws::mbar_wait_ws<NCTA>(&bar_free[s], ph ^ 1u);
-                    if (dbg_flags & 4) { if (leader) mbar_arrive(&bar_full[s]); continue; }
-                    if (leader) ws::mbar_arrive_expect_tx(&bar_full[s], (uint32_t)NCTA * 2u * C::B_BYTES);
-                    ws::tma_load_b<NCTA>(smem_base + s * C::STAGE_BYTES + 2 * C::A_BYTES, &tmap_b, kb * 32, row0, full_leader[s]);
-                    if (it == 0) WS_STAMP(16);
-                    if ((int)it == nslab - 1) WS_STAMP(17);
+                    if (lane == 0) {
+                        const uint32_t s = it % NST, ph = (it / NST) & 1u;
+                        ws::mbar_wait_ws<NCTA>(&bar_free[s], ph ^ 1u);
+                        if (dbg_flags & 4) { if (leader) mbar_arrive(&bar_full[s]); }
+                        else {
+                            if (leader) ws::mbar_arrive_expect_tx(&bar_full[s], (uint32_t)NCTA * 2u * C::B_BYTES);
+                            ws::tma_load_b<NCTA>(smem_base + s * C::STAGE_BYTES + 2 * C::A_BYTES, &tmap_b, kb * 32, row0, full_leader[s]);
+                        }
+                        if (it == 0) WS_STAMP(16);
+                        if ((int)it == nslab - 1) WS_STAMP(17);
+                    }
+                    __syncwarp();
+                    if (do_pf) pf_issue();
                 }
             }
         }

@@ -56,6 +56,20 @@ def main():
         f = flat[m]
         print(f"nc={nc}: count {m.sum():7d}  step {f[:, 0].mean():9.0f} (p99 {np.percentile(f[:, 0], 99):9.0f})  collide {f[:, 1].mean():7.0f}  "
               f"setup {f[:, 2].mean():7.0f}  vel {f[:, 3].mean():9.0f}  pos {f[:, 4].mean():8.0f}  pos_it {f[:, 6].mean():5.1f}")
+    # contact layout of the heavy envs: (leg-1 contacts, leg-2 contacts, 2-point blocks, lander contacts) -> count, mean cycles
+    from collections import Counter
+    hv = flat[flat[:, 5] > 0]
+    lay = Counter()
+    cyc = Counter()
+    for row in hv:
+        k = int(row[7])
+        key = (k & 15, (k >> 4) & 15, (k >> 8) & 15, (k >> 12) & 15)
+        lay[key] += 1
+        cyc[key] += int(row[0])
+    for key, n in sorted(lay.items(), key=lambda kv: -kv[1])[:16]:
+        print(f"  legs {key[0]}+{key[1]} (2-pt blocks {key[2]}, lander {key[3]}): {n:6d} envs-steps, mean {cyc[key] / n:9.0f} cycles")
+    top_k = top[:, 7]
+    print("  slowest env of each step, layouts:", Counter((int(k) & 15, (int(k) >> 4) & 15, (int(k) >> 8) & 15) for k in top_k).most_common(8))
     light = flat[flat[:, 7] >= 0]
     print("all: mean step cycles", light[:, 0].mean())
 
