@@ -111,9 +111,10 @@ SIGNATURES = {
     "gymrl_replay_store": (c_int, [_P, _P, c_int, c_int, c_int, c_int, _P, _P]),
     "gymrl_replay_advance": (c_int, [_P, c_int, c_int, _P]),
     "gymrl_gather_concat": (c_int, [_P, c_int, _P, c_int, c_int, _P, _P, c_int, c_int, _P, c_int, _P]),
-    "gymrl_nstep_push": (c_int, [_P] * 12 + [c_int, c_int, c_int, c_double, _P] + [_P] * 5 + [c_int, _P, _P]),
+    "gymrl_nstep_push": (c_int, [_P] * 13 + [c_int, c_int, c_int, c_double, _P] + [_P] * 5 + [c_int, _P, _P]),
     "gymrl_sumtree_update": (c_int, [_P, c_int, _P, _P, _P, c_int, c_float, c_float, c_float, _P, _P]),
-    "gymrl_sumtree_store_new": (c_int, [_P, c_int, c_int, _P, _P, _P]),
+    "gymrl_sumtree_scratch_ints": (c_int, [c_int]),
+    "gymrl_sumtree_store_new": (c_int, [_P, c_int, c_int, _P, _P, _P, _P]),
     "gymrl_sumtree_sample": (c_int, [_P, c_int, c_int, _P, _P, _P, _P, _P, _P, _P, c_int, c_u64, c_u32, _P, _P]),
     "gymrl_dqn_loss": (c_int, [_P, c_int] * 6 + [_P] * 5 + [_P, c_int, _P, c_int, _P, _P, c_int, c_int, c_float, _P]),
     "gymrl_twin_q_target": (c_int, [_P, _P, _P, _P, c_int, _P, c_int, _P, _P, c_float, _P, c_int, _P]),
@@ -127,6 +128,9 @@ SIGNATURES = {
     "gymrl_noisy_sample": (c_int, [_P, _P, c_int, c_u64, c_u64, c_u32, _P, _P]),
     "gymrl_noisy_compose": (c_int, [_P] * 8 + [c_int, c_int, _P]),
     "gymrl_noisy_backward": (c_int, [_P] * 8 + [c_int, c_int, c_int, _P]),
+    "gymrl_noisy_refresh": (c_int, [_P] * 8 + [c_int] + [_P] * 8 + [c_int, c_int, c_int, c_u64, c_u64, c_u64, c_u32, _P, c_int, _P]),
+    "gymrl_noisy_backward2": (c_int, [_P] * 8 + [c_int] + [_P] * 8 + [c_int, c_int, c_int, _P]),
+    "gymrl_replay_store_all": (c_int, [_P] * 10 + [c_int, c_int, c_int, c_int, _P, _P, _P]),
 }
 
 

@@ -100,19 +100,29 @@ class DuelingEngine:
             self.dW, self.db = z(A + 1, H), z(A + 1)
             self.ws = torch.empty(ops.backward_weight_workspace(M, A + 1, H), device=dev, dtype=torch.uint8)
 
-    def compose(self, noisy: bool, xi=None):
-        """xi: optional dict of pre-drawn normals {in_a, out_a, in_v, out_v} (parity tests)."""
+    def _layers(self):
         fp, A = self.fp, self.A
-        if noisy:
-            self.draws += 1
-            for k, (eps, ent) in enumerate(((self.eps_in_a, 0), (self.eps_out_a, 1), (self.eps_in_v, 2), (self.eps_out_v, 3))):
-                key = ("in_a", "out_a", "in_v", "out_v")[k]
-                off.noisy_sample(eps, xi[key] if xi is not None else None, seed=self.seed, entity=self.entity * 16 + ent * 4096,
-                                 draw=1, draw_base=self.ctr)
-            ops.counter_add(self.ctr, 1)
-        else:
-            for eps in (self.eps_in_a, self.eps_out_a, self.eps_in_v, self.eps_out_v):
-                eps.zero_()
+        return [dict(w_mu=fp.p("advantage.weight_mu"), w_sigma=fp.p("advantage.weight_sigma"), b_mu=fp.p("advantage.bias_mu"),
+                     b_sigma=fp.p("advantage.bias_sigma"), eps_in=self.eps_in_a, eps_out=self.eps_out_a, w=self.W[:A], b=self.b[:A]),
+                dict(w_mu=fp.p("value.weight_mu"), w_sigma=fp.p("value.weight_sigma"), b_mu=fp.p("value.bias_mu"),
+                     b_sigma=fp.p("value.bias_sigma"), eps_in=self.eps_in_v, eps_out=self.eps_out_v, w=self.W[A:], b=self.b[A:])]
+
+    def compose(self, noisy: bool, xi=None):
+        """reset_noise() + the weight composition of both NoisyLinear heads: one fused launch (gymrl_noisy_refresh), or the
+        separate sample / compose entry points when pre-drawn normals are given.
+        xi: optional dict of pre-drawn normals {in_a, out_a, in_v, out_v} (parity tests)."""
+        fp, A = self.fp, self.A
+        if xi is None:
+            if noisy:
+                self.draws += 1
+            off.noisy_refresh(self._layers(), self.H, noisy=noisy, seed=self.seed, entity_base=self.entity * 16, entity_stride=4096,
+                              draw=1, draw_base=self.ctr if noisy else None, counter_inc=1 if noisy else 0)
+            return
+        self.draws += 1
+        for k, (eps, ent) in enumerate(((self.eps_in_a, 0), (self.eps_out_a, 1), (self.eps_in_v, 2), (self.eps_out_v, 3))):
+            key = ("in_a", "out_a", "in_v", "out_v")[k]
+            off.noisy_sample(eps, xi[key], seed=self.seed, entity=self.entity * 16 + ent * 4096, draw=1, draw_base=self.ctr)
+        ops.counter_add(self.ctr, 1)
         off.noisy_compose(fp.p("advantage.weight_mu"), fp.p("advantage.weight_sigma"), self.eps_in_a, self.eps_out_a,
                           fp.p("advantage.bias_mu"), fp.p("advantage.bias_sigma"), self.W[:A], self.b[:A])
         off.noisy_compose(fp.p("value.weight_mu"), fp.p("value.weight_sigma"), self.eps_in_v, self.eps_out_v,
@@ -127,10 +137,12 @@ class DuelingEngine:
         """Given self.dout = dL/d[adv | value]."""
         fp, A = self.fp, self.A
         ops.linear_backward_weight(self.dout, self.trunk.out, self.dW, self.db, workspace=self.ws, M=M)
-        off.noisy_backward(self.dW[:A], self.db[:A], self.eps_in_a, self.eps_out_a, fp.g("advantage.weight_mu"),
-                           fp.g("advantage.weight_sigma"), fp.g("advantage.bias_mu"), fp.g("advantage.bias_sigma"))
-        off.noisy_backward(self.dW[A:], self.db[A:], self.eps_in_v, self.eps_out_v, fp.g("value.weight_mu"),
-                           fp.g("value.weight_sigma"), fp.g("value.bias_mu"), fp.g("value.bias_sigma"))
+        off.noisy_backward2(dict(dw=self.dW[:A], db=self.db[:A], eps_in=self.eps_in_a, eps_out=self.eps_out_a,
+                                 dw_mu=fp.g("advantage.weight_mu"), dw_sigma=fp.g("advantage.weight_sigma"),
+                                 db_mu=fp.g("advantage.bias_mu"), db_sigma=fp.g("advantage.bias_sigma")),
+                            dict(dw=self.dW[A:], db=self.db[A:], eps_in=self.eps_in_v, eps_out=self.eps_out_v,
+                                 dw_mu=fp.g("value.weight_mu"), dw_sigma=fp.g("value.weight_sigma"),
+                                 db_mu=fp.g("value.bias_mu"), db_sigma=fp.g("value.bias_sigma")), self.H)
         ops.linear_backward_input(self.dout[:M], self.W, self.trunk.out, RELU, out=self.trunk.dout)
         self.trunk.backward(x, M, row_index=row_index)
 
@@ -170,8 +182,11 @@ class PrioritizedNStepBuffer:
         self.batch_index = torch.zeros(self.batch_size, device=dev, dtype=i32)
         self.is_weight = torch.zeros(self.batch_size, device=dev, dtype=f32)
 
-    def store_lockstep(self, obs, action, reward, next_obs, terminal_u8, done_u8):
-        full = self.window.push(obs, action, reward, next_obs, terminal_u8, done_u8, self.gamma, self.ring, self.ring.done)
+    def store_lockstep(self, obs, action, reward, next_obs, terminal_u8, done_u8, truncated_u8=None):
+        """terminal_u8 = the reference's `terminal`; or pass the env's terminated flags plus truncated_u8 and the kernel forms
+        terminated & ~truncated itself."""
+        full = self.window.push(obs, action, reward, next_obs, terminal_u8, done_u8, self.gamma, self.ring, self.ring.done,
+                                trunc=truncated_u8)
         if full:
             self.sum_tree.store_new(self.N, self.ring.state)
             self.ring.advance(self.N)
@@ -302,8 +317,8 @@ class RainbowDQNTrainer:
         out = self.net_act.forward(cur, self.N, noisy=True)
         a = ops.select_eps_greedy(out[:, :A], 0.0, action=self.action)
         obs, r, te, tr, nobs = env.step(a, done=self.done)
-        terminal = te & (1 - tr)                       # time-limit truncation is not terminal (ref :376)
-        mem.store_lockstep(cur, a, r, nobs, terminal, self.done)
+        # time-limit truncation is not terminal (ref :376): the push kernel stores te & ~tr
+        mem.store_lockstep(cur, a, r, nobs, te, self.done, truncated_u8=tr)
         self._update_device()
         cur.copy_(obs)
 
@@ -317,7 +332,7 @@ class RainbowDQNTrainer:
             cur = self.cur
             a = self.act(cur)
             obs, r, te, tr, nobs = self.env.step(a, done=self.done)
-            mem.store_lockstep(cur, a, r, nobs, te & (1 - tr), self.done)
+            mem.store_lockstep(cur, a, r, nobs, te, self.done, truncated_u8=tr)
             self.update()
             cur.copy_(obs)
             return

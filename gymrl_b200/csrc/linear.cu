@@ -38,6 +38,9 @@ bool smallk_forward_supported(int K);
 int smallk_forward(const float* x, int ldx, const int32_t* rows, const float* w, const float* b, float* y, int ldy, int M, int N, int K,
                    int act, cudaStream_t s);
 bool smallk_dw_supported(int K);
+bool smallk_dx_supported(int N, int K);
+int smallk_dx(const float* dy, int lddy, const float* w, const float* h, int ldh, float* dx, int lddx, int M, int N, int K, int act_in,
+              int accumulate, cudaStream_t s);
 bool skinny_bwd_fused_supported(const float* dy, const float* x, int ldx, const float* dx, int lddx, int N, int K);
 int skinny_bwd_fused_chunks(int M);
 int skinny_bwd_fused(const float* dy, int lddy, const float* x, int ldx, const float* w, float* part, float* dx, int lddx, int M, int N,
@@ -378,6 +381,11 @@ extern "C" int gymrl_linear_backward_input(const float* d_dy, int lddy, const fl
     if (g_skinny && N <= 16 && skinny_backward_input_supported(N, K, d_h_in, ldh, d_dx, lddx)) {
         skinny_backward_input(d_dy, lddy, d_w, d_h_in, ldh, d_dx, lddx, M, N, K, act_in, accumulate, as_stream(stream));
         GYMRL_LAUNCH_CHECK("linear_backward_input(skinny)");
+        return GYMRL_OK;
+    }
+    if (g_skinny && smallk_dx_supported(N, K)) {   // small fan-in (K <= 8): one warp per row
+        smallk_dx(d_dy, lddy, d_w, d_h_in, ldh, d_dx, lddx, M, N, K, act_in, accumulate, as_stream(stream));
+        GYMRL_LAUNCH_CHECK("linear_backward_input(smallk)");
         return GYMRL_OK;
     }
     if (gemm_mode() == 1 && !accumulate) {

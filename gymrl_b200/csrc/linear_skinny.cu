@@ -56,7 +56,10 @@ __global__ void __launch_bounds__(256) skinny_fwd_kernel(const float* __restrict
 template <int N>
 static void launch_skinny_fwd(const float* x, int ldx, const int32_t* rows, const float* w, const float* b, float* y, int ldy, int M,
                               int K, int act, cudaStream_t s) {
-    int blocks = ceil_div(M, 8 * 8);   // 8 warps per block, ~8 rows per warp
+    // 8 warps per block; one row per warp while that still fits one resident wave (the launch is latency-bound: a warp that
+    // walks 8 rows pays 8 dependent L2 round trips — 14.8 us for 8192 x 256 x 3 — GYMRL_SKINNY_ROWS restores that for A/B runs)
+    static const int rows_per_warp = [] { const char* e = getenv("GYMRL_SKINNY_ROWS"); return e && atoi(e) > 0 ? atoi(e) : 1; }();
+    int blocks = ceil_div(M, 8 * rows_per_warp);
     if (blocks > GYMRL_NUM_SMS * 8) blocks = GYMRL_NUM_SMS * 8;
     skinny_fwd_kernel<N><<<blocks, 256, (size_t)N * K * sizeof(float), s>>>(x, ldx, rows, w, b, y, ldy, M, K, act);
 }
@@ -638,4 +641,58 @@ int skinny_bwd_fused(const float* dy, int lddy, const float* x, int ldx, const f
     SKF(1, 4); SKF(2, 4); SKF(3, 4); SKF(4, 4);
 #undef SKF
     GYMRL_FAIL(GYMRL_EINVAL, "skinny_bwd_fused: unsupported N=%d K=%d", N, K);
+}
+
+// ---- backward-input of a small fan-in layer (K <= 8 input columns, e.g. the critic's first layer over [state | action]:
+// dQ/d(s, a) for the actor gradient, sac_pendulum.py:211-218 / td3_pendulum.py:215-217): dX[m][k] = sum_n dY[m][n] W[n][k].
+// One warp per row: lanes stride over n (coalesced dY row), K accumulators per lane, W^T staged in shared memory, fixed-order
+// butterfly reduction.  The shape used to fall through to the FFMA GEMM with 64-wide tiles (21 us for 4096 x 256 x 4).
+#define SMALLK_DX_MAXK 8
+__global__ void __launch_bounds__(256) smallk_dx_kernel(const float* __restrict__ dy, int lddy, const float* __restrict__ w,
+                                                        const float* __restrict__ h, int ldh, float* __restrict__ dx, int lddx, int M, int N,
+                                                        int K, int act_in, int accumulate) {
+    extern __shared__ float wt[];   // [K][N]
+    for (int x = threadIdx.x; x < N * K; x += blockDim.x) wt[(x % K) * N + (x / K)] = w[x];
+    __syncthreads();
+    const int lane = threadIdx.x & 31, warp = threadIdx.x >> 5, wpb = blockDim.x >> 5;
+    for (int m = blockIdx.x * wpb + warp; m < M; m += gridDim.x * wpb) {
+        float acc[SMALLK_DX_MAXK];
+#pragma unroll
+        for (int k = 0; k < SMALLK_DX_MAXK; ++k) acc[k] = 0.f;
+        const float* row = dy + (size_t)m * lddy;
+        for (int n = lane; n < N; n += 32) {
+            const float g = row[n];
+#pragma unroll
+            for (int k = 0; k < SMALLK_DX_MAXK; ++k)
+                if (k < K) acc[k] = fmaf(g, wt[k * N + n], acc[k]);
+        }
+#pragma unroll
+        for (int k = 0; k < SMALLK_DX_MAXK; ++k) {
+            if (k < K) {
+#pragma unroll
+                for (int o = 16; o > 0; o >>= 1) acc[k] += __shfl_xor_sync(0xffffffffu, acc[k], o);
+            }
+        }
+        float v = 0.f;
+#pragma unroll
+        for (int k = 0; k < SMALLK_DX_MAXK; ++k) v = lane == k ? acc[k] : v;
+        if (lane < K) {
+            if (h) {
+                const float hv = h[(size_t)m * ldh + lane];
+                if (act_in == GYMRL_ACT_TANH) v *= (1.0f - hv * hv);
+                else if (act_in == GYMRL_ACT_RELU) v = hv > 0.f ? v : 0.f;
+            }
+            float* dst = dx + (size_t)m * lddx + lane;
+            *dst = accumulate ? *dst + v : v;
+        }
+    }
+}
+bool smallk_dx_supported(int N, int K) { return K >= 1 && K <= SMALLK_DX_MAXK && N >= 32 && (size_t)N * K * sizeof(float) <= 32768; }
+int smallk_dx(const float* dy, int lddy, const float* w, const float* h, int ldh, float* dx, int lddx, int M, int N, int K, int act_in,
+              int accumulate, cudaStream_t s) {
+    int blocks = ceil_div(M, 8);
+    if (blocks > GYMRL_NUM_SMS * 4) blocks = GYMRL_NUM_SMS * 4;
+    smallk_dx_kernel<<<blocks, 256, (size_t)N * K * sizeof(float), s>>>(dy, lddy, w, h, ldh, dx, lddx, M, N, K, act_in, accumulate);
+    gymrl_count_launch();
+    return GYMRL_OK;
 }

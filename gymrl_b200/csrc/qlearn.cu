@@ -542,3 +542,100 @@ extern "C" int gymrl_noisy_backward(const float* d_dw, const float* d_db, const 
     GYMRL_LAUNCH_CHECK("noisy_backward");
     return GYMRL_OK;
 }
+
+// ---- fused NoisyNet refresh: everything reset_noise() + the weight composition do for up to two NoisyLinear layers that share
+// their input width (the dueling head: advantage [A][K] and value [1][K]) in ONE single-block launch — the four factorised
+// noise vectors (same Philox keys and draw order as gymrl_noisy_sample: entity_base + {0,1,2,3} * entity_stride for in0, out0,
+// in1, out1), W = mu + sigma * outer(eps_out, eps_in), b = b_mu + b_sigma * eps_out, and the advance of the device draw counter.
+// Replaces 4 x noisy_sample + counter_add + 2 x noisy_compose (7 launches of <= 768 threads per network forward).
+struct NoisyLayerArgs {
+    const float *w_mu, *w_sigma, *b_mu, *b_sigma;
+    float *eps_in, *eps_out, *w, *b;
+    int N;
+};
+__device__ __forceinline__ float noisy_eps_draw(uint64_t seed, uint64_t entity, int i, uint32_t draw) {
+    const u32x4 r = philox_draw(seed, entity + (uint64_t)(i >> 1), draw, PHILOX_NOISYNET);
+    const float u1 = u01_open0_f32(r.x), u2 = u01_f32(r.y);
+    const float rad = sqrtf(-2.0f * logf(u1));
+    float sn, cs;
+    sincosf(6.283185307179586f * u2, &sn, &cs);
+    const float xi = (i & 1) ? rad * sn : rad * cs;
+    const float sg = xi > 0.f ? 1.0f : (xi < 0.f ? -1.0f : 0.0f);
+    return sg * sqrtf(fabsf(xi));
+}
+__global__ void __launch_bounds__(256) noisy_refresh_kernel(const NoisyLayerArgs l0, const NoisyLayerArgs l1, int n_layers, int K, int noisy,
+                                                            uint64_t seed, uint64_t entity_base, uint64_t entity_stride, uint32_t draw,
+                                                            uint32_t* __restrict__ draw_base, int counter_inc) {
+    const int t = threadIdx.x;
+    if (draw_base) draw += *draw_base;
+    for (int l = 0; l < n_layers; ++l) {
+        const NoisyLayerArgs& L = l ? l1 : l0;
+        const uint64_t e_in = entity_base + (uint64_t)(2 * l) * entity_stride, e_out = entity_base + (uint64_t)(2 * l + 1) * entity_stride;
+        for (int i = t; i < K; i += blockDim.x) L.eps_in[i] = noisy ? noisy_eps_draw(seed, e_in, i, draw) : 0.0f;
+        for (int i = t; i < L.N; i += blockDim.x) L.eps_out[i] = noisy ? noisy_eps_draw(seed, e_out, i, draw) : 0.0f;
+    }
+    __syncthreads();
+    for (int l = 0; l < n_layers; ++l) {
+        const NoisyLayerArgs& L = l ? l1 : l0;
+        for (int x = t; x < L.N * K; x += blockDim.x) {
+            const int n = x / K, k = x % K;
+            L.w[x] = L.w_mu[x] + L.w_sigma[x] * (L.eps_out[n] * L.eps_in[k]);
+        }
+        for (int n = t; n < L.N; n += blockDim.x) L.b[n] = L.b_mu[n] + L.b_sigma[n] * L.eps_out[n];
+    }
+    if (t == 0 && draw_base && counter_inc) *draw_base += (uint32_t)counter_inc;   // every thread read it before the barrier above
+}
+extern "C" int gymrl_noisy_refresh(const float* d_w_mu0, const float* d_w_sigma0, const float* d_b_mu0, const float* d_b_sigma0,
+                                   float* d_eps_in0, float* d_eps_out0, float* d_w0, float* d_b0, int N0, const float* d_w_mu1,
+                                   const float* d_w_sigma1, const float* d_b_mu1, const float* d_b_sigma1, float* d_eps_in1,
+                                   float* d_eps_out1, float* d_w1, float* d_b1, int N1, int K, int noisy, uint64_t seed,
+                                   uint64_t entity_base, uint64_t entity_stride, uint32_t draw, uint32_t* d_draw_base, int counter_inc,
+                                   void* stream) {
+    GYMRL_REQUIRE(d_w_mu0 && d_w_sigma0 && d_b_mu0 && d_b_sigma0 && d_eps_in0 && d_eps_out0 && d_w0 && d_b0 && N0 > 0 && K > 0, "bad layer 0");
+    const int n_layers = d_w_mu1 ? 2 : 1;
+    if (n_layers == 2)
+        GYMRL_REQUIRE(d_w_sigma1 && d_b_mu1 && d_b_sigma1 && d_eps_in1 && d_eps_out1 && d_w1 && d_b1 && N1 > 0, "bad layer 1");
+    NoisyLayerArgs l0{d_w_mu0, d_w_sigma0, d_b_mu0, d_b_sigma0, d_eps_in0, d_eps_out0, d_w0, d_b0, N0};
+    NoisyLayerArgs l1{d_w_mu1, d_w_sigma1, d_b_mu1, d_b_sigma1, d_eps_in1, d_eps_out1, d_w1, d_b1, n_layers == 2 ? N1 : 0};
+    noisy_refresh_kernel<<<1, 256, 0, as_stream(stream)>>>(l0, l1, n_layers, K, noisy, seed, entity_base, entity_stride, draw, d_draw_base,
+                                                          counter_inc);
+    gymrl_count_launch();
+    GYMRL_LAUNCH_CHECK("noisy_refresh");
+    return GYMRL_OK;
+}
+
+// the backward of the composition for the same pair of layers in one launch (blockIdx.y = layer)
+struct NoisyBwdArgs {
+    const float *dw, *db, *eps_in, *eps_out;
+    float *dw_mu, *dw_sigma, *db_mu, *db_sigma;
+    int N;
+};
+__global__ void noisy_backward2_kernel(const NoisyBwdArgs l0, const NoisyBwdArgs l1, int K, int accumulate) {
+    const NoisyBwdArgs& L = blockIdx.y ? l1 : l0;
+    const int t = blockIdx.x * blockDim.x + threadIdx.x;
+    if (t < L.N * K) {
+        const int n = t / K, k = t % K;
+        const float g = L.dw[t], gs = g * (L.eps_out[n] * L.eps_in[k]);
+        L.dw_mu[t] = accumulate ? L.dw_mu[t] + g : g;
+        L.dw_sigma[t] = accumulate ? L.dw_sigma[t] + gs : gs;
+    }
+    if (t < L.N) {
+        const float g = L.db[t], gs = g * L.eps_out[t];
+        L.db_mu[t] = accumulate ? L.db_mu[t] + g : g;
+        L.db_sigma[t] = accumulate ? L.db_sigma[t] + gs : gs;
+    }
+}
+extern "C" int gymrl_noisy_backward2(const float* d_dw0, const float* d_db0, const float* d_eps_in0, const float* d_eps_out0,
+                                     float* d_dw_mu0, float* d_dw_sigma0, float* d_db_mu0, float* d_db_sigma0, int N0, const float* d_dw1,
+                                     const float* d_db1, const float* d_eps_in1, const float* d_eps_out1, float* d_dw_mu1,
+                                     float* d_dw_sigma1, float* d_db_mu1, float* d_db_sigma1, int N1, int K, int accumulate, void* stream) {
+    GYMRL_REQUIRE(d_dw0 && d_db0 && d_eps_in0 && d_eps_out0 && d_dw_mu0 && d_dw_sigma0 && d_db_mu0 && d_db_sigma0 && N0 > 0 && K > 0, "bad layer 0");
+    GYMRL_REQUIRE(d_dw1 && d_db1 && d_eps_in1 && d_eps_out1 && d_dw_mu1 && d_dw_sigma1 && d_db_mu1 && d_db_sigma1 && N1 > 0, "bad layer 1");
+    NoisyBwdArgs l0{d_dw0, d_db0, d_eps_in0, d_eps_out0, d_dw_mu0, d_dw_sigma0, d_db_mu0, d_db_sigma0, N0};
+    NoisyBwdArgs l1{d_dw1, d_db1, d_eps_in1, d_eps_out1, d_dw_mu1, d_dw_sigma1, d_db_mu1, d_db_sigma1, N1};
+    const int nmax = N0 > N1 ? N0 : N1;
+    noisy_backward2_kernel<<<dim3(ceil_div(nmax * K, 256), 2), 256, 0, as_stream(stream)>>>(l0, l1, K, accumulate);
+    gymrl_count_launch();
+    GYMRL_LAUNCH_CHECK("noisy_backward2");
+    return GYMRL_OK;
+}

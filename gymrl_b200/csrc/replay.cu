@@ -11,8 +11,9 @@
 //       the SAME binary-heap layout as the reference (2*cap-1 float64 nodes, leaf i at cap-1+i, "go left iff
 //       v <= tree[left]"), so non-power-of-two capacities reproduce the reference's rotated prefix order
 //       (SURVEY q4).  One thread per sample walks root->leaf (the tree is L2 resident: 2^21 leaves = 32 MB);
-//       updates walk leaf->root with float64 atomics; duplicates inside a batch resolve last-writer-wins in
-//       batch order like the reference's Python loop (q6); priority_max is a true max over the leaves (q5).
+//       updates write the leaves and recompute the touched ancestors level by level (one block, no atomics on the
+//       tree, bitwise reproducible); duplicates inside a batch resolve last-writer-wins in batch order like the
+//       reference's Python loop (q6); priority_max is a true max over the leaves (q5).
 // These are latency-bound pointer walks over an L2-resident tree, not bandwidth-bound streams; the
 // algorithmic bytes per sample are in DESIGN.md.
 #include "common.cuh"
@@ -107,6 +108,52 @@ extern "C" int gymrl_replay_advance(int32_t* d_ring_state, int n, int capacity, 
     return GYMRL_OK;
 }
 
+// One launch for a whole lockstep's transitions: obs, next_obs [n][obs_dim], action [n][act_width] (4-byte elements), reward [n],
+// done (uint8 -> float) written at ring rows (cursor + i) % capacity, and the {cursor, size} state advanced by the block that
+// finishes last (d_done_ctr: one zero-initialised word, left zero).  Replaces 5 x gymrl_replay_store + gymrl_replay_advance.
+__global__ void replay_store_all_kernel(float* __restrict__ r_obs, float* __restrict__ r_nobs, float* __restrict__ r_act,
+                                        float* __restrict__ r_rew, float* __restrict__ r_done, const float* __restrict__ obs,
+                                        const float* __restrict__ nobs, const float* __restrict__ act, const float* __restrict__ rew,
+                                        const uint8_t* __restrict__ done, int n, int D, int AW, int capacity,
+                                        int32_t* __restrict__ ring_state, unsigned int* __restrict__ done_ctr) {
+    const int cursor = ring_state[0];
+    const int W = 2 * D + AW + 2;                 // words per transition
+    const long long t = (long long)blockIdx.x * blockDim.x + threadIdx.x;
+    if (t < (long long)n * W) {
+        const int i = (int)(t / W), c = (int)(t % W);
+        const size_t pos = (size_t)(((long long)cursor + i) % capacity);
+        if (c < D) r_obs[pos * D + c] = obs[(size_t)i * D + c];
+        else if (c < 2 * D) r_nobs[pos * D + (c - D)] = nobs[(size_t)i * D + (c - D)];
+        else if (c < 2 * D + AW) r_act[pos * AW + (c - 2 * D)] = act[(size_t)i * AW + (c - 2 * D)];
+        else if (c == 2 * D + AW) r_rew[pos] = rew[i];
+        else r_done[pos] = (float)done[i];
+    }
+    __shared__ bool s_last;
+    __syncthreads();                              // every thread of the block has read the cursor
+    if (threadIdx.x == 0) { __threadfence(); s_last = atomicAdd(done_ctr, 1u) == gridDim.x - 1; }
+    __syncthreads();
+    if (s_last && threadIdx.x == 0) {
+        ring_state[0] = (int32_t)(((long long)cursor + n) % capacity);
+        ring_state[1] = min(capacity, ring_state[1] + n);
+        *done_ctr = 0u;
+    }
+}
+extern "C" int gymrl_replay_store_all(float* r_obs, float* r_next_obs, void* r_action, float* r_reward, float* r_done,
+                                      const float* d_obs, const float* d_next_obs, const void* d_action, const float* d_reward,
+                                      const uint8_t* d_done, int n, int obs_dim, int act_width, int capacity, int32_t* d_ring_state,
+                                      uint32_t* d_done_ctr, void* stream) {
+    GYMRL_REQUIRE(r_obs && r_next_obs && r_action && r_reward && r_done && d_obs && d_next_obs && d_action && d_reward && d_done,
+                  "NULL ring / input pointer");
+    GYMRL_REQUIRE(d_ring_state && d_done_ctr && n > 0 && obs_dim > 0 && act_width > 0 && capacity >= n, "bad arguments");
+    const long long tot = (long long)n * (2 * obs_dim + act_width + 2);
+    replay_store_all_kernel<<<(unsigned)ceil_div_ll(tot, 256), 256, 0, as_stream(stream)>>>(
+        r_obs, r_next_obs, (float*)r_action, r_reward, r_done, d_obs, d_next_obs, (const float*)d_action, d_reward, d_done, n, obs_dim,
+        act_width, capacity, d_ring_state, d_done_ctr);
+    gymrl_count_launch();
+    GYMRL_LAUNCH_CHECK("replay_store_all");
+    return GYMRL_OK;
+}
+
 // dst[i] = [ a[ia(i)][0:wa] , b[ib(i)][0:wb] ]  (4-byte elements) — row gather and torch.cat([state, action], 1)
 // (Critic.forward, algorithms/sac_pendulum.py:112) in one pass.  b nullable.
 __global__ void gather_concat_kernel(float* __restrict__ dst, int ldd, const float* __restrict__ a, int wa, int lda,
@@ -140,14 +187,20 @@ extern "C" int gymrl_gather_concat(void* d_dst, int ld_dst, const void* d_a, int
 __global__ void nstep_push_kernel(float* __restrict__ w_obs, int32_t* __restrict__ w_act, float* __restrict__ w_rew,
                                   float* __restrict__ w_nobs, uint8_t* __restrict__ w_term, uint8_t* __restrict__ w_done,
                                   const float* __restrict__ obs, const int32_t* __restrict__ act, const float* __restrict__ rew,
-                                  const float* __restrict__ nobs, const uint8_t* __restrict__ term, const uint8_t* __restrict__ done,
-                                  int N, int D, int n_steps, double gamma, const int32_t* __restrict__ pushed_ptr,
+                                  const float* __restrict__ nobs, const uint8_t* __restrict__ term, const uint8_t* __restrict__ trunc,
+                                  const uint8_t* __restrict__ done, int N, int D, int n_steps, double gamma, int32_t* __restrict__ pushed_ptr,
                                   float* __restrict__ r_obs, int32_t* __restrict__ r_act, float* __restrict__ r_rew,
                                   float* __restrict__ r_nobs, float* __restrict__ r_term, int capacity,
                                   const int32_t* __restrict__ ring_state) {
     const int e = blockIdx.x * blockDim.x + threadIdx.x;
-    if (e >= N) return;
     const int pushed = *pushed_ptr;
+    // the push counter is advanced by the block that finishes last (pushed_ptr[1]: blocks done, zero between calls)
+    __shared__ bool s_last;
+    __syncthreads();
+    if (threadIdx.x == 0) s_last = atomicAdd(pushed_ptr + 1, 1) == (int)gridDim.x - 1;
+    __syncthreads();
+    if (s_last && threadIdx.x == 0) { pushed_ptr[0] = pushed + 1; pushed_ptr[1] = 0; }
+    if (e >= N) return;
     const int slot = pushed % n_steps;
     // overwrite the oldest slot with the new transition (deque(maxlen=n).append)
     for (int d = 0; d < D; ++d) {
@@ -156,7 +209,8 @@ __global__ void nstep_push_kernel(float* __restrict__ w_obs, int32_t* __restrict
     }
     w_act[(size_t)slot * N + e] = act[e];
     w_rew[(size_t)slot * N + e] = rew[e];
-    w_term[(size_t)slot * N + e] = term[e];
+    // `terminal` of the reference's train loop (rainbow :376): terminated and not cut by the time limit
+    w_term[(size_t)slot * N + e] = trunc ? (uint8_t)(term[e] & (trunc[e] ? 0 : 1)) : term[e];
     w_done[(size_t)slot * N + e] = done[e];
     if (pushed + 1 < n_steps) return;  // window not yet full: nothing emitted
     // fold back to front: R = r + gamma (1-d) R; (s', terminal) from the EARLIEST done in the window
@@ -180,11 +234,11 @@ __global__ void nstep_push_kernel(float* __restrict__ w_obs, int32_t* __restrict
     r_rew[pos] = (float)R;
     r_term[pos] = terminal;
 }
-__global__ void counter_inc_kernel(int32_t* c) { *c += 1; }
 
 extern "C" int gymrl_nstep_push(float* w_obs, int32_t* w_act, float* w_rew, float* w_nobs, uint8_t* w_term, uint8_t* w_done,
                                 const float* d_obs, const int32_t* d_act, const float* d_rew, const float* d_nobs,
-                                const uint8_t* d_term, const uint8_t* d_done, int n_envs, int obs_dim, int n_steps, double gamma,
+                                const uint8_t* d_term, const uint8_t* d_trunc, const uint8_t* d_done, int n_envs, int obs_dim, int n_steps,
+                                double gamma,
                                 int32_t* d_pushed, float* r_obs, int32_t* r_act, float* r_rew, float* r_nobs, float* r_term,
                                 int capacity, const int32_t* d_ring_state, void* stream) {
     GYMRL_REQUIRE(w_obs && w_act && w_rew && w_nobs && w_term && w_done && d_obs && d_act && d_rew && d_nobs && d_term && d_done,
@@ -193,65 +247,201 @@ extern "C" int gymrl_nstep_push(float* w_obs, int32_t* w_act, float* w_rew, floa
     GYMRL_REQUIRE(n_envs > 0 && obs_dim > 0 && n_steps > 0 && capacity >= n_envs, "bad shape");
     cudaStream_t s = as_stream(stream);
     nstep_push_kernel<<<ceil_div(n_envs, 128), 128, 0, s>>>(w_obs, w_act, w_rew, w_nobs, w_term, w_done, d_obs, d_act, d_rew, d_nobs,
-                                                          d_term, d_done, n_envs, obs_dim, n_steps, gamma, d_pushed, r_obs, r_act,
-                                                          r_rew, r_nobs, r_term, capacity, d_ring_state);
-    counter_inc_kernel<<<1, 1, 0, s>>>(d_pushed);
-    gymrl_count_launch(2);
+                                                          d_term, d_trunc, d_done, n_envs, obs_dim, n_steps, gamma, d_pushed, r_obs,
+                                                          r_act, r_rew, r_nobs, r_term, capacity, d_ring_state);
+    gymrl_count_launch();
     GYMRL_LAUNCH_CHECK("nstep_push");
     return GYMRL_OK;
 }
 
 // ---- sum tree ----------------------------------------------------------------------------------------
-__device__ __forceinline__ void sumtree_set_leaf(double* tree, int capacity, int data_index, double priority) {
-    int node = data_index + capacity - 1;
-    const double change = priority - tree[node];
-    tree[node] = priority;
-    while (node != 0) {
-        node = (node - 1) / 2;
-        atomicAdd(&tree[node], change);
+// Batched leaf writes.  Round 1 walked leaf -> root with a float64 atomicAdd(change) per level: 8192 leaves x 21 levels of atomics
+// that all meet at the root (measured 53-55 us per batch, and the sums depended on the arrival order).  Now every internal node is
+// always exactly fl(left + right) — a pure function of the leaves below it — which makes a batch embarrassingly parallel:
+//   mark    one thread per item: winner[leaf] = last batch position that writes it (duplicates: last writer wins, like the
+//           reference's Python loop) and expected[s] = number of distinct touched leaves under sub-root s (the node's ancestor
+//           at depth T = min(13, deepest complete internal level));
+//   set     one warp per item: the winner writes its leaf and arrives at its sub-root; the warp whose arrival completes a
+//           sub-root recomputes that whole subtree (<= 256 leaves) bottom-up, a warp-synchronous level at a time; the block that
+//           finishes last rebuilds the <= 8191 nodes above level T in shared memory from row T.
+// No atomics on the tree, no grid-wide barrier, bitwise reproducible.  Against the reference's incremental
+// `tree[parent] += change` only the summation order differs (tests: leaves exact, sums rtol 1e-12).
+// Scratch (d_winner_scratch): int32[capacity + GYMRL_SUMTREE_SCRATCH_EXTRA] = winner[capacity] (-1) | expected[8192] | arrive[8192]
+// | blocks_done (all 0); every call leaves it in that state.
+#define ST_TOP_MAX 13
+#define ST_ROWS (1 << ST_TOP_MAX)
+#define ST_EXTRA (2 * ST_ROWS + 1)
+#define ST_SROWS 1024
+__host__ __device__ __forceinline__ int heap_depth(int node) {
+    int d = 0;
+    for (unsigned v = (unsigned)node + 1u; v > 1u; v >>= 1) ++d;
+    return d;
+}
+// deepest level d <= ST_TOP_MAX that is complete and internal (2^(d+1) <= capacity); -1 if the tree is a single leaf
+__host__ __device__ __forceinline__ int st_top_level(int capacity) {
+    int d = -1;
+    while (d + 1 <= ST_TOP_MAX && (2ll << (d + 1)) <= (long long)capacity) ++d;
+    return d;
+}
+__device__ __forceinline__ int st_sub_root(int node, int T) {
+    int d = heap_depth(node);
+    while (d > T) { node = (node - 1) >> 1; --d; }
+    return node;
+}
+__device__ __forceinline__ int st_leaf_of(const int32_t* idx, const int32_t* ring_state, int i, int capacity) {
+    return idx ? idx[i] : (int)(((long long)ring_state[0] + i) % capacity);
+}
+
+__global__ void sumtree_mark_kernel(int32_t* __restrict__ scratch, const int32_t* __restrict__ idx, const int32_t* __restrict__ ring_state,
+                                    int n, int capacity) {
+    const int i = blockIdx.x * blockDim.x + threadIdx.x;
+    if (i >= n) return;
+    const int leaf = st_leaf_of(idx, ring_state, i, capacity);
+    const int old = atomicMax(&scratch[leaf], i);
+    const int T = st_top_level(capacity);
+    if (old == -1 && T >= 0) atomicAdd(&scratch[capacity + st_sub_root(leaf + capacity - 1, T) - ((1 << T) - 1)], 1);
+}
+
+// mode 0: leaf <- priority (prio64[i], or from the TD error);  mode 1: leaf <- the store rule (max of the leaves, 1.0 when empty)
+__global__ void __launch_bounds__(256) sumtree_set_kernel(double* __restrict__ tree, int capacity, int n, int mode, int32_t* __restrict__ scratch,
+                                                          const int32_t* __restrict__ idx, const double* __restrict__ prio64,
+                                                          const float* __restrict__ td, float eps, float alpha, float clip_max,
+                                                          const int32_t* __restrict__ ring_state, double* __restrict__ maxp) {
+    __shared__ double s_row[ST_SROWS];    // (a fold of) row T of the tree — last block only
+    __shared__ bool s_last;
+    const int lane = threadIdx.x & 31;
+    const int i = blockIdx.x * (blockDim.x >> 5) + (threadIdx.x >> 5);
+    const int T = st_top_level(capacity);
+    const int maxd = heap_depth(2 * capacity - 2);
+    int32_t* winner = scratch;
+    int32_t* expected = scratch + capacity;
+    int32_t* arrive = expected + ST_ROWS;
+    int32_t* blocks_done = arrive + ST_ROWS;
+    if (i < n) {
+        int sub = -1;   // sub-root this warp recomputes
+        if (lane == 0) {
+            const int leaf = st_leaf_of(idx, ring_state, i, capacity);
+            if (winner[leaf] == i) {
+                double p;
+                if (mode == 1) {
+                    const double m = *maxp;
+                    p = (ring_state[1] == 0 && m == 0.0) ? 1.0 : m;    // rainbow :201: 1.0 for the very first item, else max(leaves)
+                } else if (prio64) p = prio64[i];
+                else {
+                    // rainbow :259  (np.abs(td) + 0.01) ** alpha  — a float32 expression under NumPy >= 2;
+                    // ddqn_per :142-147  min(|td| + 1e-4, 1) ** 0.6
+                    float a = fabsf(td[i]) + eps;
+                    if (clip_max > 0.f) a = fminf(a, clip_max);
+                    p = (double)powf(a, alpha);
+                }
+                const int node = leaf + capacity - 1;
+                tree[node] = p;
+                winner[leaf] = -1;
+                if (T >= 0) {
+                    const int root = st_sub_root(node, T);
+                    const int r = root - ((1 << T) - 1);
+                    __threadfence();
+                    if (atomicAdd(&arrive[r], 1) + 1 == expected[r]) {   // every touched leaf under this sub-root is written
+                        arrive[r] = 0; expected[r] = 0;
+                        sub = root;
+                    }
+                }
+            }
+        }
+        sub = __shfl_sync(0xffffffffu, sub, 0);
+        if (sub >= 0) {
+            __threadfence();
+            const int H = maxd - T;                       // relative depth of the deepest leaves under a sub-root
+            for (int k = H - 1; k >= 0; --k) {
+                const long long first = (((long long)sub + 1) << k) - 1;
+                for (int x = lane; x < (1 << k); x += 32) {
+                    const long long nd = first + x;
+                    if (nd < capacity - 1) tree[nd] = __ldcg(&tree[2 * nd + 1]) + __ldcg(&tree[2 * nd + 2]);   // internal nodes only
+                }
+                __syncwarp();
+            }
+        }
+    }
+    // ---- the block that finishes last rebuilds the levels above T from row T ----
+    __threadfence();
+    __syncthreads();
+    if (threadIdx.x == 0) { __threadfence(); s_last = atomicAdd(blocks_done, 1) == (int)gridDim.x - 1; }
+    __syncthreads();
+    if (!s_last) return;
+    __threadfence();
+    if (threadIdx.x == 0) {
+        *blocks_done = 0;
+        if (mode == 1) *maxp = 0.0;   // consumed: sumtree_max_kernel accumulates into it with atomicMax
+    }
+    if (T < 1) return;
+    // Rows wider than the 1024-entry shared buffer are first folded three levels in registers: a thread owns eight adjacent
+    // nodes of row T and writes their parents / grandparents / great-grandparent (T is 11..13 there).
+    int top = T;
+    if ((1 << T) > ST_SROWS) {
+        const int rows = 1 << T, base = rows - 1;
+        for (int x = threadIdx.x; x < rows / 8; x += blockDim.x) {
+            double v[8];
+#pragma unroll
+            for (int j = 0; j < 8; ++j) v[j] = __ldcg(&tree[base + 8 * x + j]);
+            double a[4], b[2];
+#pragma unroll
+            for (int j = 0; j < 4; ++j) { a[j] = v[2 * j] + v[2 * j + 1]; tree[(rows / 2 - 1) + 4 * x + j] = a[j]; }
+#pragma unroll
+            for (int j = 0; j < 2; ++j) { b[j] = a[2 * j] + a[2 * j + 1]; tree[(rows / 4 - 1) + 2 * x + j] = b[j]; }
+            const double c = b[0] + b[1];
+            tree[(rows / 8 - 1) + x] = c;
+            s_row[x] = c;
+        }
+        top = T - 3;
+    } else {
+        const int rows = 1 << T, base = rows - 1;
+        for (int x = threadIdx.x; x < rows; x += blockDim.x) s_row[x] = __ldcg(&tree[base + x]);
+    }
+    __syncthreads();
+    for (int d = top - 1; d >= 0; --d) {
+        const int cnt = 1 << d;
+        double v[ST_SROWS / 2 / 256];
+#pragma unroll
+        for (int j = 0; j < ST_SROWS / 2 / 256; ++j) {
+            const int x = threadIdx.x + j * 256;
+            if (x < cnt) v[j] = s_row[2 * x] + s_row[2 * x + 1];
+        }
+        __syncthreads();
+#pragma unroll
+        for (int j = 0; j < ST_SROWS / 2 / 256; ++j) {
+            const int x = threadIdx.x + j * 256;
+            if (x < cnt) { s_row[x] = v[j]; tree[cnt - 1 + x] = v[j]; }
+        }
+        __syncthreads();
     }
 }
 
-// pass 1: winner[leaf] = last batch position that writes it; pass 2: only winners apply (last-writer-wins)
-__global__ void sumtree_mark_kernel(int32_t* __restrict__ winner, const int32_t* __restrict__ idx, int n) {
-    const int i = blockIdx.x * blockDim.x + threadIdx.x;
-    if (i < n) atomicMax(&winner[idx[i]], i);
+static int sumtree_launch_set(double* d_tree, int capacity, int n, int mode, int32_t* d_scratch, const int32_t* d_idx,
+                              const double* d_priority, const float* d_td_error, float eps, float alpha, float clip_max,
+                              const int32_t* d_ring_state, double* d_maxp, cudaStream_t s) {
+    sumtree_mark_kernel<<<ceil_div(n, 256), 256, 0, s>>>(d_scratch, d_idx, d_ring_state, n, capacity);
+    sumtree_set_kernel<<<ceil_div(n, 8), 256, 0, s>>>(d_tree, capacity, n, mode, d_scratch, d_idx, d_priority, d_td_error, eps, alpha,
+                                                        clip_max, d_ring_state, d_maxp);
+    gymrl_count_launch(2);
+    return GYMRL_OK;
 }
-__global__ void sumtree_apply_kernel(double* __restrict__ tree, int capacity, int32_t* __restrict__ winner,
-                                     const int32_t* __restrict__ idx, const double* __restrict__ prio64,
-                                     const float* __restrict__ td, int n, float eps, float alpha, float clip_max) {
-    const int i = blockIdx.x * blockDim.x + threadIdx.x;
-    if (i >= n) return;
-    const int leaf = idx[i];
-    if (winner[leaf] != i) return;
-    double p;
-    if (prio64) p = prio64[i];
-    else {
-        // rainbow :259  (np.abs(td) + 0.01) ** alpha  — a float32 expression under NumPy >= 2;
-        // ddqn_per :142-147  min(|td| + 1e-4, 1) ** 0.6
-        float a = fabsf(td[i]) + eps;
-        if (clip_max > 0.f) a = fminf(a, clip_max);
-        p = (double)powf(a, alpha);
-    }
-    sumtree_set_leaf(tree, capacity, leaf, p);
-    winner[leaf] = -1;
-}
+
+extern "C" int gymrl_sumtree_scratch_ints(int capacity) { return capacity + ST_EXTRA; }
 
 extern "C" int gymrl_sumtree_update(double* d_tree, int capacity, const int32_t* d_idx, const double* d_priority,
                                     const float* d_td_error, int n, float eps, float alpha, float clip_max, int32_t* d_winner_scratch,
                                     void* stream) {
     GYMRL_REQUIRE(d_tree && d_idx && d_winner_scratch && n > 0 && capacity > 0, "bad arguments");
     GYMRL_REQUIRE((d_priority != nullptr) != (d_td_error != nullptr), "pass exactly one of priority / td_error");
-    cudaStream_t s = as_stream(stream);
-    sumtree_mark_kernel<<<ceil_div(n, 256), 256, 0, s>>>(d_winner_scratch, d_idx, n);
-    sumtree_apply_kernel<<<ceil_div(n, 256), 256, 0, s>>>(d_tree, capacity, d_winner_scratch, d_idx, d_priority, d_td_error, n, eps,
-                                                         alpha, clip_max);
-    gymrl_count_launch(2);
+    int rc = sumtree_launch_set(d_tree, capacity, n, 0, d_winner_scratch, d_idx, d_priority, d_td_error, eps, alpha, clip_max, nullptr, nullptr,
+                                as_stream(stream));
+    if (rc != GYMRL_OK) return rc;
     GYMRL_LAUNCH_CHECK("sumtree_update");
     return GYMRL_OK;
 }
 
 // Store path: leaves [cursor, cursor+n) get priority max(leaves) (1.0 for the very first item), rainbow :201-202.
+// d_max_scratch must be zero on the first call; the set kernel leaves it zero again.
 __global__ void sumtree_max_kernel(const double* __restrict__ tree, int capacity, double* __restrict__ out) {
     __shared__ double scratch[32];
     double m = 0.0;
@@ -268,26 +458,17 @@ __global__ void sumtree_max_kernel(const double* __restrict__ tree, int capacity
         }
     }
 }
-__global__ void sumtree_store_kernel(double* __restrict__ tree, int capacity, int n, const int32_t* __restrict__ ring_state,
-                                     const double* __restrict__ maxp) {
-    const int i = blockIdx.x * blockDim.x + threadIdx.x;
-    if (i >= n) return;
-    const int pos = (int)(((long long)ring_state[0] + i) % capacity);
-    const double p = (ring_state[1] == 0 && *maxp == 0.0) ? 1.0 : *maxp;
-    sumtree_set_leaf(tree, capacity, pos, p);
-}
-__global__ void zero_double_kernel(double* p) { *p = 0.0; }
 
 extern "C" int gymrl_sumtree_store_new(double* d_tree, int capacity, int n, const int32_t* d_ring_state, double* d_max_scratch,
-                                       void* stream) {
-    GYMRL_REQUIRE(d_tree && d_ring_state && d_max_scratch && n > 0 && capacity >= n, "bad arguments");
+                                       int32_t* d_winner_scratch, void* stream) {
+    GYMRL_REQUIRE(d_tree && d_ring_state && d_max_scratch && d_winner_scratch && n > 0 && capacity >= n, "bad arguments");
     cudaStream_t s = as_stream(stream);
-    zero_double_kernel<<<1, 1, 0, s>>>(d_max_scratch);
     int blocks = ceil_div(capacity, 1024);
     if (blocks > GYMRL_NUM_SMS * 2) blocks = GYMRL_NUM_SMS * 2;
     sumtree_max_kernel<<<blocks, 256, 0, s>>>(d_tree, capacity, d_max_scratch);
-    sumtree_store_kernel<<<ceil_div(n, 256), 256, 0, s>>>(d_tree, capacity, n, d_ring_state, d_max_scratch);
-    gymrl_count_launch(3);
+    gymrl_count_launch();
+    int rc = sumtree_launch_set(d_tree, capacity, n, 1, d_winner_scratch, nullptr, nullptr, nullptr, 0.f, 0.f, 0.f, d_ring_state, d_max_scratch, s);
+    if (rc != GYMRL_OK) return rc;
     GYMRL_LAUNCH_CHECK("sumtree_store_new");
     return GYMRL_OK;
 }
@@ -298,55 +479,69 @@ __global__ void sumtree_sample_kernel(const double* __restrict__ tree, int capac
                                       float* __restrict__ out_w, double* __restrict__ out_prio, unsigned int* __restrict__ wmax_bits,
                                       int return_tree_index, uint64_t seed, uint32_t draw, const uint32_t* __restrict__ draw_base) {
     const int i = blockIdx.x * blockDim.x + threadIdx.x;
-    if (i >= B) return;
-    if (draw_base) draw += *draw_base;
-    const double total = tree[0];
-    const double segment = total / (double)B;
-    double u;
-    if (uniforms) u = uniforms[i];
-    else {
-        const u32x4 r = philox_draw(seed, (uint64_t)i, draw, PHILOX_REPLAY);
-        u = u01_f64(r.x, r.y);
+    if (i < B) {
+        if (draw_base) draw += *draw_base;
+        const double total = tree[0];
+        const double segment = total / (double)B;
+        double u;
+        if (uniforms) u = uniforms[i];
+        else {
+            const u32x4 r = philox_draw(seed, (uint64_t)i, draw, PHILOX_REPLAY);
+            u = u01_f64(r.x, r.y);
+        }
+        const double a = segment * (double)i, b = segment * (double)(i + 1);
+        double v = a + (b - a) * u;  // np.random.uniform(a, b)
+        if (return_tree_index & 2) v = u;  // flag bit 1: `uniforms` holds raw prefix values (SumTree.get_index(v))
+        const int tree_capacity = 2 * capacity - 1;
+        int parent = 0;
+        while (true) {
+            const int left = 2 * parent + 1;
+            if (left >= tree_capacity) break;
+            const double lv = tree[left];
+            if (v <= lv) parent = left;
+            else { v -= lv; parent = left + 1; }
+        }
+        const double priority = tree[parent];
+        const int data_index = parent - capacity + 1;
+        out_idx[i] = (return_tree_index & 1) ? parent : data_index;
+        if (out_prio) out_prio[i] = priority;
+        const double prob = priority / total;
+        const float w = (float)pow((double)ring_state[1] * prob, -(*beta_ptr));
+        out_w[i] = w;
+        atomicMax(wmax_bits, __float_as_uint(w));  // w > 0
     }
-    const double a = segment * (double)i, b = segment * (double)(i + 1);
-    double v = a + (b - a) * u;  // np.random.uniform(a, b)
-    if (return_tree_index & 2) v = u;  // flag bit 1: `uniforms` holds raw prefix values (SumTree.get_index(v))
-    const int tree_capacity = 2 * capacity - 1;
-    int parent = 0;
-    while (true) {
-        const int left = 2 * parent + 1;
-        if (left >= tree_capacity) break;
-        const double lv = tree[left];
-        if (v <= lv) parent = left;
-        else { v -= lv; parent = left + 1; }
+    // is_weight /= is_weight.max() (rainbow :243) by the block that finishes last: scratch[0] = max bits, scratch[1] = blocks done;
+    // both are left zero for the next call (no separate zeroing / normalising launches)
+    __shared__ bool s_last;
+    __threadfence();
+    __syncthreads();
+    if (threadIdx.x == 0) s_last = atomicAdd(wmax_bits + 1, 1u) == gridDim.x - 1;
+    __syncthreads();
+    if (s_last) {
+        __threadfence();
+        const float wmax = __uint_as_float(atomicOr(wmax_bits, 0u));
+        for (int k0 = 0; k0 < B; k0 += 16 * blockDim.x) {     // 16 independent loads in flight per thread
+            float v[16];
+#pragma unroll
+            for (int j = 0; j < 16; ++j) { const int k = k0 + j * blockDim.x + threadIdx.x; v[j] = k < B ? __ldcg(out_w + k) : 0.f; }
+#pragma unroll
+            for (int j = 0; j < 16; ++j) { const int k = k0 + j * blockDim.x + threadIdx.x; if (k < B) out_w[k] = v[j] / wmax; }
+        }
+        __syncthreads();
+        if (threadIdx.x == 0) { wmax_bits[0] = 0u; wmax_bits[1] = 0u; }
     }
-    const double priority = tree[parent];
-    const int data_index = parent - capacity + 1;
-    out_idx[i] = (return_tree_index & 1) ? parent : data_index;
-    if (out_prio) out_prio[i] = priority;
-    const double prob = priority / total;
-    const float w = (float)pow((double)ring_state[1] * prob, -(*beta_ptr));
-    out_w[i] = w;
-    atomicMax(wmax_bits, __float_as_uint(w));  // w > 0
 }
-__global__ void sumtree_normalize_kernel(float* __restrict__ w, int B, unsigned int* __restrict__ wmax_bits) {
-    const int i = blockIdx.x * blockDim.x + threadIdx.x;
-    if (i < B) w[i] = w[i] / __uint_as_float(*wmax_bits);
-}
-__global__ void zero_u32_kernel(unsigned int* p) { *p = 0u; }
-
 extern "C" int gymrl_sumtree_sample(const double* d_tree, int capacity, int batch, const double* d_uniforms,
                                     const int32_t* d_ring_state, const double* d_beta, int32_t* d_out_idx, float* d_out_is_weight,
                                     double* d_out_priority, uint32_t* d_scratch_u32, int return_tree_index, uint64_t seed,
                                     uint32_t draw, const uint32_t* d_draw_base, void* stream) {
     GYMRL_REQUIRE(d_tree && d_ring_state && d_beta && d_out_idx && d_out_is_weight && d_scratch_u32 && batch > 0 && capacity > 0, "bad arguments");
     cudaStream_t s = as_stream(stream);
-    zero_u32_kernel<<<1, 1, 0, s>>>(d_scratch_u32);
+    // d_scratch_u32: 2 words, zero on the first call (the kernel leaves them zero)
     sumtree_sample_kernel<<<ceil_div(batch, 128), 128, 0, s>>>(d_tree, capacity, batch, d_uniforms, d_ring_state, d_beta, d_out_idx,
                                                               d_out_is_weight, d_out_priority, d_scratch_u32, return_tree_index,
                                                               seed, draw, d_draw_base);
-    sumtree_normalize_kernel<<<ceil_div(batch, 256), 256, 0, s>>>(d_out_is_weight, batch, d_scratch_u32);
-    gymrl_count_launch(3);
+    gymrl_count_launch();
     GYMRL_LAUNCH_CHECK("sumtree_sample");
     return GYMRL_OK;
 }

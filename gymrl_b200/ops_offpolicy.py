@@ -23,16 +23,17 @@ class ReplayRing:
         self.reward = torch.zeros(capacity, device=device, dtype=f32)
         self.done = torch.zeros(capacity, device=device, dtype=f32)      # stored as float like the reference's tensors
         self._size_host = 0
+        self._done_ctr = torch.zeros(1, device=device, dtype=i32)        # gymrl_replay_store_all: blocks finished (zero between calls)
 
     def store(self, obs, action, reward, next_obs, done_u8):
+        """One launch: the five fields at rows (cursor + i) % capacity and the {cursor, size} advance."""
         n = obs.shape[0]
-        L, s, st = load(), stream_ptr(), self.state
-        check(L.gymrl_replay_store(ptr(self.obs), ptr(obs, f32), n, self.obs_dim, 0, self.capacity, ptr(st, i32), s))
-        check(L.gymrl_replay_store(ptr(self.next_obs), ptr(next_obs, f32), n, self.obs_dim, 0, self.capacity, ptr(st, i32), s))
-        check(L.gymrl_replay_store(ptr(self.action), ptr(action), n, self.act_width, 0, self.capacity, ptr(st, i32), s))
-        check(L.gymrl_replay_store(ptr(self.reward), ptr(reward, f32), n, 1, 0, self.capacity, ptr(st, i32), s))
-        check(L.gymrl_replay_store(ptr(self.done), ptr(done_u8, u8), n, 1, 1, self.capacity, ptr(st, i32), s))
-        self.advance(n)
+        assert action.dtype == self.action.dtype and action.is_contiguous() and obs.is_contiguous() and next_obs.is_contiguous()
+        check(load().gymrl_replay_store_all(ptr(self.obs), ptr(self.next_obs), ptr(self.action), ptr(self.reward), ptr(self.done),
+                                            ptr(obs, f32), ptr(next_obs, f32), ptr(action), ptr(reward, f32), ptr(done_u8, u8), n,
+                                            self.obs_dim, self.act_width, self.capacity, ptr(self.state, i32), ptr(self._done_ctr, i32),
+                                            stream_ptr()))
+        self._size_host = min(self.capacity, self._size_host + int(n))
 
     def advance(self, n):
         check(load().gymrl_replay_advance(ptr(self.state, i32), int(n), self.capacity, stream_ptr()))
@@ -66,13 +67,14 @@ class NStepWindow:
         self.obs, self.nobs = z(n_steps, n_envs, obs_dim), z(n_steps, n_envs, obs_dim)
         self.act, self.rew = z(n_steps, n_envs, dt=i32), z(n_steps, n_envs)
         self.term, self.done = z(n_steps, n_envs, dt=u8), z(n_steps, n_envs, dt=u8)
-        self.pushed = torch.zeros(1, device=device, dtype=i32)
+        self.pushed = torch.zeros(2, device=device, dtype=i32)          # {pushes so far, blocks-done scratch}
         self.pushed_host = 0
 
-    def push(self, obs, act, rew, nobs, term, done, gamma, ring: "ReplayRing", r_term):
-        """Returns True when an n-step transition per env was written at ring rows [cursor, cursor+N)."""
+    def push(self, obs, act, rew, nobs, term, done, gamma, ring: "ReplayRing", r_term, trunc=None):
+        """Returns True when an n-step transition per env was written at ring rows [cursor, cursor+N).  With `trunc` the
+        stored terminal flag is term & ~trunc (a time-limit cut is not terminal, rainbow :376)."""
         check(load().gymrl_nstep_push(ptr(self.obs), ptr(self.act), ptr(self.rew), ptr(self.nobs), ptr(self.term), ptr(self.done),
-                                      ptr(obs, f32), ptr(act, i32), ptr(rew, f32), ptr(nobs, f32), ptr(term, u8), ptr(done, u8),
+                                      ptr(obs, f32), ptr(act, i32), ptr(rew, f32), ptr(nobs, f32), ptr(term, u8), ptr(trunc, u8), ptr(done, u8),
                                       self.N, self.D, self.n, float(gamma), ptr(self.pushed, i32), ptr(ring.obs), ptr(ring.action),
                                       ptr(ring.reward), ptr(ring.next_obs), ptr(r_term, f32), ring.capacity, ptr(ring.state, i32),
                                       stream_ptr()))
@@ -87,9 +89,11 @@ class DeviceSumTree:
     def __init__(self, capacity, device):
         self.capacity = int(capacity)
         self.tree = torch.zeros(2 * self.capacity - 1, device=device, dtype=f64)
-        self.winner = torch.full((self.capacity,), -1, device=device, dtype=i32)
+        n_scratch = int(load().gymrl_sumtree_scratch_ints(self.capacity))
+        self.winner = torch.zeros(n_scratch, device=device, dtype=i32)     # winner[capacity] = -1 | per-subtree counters = 0
+        self.winner[:self.capacity] = -1
         self.max_scratch = torch.zeros(1, device=device, dtype=f64)
-        self.u32_scratch = torch.zeros(1, device=device, dtype=i32)
+        self.u32_scratch = torch.zeros(2, device=device, dtype=i32)      # {max IS-weight bits, blocks done}: zero between calls
 
     def update(self, idx, priority=None, td_error=None, eps=0.01, alpha=0.6, clip_max=0.0):
         n = idx.numel()
@@ -98,7 +102,7 @@ class DeviceSumTree:
 
     def store_new(self, n, ring_state):
         check(load().gymrl_sumtree_store_new(ptr(self.tree, f64), self.capacity, int(n), ptr(ring_state, i32), ptr(self.max_scratch, f64),
-                                             stream_ptr()))
+                                             ptr(self.winner, i32), stream_ptr()))
 
     def sample(self, batch, ring_state, beta_t, *, uniforms=None, out_idx=None, out_w=None, out_prio=None, tree_index=False, seed=0,
                draw=0, draw_base=None, raw_values=False):
@@ -229,3 +233,24 @@ def noisy_backward(dw, db, eps_in, eps_out, dw_mu, dw_sigma, db_mu, db_sigma, ac
     N, K = dw.shape
     check(load().gymrl_noisy_backward(ptr(dw, f32), ptr(db, f32), ptr(eps_in, f32), ptr(eps_out, f32), ptr(dw_mu, f32), ptr(dw_sigma, f32),
                                       ptr(db_mu, f32), ptr(db_sigma, f32), N, K, int(accumulate), stream_ptr()))
+
+
+def noisy_refresh(layers, K, *, noisy=True, seed=0, entity_base=0, entity_stride=4096, draw=0, draw_base=None, counter_inc=0):
+    """layers: one or two dicts {w_mu, w_sigma, b_mu, b_sigma, eps_in, eps_out, w, b} (NoisyLinear layers sharing the input
+    width K).  Draws the factorised noise (or zeroes it), composes W / b and advances the draw counter in ONE launch."""
+    def args(l):
+        if l is None:
+            return [None] * 8 + [0]
+        return [ptr(l["w_mu"], f32), ptr(l["w_sigma"], f32), ptr(l["b_mu"], f32), ptr(l["b_sigma"], f32), ptr(l["eps_in"], f32),
+                ptr(l["eps_out"], f32), ptr(l["w"], f32), ptr(l["b"], f32), int(l["w_mu"].shape[0])]
+    l0, l1 = layers[0], (layers[1] if len(layers) > 1 else None)
+    check(load().gymrl_noisy_refresh(*args(l0), *args(l1), int(K), int(bool(noisy)), seed, int(entity_base), int(entity_stride), int(draw),
+                                     ptr(draw_base, i32), int(counter_inc), stream_ptr()))
+
+
+def noisy_backward2(l0, l1, K, accumulate=False):
+    """l: dict {dw, db, eps_in, eps_out, dw_mu, dw_sigma, db_mu, db_sigma}; both layers in one launch."""
+    def args(l):
+        return [ptr(l["dw"], f32), ptr(l["db"], f32), ptr(l["eps_in"], f32), ptr(l["eps_out"], f32), ptr(l["dw_mu"], f32),
+                ptr(l["dw_sigma"], f32), ptr(l["db_mu"], f32), ptr(l["db_sigma"], f32), int(l["dw"].shape[0])]
+    check(load().gymrl_noisy_backward2(*args(l0), *args(l1), int(K), int(accumulate), stream_ptr()))

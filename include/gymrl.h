@@ -337,29 +337,47 @@ int gymrl_gather_concat(void* d_dst, int ld_dst, const void* d_a, int width_a, i
  * envs in lockstep: append to each env's n-slot window (planes [n][N][...]), and once the window is full
  * fold R = sum gamma^k r_k back-to-front (cut at done; s'/terminal from the earliest done) and write the
  * n-step transition into ring row (cursor + env).  Caller then calls gymrl_sumtree_store_new +
- * gymrl_replay_advance iff the window was full (pushed + 1 >= n_steps, known on the host). */
+ * gymrl_replay_advance iff the window was full (pushed + 1 >= n_steps, known on the host).
+ * d_trunc (nullable): time-limit flags; the stored terminal is d_term & !d_trunc (rainbow :376).  d_pushed: int32[2] =
+ * {pushes so far, scratch}, both zero at the start; the call advances the count itself. */
 int gymrl_nstep_push(float* w_obs, int32_t* w_act, float* w_rew, float* w_nobs, uint8_t* w_term, uint8_t* w_done,
                      const float* d_obs, const int32_t* d_act, const float* d_rew, const float* d_nobs,
-                     const uint8_t* d_term, const uint8_t* d_done, int n_envs, int obs_dim, int n_steps, double gamma,
-                     int32_t* d_pushed, float* r_obs, int32_t* r_act, float* r_rew, float* r_nobs, float* r_term,
+                     const uint8_t* d_term, const uint8_t* d_trunc, const uint8_t* d_done, int n_envs, int obs_dim, int n_steps,
+                     double gamma, int32_t* d_pushed, float* r_obs, int32_t* r_act, float* r_rew, float* r_nobs, float* r_term,
                      int capacity, const int32_t* d_ring_state, void* stream);
+/* ReplayBuffer.push for a lockstep of n transitions (dqn_cartpole.py:75-76, sac_pendulum.py:140-141) in one launch: all five
+ * fields at ring rows (cursor + i) % capacity, then {cursor, size} advanced (what gymrl_replay_store x 5 + gymrl_replay_advance
+ * do in six).  action elements are 4 bytes (int32 or float32); d_done_ctr: one word, zero before the first call (left zero). */
+int gymrl_replay_store_all(float* r_obs, float* r_next_obs, void* r_action, float* r_reward, float* r_done,
+                           const float* d_obs, const float* d_next_obs, const void* d_action, const float* d_reward,
+                           const uint8_t* d_done, int n, int obs_dim, int act_width, int capacity, int32_t* d_ring_state,
+                           uint32_t* d_done_ctr, void* stream);
 /* SumTree (rainbow_dqn_cartpole.py:116-152): float64 binary heap of 2*capacity-1 nodes, leaf i at
  * capacity-1+i — identical layout and tie rule, so results match the reference for any capacity.
  * update: batch of (data index, priority) with last-writer-wins for duplicates (update_priorities :258-261);
  * pass d_priority (float64) OR d_td_error (float32): priority = min(|td| + eps, clip_max?)^alpha evaluated in
  * float32 like the reference's NumPy expression (clip_max <= 0 disables the min; ddqn_per_cartpole.py:142-147
- * uses eps 1e-4, clip 1, alpha 0.6).  d_winner_scratch: int32[capacity] initialised to -1 once. */
+ * uses eps 1e-4, clip 1, alpha 0.6).
+ * Every internal node is kept exactly fl(left + right): a batch = mark (last writer per leaf, touched leaves per subtree) +
+ * set (the winners write their leaves; the warp that completes a 256-leaf subtree recomputes it; the last block rebuilds the
+ * top 13 levels in shared memory) — no atomics on the tree, bitwise reproducible; against the reference's
+ * `tree[parent] += change` only the summation order differs.
+ * d_winner_scratch: int32[gymrl_sumtree_scratch_ints(capacity)], the first `capacity` entries -1 and the rest 0 before the
+ * first call (every call leaves it so). */
+int gymrl_sumtree_scratch_ints(int capacity);
 int gymrl_sumtree_update(double* d_tree, int capacity, const int32_t* d_idx, const double* d_priority,
                          const float* d_td_error, int n, float eps, float alpha, float clip_max,
                          int32_t* d_winner_scratch, void* stream);
 /* New transitions at ring rows [cursor, cursor+n) get priority max(all leaves) (1.0 while the tree is empty):
- * rainbow :201-202 with the O(capacity) max scan done as a device reduction. */
+ * rainbow :201-202 with the O(capacity) max scan done as a device reduction.
+ * d_max_scratch: one float64, zero before the first call (the call leaves it zero); d_winner_scratch as above. */
 int gymrl_sumtree_store_new(double* d_tree, int capacity, int n, const int32_t* d_ring_state, double* d_max_scratch,
-                            void* stream);
+                            int32_t* d_winner_scratch, void* stream);
 /* PrioritizedNStepBuffer.sample (rainbow :220-256): stratified v_i ~ U(seg*i, seg*(i+1)), root->leaf descent,
  * is_weight = (size * p/total)^(-beta) / max.  d_uniforms: optional pre-drawn U[0,1) float64[B] (parity).
  * return_tree_index bit 0: return tree indices like dialect B (ddqn_per_cartpole.py:94-106); bit 1: d_uniforms holds
- * raw prefix values v (a batch of SumTree.get_index(v) calls). */
+ * raw prefix values v (a batch of SumTree.get_index(v) calls).  d_scratch_u32: two words, zero before the first call
+ * (left zero): the running max of the weights and the count of finished blocks — the last block normalises. */
 int gymrl_sumtree_sample(const double* d_tree, int capacity, int batch, const double* d_uniforms,
                          const int32_t* d_ring_state, const double* d_beta, int32_t* d_out_idx, float* d_out_is_weight,
                          double* d_out_priority, uint32_t* d_scratch_u32, int return_tree_index, uint64_t seed,
@@ -434,6 +452,22 @@ int gymrl_noisy_compose(const float* d_w_mu, const float* d_w_sigma, const float
 int gymrl_noisy_backward(const float* d_dw, const float* d_db, const float* d_eps_in, const float* d_eps_out,
                          float* d_dw_mu, float* d_dw_sigma, float* d_db_mu, float* d_db_sigma, int N, int K,
                          int accumulate, void* stream);
+/* reset_noise() + the composition for up to two NoisyLinear layers with a common input width K (the dueling head of
+ * rainbow_dqn_cartpole.py:100-124: advantage [N0][K], value [N1][K]; layer 1 optional: d_w_mu1 = NULL) in ONE launch: draws
+ * eps_in0, eps_out0, eps_in1, eps_out1 with the Philox keys gymrl_noisy_sample would use for entity_base + {0,1,2,3} *
+ * entity_stride (noisy = 0: eps = 0, i.e. W = mu — a network in eval mode), composes W and b, and adds counter_inc to the
+ * device draw counter d_draw_base (nullable) after every thread has read it. */
+int gymrl_noisy_refresh(const float* d_w_mu0, const float* d_w_sigma0, const float* d_b_mu0, const float* d_b_sigma0,
+                        float* d_eps_in0, float* d_eps_out0, float* d_w0, float* d_b0, int N0, const float* d_w_mu1,
+                        const float* d_w_sigma1, const float* d_b_mu1, const float* d_b_sigma1, float* d_eps_in1,
+                        float* d_eps_out1, float* d_w1, float* d_b1, int N1, int K, int noisy, uint64_t seed,
+                        uint64_t entity_base, uint64_t entity_stride, uint32_t draw, uint32_t* d_draw_base, int counter_inc,
+                        void* stream);
+/* gymrl_noisy_backward for the same pair of layers in one launch. */
+int gymrl_noisy_backward2(const float* d_dw0, const float* d_db0, const float* d_eps_in0, const float* d_eps_out0,
+                          float* d_dw_mu0, float* d_dw_sigma0, float* d_db_mu0, float* d_db_sigma0, int N0, const float* d_dw1,
+                          const float* d_db1, const float* d_eps_in1, const float* d_eps_out1, float* d_dw_mu1,
+                          float* d_dw_sigma1, float* d_db_mu1, float* d_db_sigma1, int N1, int K, int accumulate, void* stream);
 
 /* Fused output heads + PPO loss + heads backward over the head-trunk activations d_h [batch][2H] = (actor | critic):
  *   logits = Wa h_a + ba (Wa [4][H]), V = Wc h_c + bc (Wc [1][H]); the loss of gymrl_ppo_loss (same cfg, same metrics);

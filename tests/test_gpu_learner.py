@@ -367,7 +367,8 @@ def test_linear_forward_gather_and_strided_views(ops):
     assert (lv[:, :4] == 0).all() and (lv[:, 5:] == 0).all()
 
 
-@pytest.mark.parametrize("M,N,K,act", [(16384, 512, 256, 1), (4096, 256, 256, 2), (4096, 4, 256, 1), (4096, 1, 256, 1), (301, 70, 19, 0)])
+@pytest.mark.parametrize("M,N,K,act", [(16384, 512, 256, 1), (4096, 256, 256, 2), (4096, 4, 256, 1), (4096, 1, 256, 1), (301, 70, 19, 0),
+                                       (4096, 256, 4, 0), (1000, 256, 3, 2), (513, 64, 8, 1)])   # last three: small fan-in dX (smallk_dx)
 def test_linear_backward_vs_torch_autograd(ops, M, N, K, act):
     g = torch.Generator().manual_seed(M * 3 + N + K)
     h_prev = torch.tanh(torch.randn(M, K, generator=g)) if act == 1 else torch.relu(torch.randn(M, K, generator=g))
