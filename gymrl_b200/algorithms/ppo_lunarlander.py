@@ -22,6 +22,7 @@ from __future__ import annotations
 
 import signal
 import sys
+import os
 import time
 from collections import deque
 from typing import Optional, Tuple
@@ -142,6 +143,11 @@ class ActorCriticEngine:
         self.deferred_reduce = True   # forward_trunk/backward may run inside an ops.reduce_defer_begin() scope
         # heads + loss + heads backward as one sweep (gymrl_ppo_heads_fused) where the kernel is built for the shape
         self.can_fuse_heads = self.A == 4 and self.H in (128, 256)
+        # GYMRL_PPO_BRANCHES=1: dW kernels of the trunk backward on a side stream / graph branch (see backward_trunk)
+        self.branches = None
+        if os.environ.get("GYMRL_PPO_BRANCHES", "0") == "1":
+            from ..graphs import Branches
+            self.branches = Branches(1)
 
     def alloc_workspace(self, M: int):
         need = max(ops.backward_weight_workspace(M, 2 * self.H, self.H), ops.backward_weight_workspace(M, self.H, self.H),
@@ -183,6 +189,18 @@ class ActorCriticEngine:
     def backward_trunk(self, x: torch.Tensor, acts: _Acts, M: int, row_index: Optional[torch.Tensor] = None):
         """Given acts.dac[:M] = dL/d(pre-activation of the head trunks), fill the gradients of the three trunk layers."""
         T, ws = _ffi.ACT_TANH, self.ws_layers
+        br = getattr(self, "branches", None)
+        if br is not None:
+            # dW of a layer is independent of its dX chain: two graph branches (the kernels fill the chip on their own, so what
+            # overlaps is one kernel's tail / epilogue with the next one's ramp-up; opt-in, see GYMRL_PPO_BRANCHES)
+            br.run(lambda: ops.linear_backward_input(acts.dac[:M], self.Wac, acts.h2[:M], T, out=acts.dh2),
+                   lambda: ops.linear_backward_weight(acts.dac, acts.h2, self.gWac, self.gbac, workspace=ws[2], M=M))
+
+            def rest():
+                ops.linear_backward_input(acts.dh2[:M], self.W2, acts.h1[:M], T, out=acts.dh1)
+                ops.linear_backward(acts.dh1, x, self.W1, self.gW1, self.gb1, row_index=row_index, workspace=ws[4], M=M)
+            br.run(rest, lambda: ops.linear_backward_weight(acts.dh2, acts.h1, self.gW2, self.gb2, workspace=ws[3], M=M))
+            return
         ops.linear_backward(acts.dac, acts.h2, self.Wac, self.gWac, self.gbac, dx=acts.dh2, act_in=T, workspace=ws[2], M=M)
         ops.linear_backward(acts.dh2, acts.h1, self.W2, self.gW2, self.gb2, dx=acts.dh1, act_in=T, workspace=ws[3], M=M)
         ops.linear_backward(acts.dh1, x, self.W1, self.gW1, self.gb1, row_index=row_index, workspace=ws[4], M=M)

@@ -240,6 +240,8 @@ class RainbowDQNTrainer:
         self.net_nxt = DuelingEngine(self.policy_net, self.fp, A, H, B, False, self.seed, 3)
         self.net_tgt = DuelingEngine(self.target_net, self.fp_t, A, H, B, False, self.seed, 4)
         self.memory = PrioritizedNStepBuffer(cfg, D, N, dev)
+        from ..graphs import Branches
+        self.branches = Branches(2)
         self.td = torch.zeros(B, device=dev, dtype=f32)
         self.loss_acc = torch.zeros(2, device=dev, dtype=f32)
         self.action = torch.zeros(N, device=dev, dtype=i32)
@@ -296,15 +298,17 @@ class RainbowDQNTrainer:
         ring = mem.ring
         idx, w = mem.sample(self.total_steps, self.max_train_steps, uniforms=uniforms, seed=self.seed, draw=1, draw_base=self.ctr_upd,
                             set_beta=False)
-        qo = self.net_nxt.forward(ring.next_obs, B, row_index=idx, noisy=True, xi=xi_next)       # online net, fresh noise (q8)
-        qt = self.net_tgt.forward(ring.next_obs, B, row_index=idx, noisy=False)                  # target net is .eval(): mu only
-        q = self.net_upd.forward(ring.obs, B, row_index=idx, noisy=True, xi=xi_cur)
+        # three independent forwards (online net on s' with fresh noise (q8), target net in eval mode: mu only, online net on s)
+        # as parallel branches
+        qo, qt, q = self.branches.run(lambda: self.net_nxt.forward(ring.next_obs, B, row_index=idx, noisy=True, xi=xi_next),
+                                      lambda: self.net_tgt.forward(ring.next_obs, B, row_index=idx, noisy=False),
+                                      lambda: self.net_upd.forward(ring.obs, B, row_index=idx, noisy=True, xi=xi_cur))
         self.loss_acc.zero_()
         off.dqn_loss(q[:, :A], qt[:, :A], ring.action, ring.reward, ring.done, cfg.gamma ** cfg.n_steps, v=q[:, A:], vnext_target=qt[:, A:],
                      qnext_online=qo[:, :A], vnext_online=qo[:, A:], row_index=idx, is_weight=w, dq=self.net_upd.dout[:, :A],
                      dv=self.net_upd.dout[:, A:], td_error=self.td, loss_acc=self.loss_acc)
-        mem.update_priorities(idx, self.td)                                                     # before backward (ref :340)
-        self.net_upd.backward(ring.obs, B, row_index=idx)
+        # priorities before backward (ref :340); the tree write-back and the backward pass touch disjoint data: two branches
+        self.branches.run(lambda: self.net_upd.backward(ring.obs, B, row_index=idx), lambda: mem.update_priorities(idx, self.td))
         self.optimizer.launch(max_norm=cfg.grad_clip)
         ops.polyak(self._target_params(), self._policy_params(), cfg.tau)
         ops.counter_add(self.ctr_upd, 1)

@@ -122,6 +122,8 @@ class SACTrainer:
         self.q1t = Chain.from_names(self.fp_ct, Critic.Q1, B, False)
         self.q2t = Chain.from_names(self.fp_ct, Critic.Q2, B, False)
         self.memory = ReplayBuffer(cfg.memory_capacity, D, A, dev)
+        from ..graphs import Branches
+        self.branches = Branches(1)          # the twin critics run as two parallel branches (side stream / graph branch)
         z = lambda *s, dt=f32: torch.zeros(*s, device=dev, dtype=dt)
         self.idx = z(B, dt=i32)
         self.sa, self.sa2 = z(B, D + A), z(B, D + A)
@@ -188,16 +190,15 @@ class SACTrainer:
         nz = noise_next if noise_next is not None else off.fill_normal(self.noise_b, seed=self.seed, entity0=0, draw=2, draw_base=self.ctr_nz)
         ops.sample_tanh_gaussian(out[:, :A], out[:, A:], bound, lsmin, lsmax, nz, action=self.act_b, logp=self.logp_b)
         off.gather_concat(mem.next_obs, idx, self.act_b, None, out=self.sa2, n=B)
-        q1t, q2t = self.q1t.forward(self.sa2, B), self.q2t.forward(self.sa2, B)
+        q1t, q2t = self.branches.run(lambda: self.q1t.forward(self.sa2, B), lambda: self.q2t.forward(self.sa2, B))
         off.twin_q_target(mem.reward, mem.done, q1t, q2t, cfg.gamma, row_index=idx, logp_next=self.logp_b, log_alpha=self.log_alpha,
                           out=self.y)
         # ---- critic (ref :239-246) ----
         off.gather_concat(mem.obs, idx, mem.action, idx, out=self.sa, n=B)
-        q1, q2 = self.q1.forward(self.sa, B), self.q2.forward(self.sa, B)
+        q1, q2 = self.branches.run(lambda: self.q1.forward(self.sa, B), lambda: self.q2.forward(self.sa, B))
         self.closs.zero_()
         off.twin_q_loss(q1, q2, self.y, self.q1.dout, self.q2.dout, self.closs)
-        self.q1.backward(self.sa, B)
-        self.q2.backward(self.sa, B)
+        self.branches.run(lambda: self.q1.backward(self.sa, B), lambda: self.q2.backward(self.sa, B))   # the twins are independent
         self.critic_optimizer.step()
         # ---- actor (ref :248-255) ----
         out = self.pi_upd.forward(mem.obs, B, row_index=idx)
@@ -205,11 +206,11 @@ class SACTrainer:
         ops.sample_tanh_gaussian(out[:, :A], out[:, A:], bound, lsmin, lsmax, nz, action=self.act_b, logp=self.logp_b,
                                  pre_tanh=self.pre_b)
         off.gather_concat(mem.obs, idx, self.act_b, None, out=self.sa2, n=B)
-        q1, q2 = self.q1.forward(self.sa2, B), self.q2.forward(self.sa2, B)
+        q1, q2 = self.branches.run(lambda: self.q1.forward(self.sa2, B), lambda: self.q2.forward(self.sa2, B))
         self.acc.zero_()
         off.min_q_grad(q1, q2, self.q1.dout, self.q2.dout, acc=self.acc[2:3])
-        dx1 = self.q1.backward(self.sa2, B, param_grads=False, input_grad=True)
-        dx2 = self.q2.backward(self.sa2, B, param_grads=False, input_grad=True)
+        dx1, dx2 = self.branches.run(lambda: self.q1.backward(self.sa2, B, param_grads=False, input_grad=True),
+                                     lambda: self.q2.backward(self.sa2, B, param_grads=False, input_grad=True))
         dx1.add_(dx2)                                       # d(-minQ/B)/d[s, a]   (torch add: tiny [B, D+A] glue)
         dhead = self.pi_upd.dout
         off.sac_actor_grad(self.pre_b, nz, out[:, A:], dx1[:, D:], self.log_alpha, bound, lsmin, lsmax, dhead[:, :A], dhead[:, A:],

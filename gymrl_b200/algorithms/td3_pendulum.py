@@ -89,6 +89,8 @@ class TD3Trainer(LockstepGraphs):
         self.q2 = Chain.from_names(self.fp_c, Critic.Q2, B, True)
         self.q1t = Chain.from_names(self.fp_ct, Critic.Q1, B, False)
         self.q2t = Chain.from_names(self.fp_ct, Critic.Q2, B, False)
+        from ..graphs import Branches
+        self.branches = Branches(1)
         self.memory = ReplayBuffer(cfg.memory_capacity, D, A, dev)
         z = lambda *s, dt=f32: torch.zeros(*s, device=dev, dtype=dt)
         self.idx = z(B, dt=i32)
@@ -150,15 +152,14 @@ class TD3Trainer(LockstepGraphs):
         nz = noise if noise is not None else off.fill_normal(self.noise_b, seed=self.seed, entity0=0, draw=1, draw_base=self.ctr_upd)
         ops.add_gaussian_noise_clip(self.mu_b, cfg.policy_noise, bound, cfg.noise_clip, nz, action=self.act_b)
         off.gather_concat(mem.next_obs, idx, self.act_b, None, out=self.sa2, n=B)
-        q1t, q2t = self.q1t.forward(self.sa2, B), self.q2t.forward(self.sa2, B)
+        q1t, q2t = self.branches.run(lambda: self.q1t.forward(self.sa2, B), lambda: self.q2t.forward(self.sa2, B))   # twins in parallel
         off.twin_q_target(mem.reward, mem.done, q1t, q2t, cfg.gamma, row_index=idx, out=self.y)
         # ---- critic (ref :206-213) ----
         off.gather_concat(mem.obs, idx, mem.action, idx, out=self.sa, n=B)
-        q1, q2 = self.q1.forward(self.sa, B), self.q2.forward(self.sa, B)
+        q1, q2 = self.branches.run(lambda: self.q1.forward(self.sa, B), lambda: self.q2.forward(self.sa, B))
         self.closs.zero_()
         off.twin_q_loss(q1, q2, self.y, self.q1.dout, self.q2.dout, self.closs)
-        self.q1.backward(self.sa, B)
-        self.q2.backward(self.sa, B)
+        self.branches.run(lambda: self.q1.backward(self.sa, B), lambda: self.q2.backward(self.sa, B))
         self.critic_optimizer.step()
         # ---- delayed actor + target sync (ref :215-226) ----
         if u % cfg.policy_freq == 0:

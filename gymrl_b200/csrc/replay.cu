@@ -352,13 +352,56 @@ __global__ void __launch_bounds__(256) sumtree_set_kernel(double* __restrict__ t
         if (sub >= 0) {
             __threadfence();
             const int H = maxd - T;                       // relative depth of the deepest leaves under a sub-root
-            for (int k = H - 1; k >= 0; --k) {
-                const long long first = (((long long)sub + 1) << k) - 1;
-                for (int x = lane; x < (1 << k); x += 32) {
-                    const long long nd = first + x;
-                    if (nd < capacity - 1) tree[nd] = __ldcg(&tree[2 * nd + 1]) + __ldcg(&tree[2 * nd + 2]);   // internal nodes only
+            if (H >= 1 && H <= 8) {
+                // fast path (<= 256 leaves): the row above the deepest leaves in registers (1, 2 or 4 nodes per lane, one L2 round
+                // trip), then pairwise in-lane and by shuffles — left + right at every node, like the generic loop below
+                const int R = 1 << (H - 1);
+                const int P = R >= 32 ? R / 32 : 1;
+                const long long root1 = (long long)sub + 1;
+                const long long first = (root1 << (H - 1)) - 1;
+                double v[4];
+#pragma unroll
+                for (int j = 0; j < 4; ++j) {
+                    v[j] = 0.0;
+                    const int x = lane * P + j;
+                    if (j < P && x < R) {
+                        const long long nd = first + x;
+                        if (nd < capacity - 1) { v[j] = __ldcg(&tree[2 * nd + 1]) + __ldcg(&tree[2 * nd + 2]); tree[nd] = v[j]; }
+                        else v[j] = __ldcg(&tree[nd]);    // a leaf one level up (capacities that are not a power of two)
+                    }
                 }
-                __syncwarp();
+                double cur = v[0];
+                int k = H - 1;
+                if (P == 4) {
+                    const long long f2 = (root1 << (H - 2)) - 1, f3 = (root1 << (H - 3)) - 1;
+                    const double a0 = v[0] + v[1], a1 = v[2] + v[3];
+                    tree[f2 + 2 * lane] = a0; tree[f2 + 2 * lane + 1] = a1;
+                    cur = a0 + a1;
+                    tree[f3 + lane] = cur;
+                    k = H - 3;
+                } else if (P == 2) {
+                    cur = v[0] + v[1];
+                    tree[(root1 << (H - 2)) - 1 + lane] = cur;
+                    k = H - 2;
+                }
+                const int width = 1 << k;                 // lanes [0, width) hold the nodes of relative depth k
+                for (int st = 1; st < width; st <<= 1) {
+                    const double right = __shfl_down_sync(0xffffffffu, cur, st);
+                    --k;
+                    if (lane < width && (lane % (2 * st)) == 0) {
+                        cur = cur + right;
+                        tree[(root1 << k) - 1 + lane / (2 * st)] = cur;
+                    }
+                }
+            } else {
+                for (int k = H - 1; k >= 0; --k) {
+                    const long long first = (((long long)sub + 1) << k) - 1;
+                    for (int x = lane; x < (1 << k); x += 32) {
+                        const long long nd = first + x;
+                        if (nd < capacity - 1) tree[nd] = __ldcg(&tree[2 * nd + 1]) + __ldcg(&tree[2 * nd + 2]);   // internal nodes only
+                    }
+                    __syncwarp();
+                }
             }
         }
     }
@@ -478,10 +521,16 @@ __global__ void sumtree_sample_kernel(const double* __restrict__ tree, int capac
                                       const int32_t* __restrict__ ring_state, const double* __restrict__ beta_ptr, int32_t* __restrict__ out_idx,
                                       float* __restrict__ out_w, double* __restrict__ out_prio, unsigned int* __restrict__ wmax_bits,
                                       int return_tree_index, uint64_t seed, uint32_t draw, const uint32_t* __restrict__ draw_base) {
+    // levels 0 .. TL of the tree (<= 2047 nodes) are staged in shared memory: the descent's first 11 of ~21 dependent loads
+    __shared__ double s_top[2047];
+    const int TL = min(10, st_top_level(capacity));
+    const int staged = TL >= 0 ? (2 << TL) - 1 : 0;
+    for (int x = threadIdx.x; x < staged; x += blockDim.x) s_top[x] = tree[x];
+    __syncthreads();
     const int i = blockIdx.x * blockDim.x + threadIdx.x;
     if (i < B) {
         if (draw_base) draw += *draw_base;
-        const double total = tree[0];
+        const double total = staged > 0 ? s_top[0] : tree[0];
         const double segment = total / (double)B;
         double u;
         if (uniforms) u = uniforms[i];
@@ -497,7 +546,7 @@ __global__ void sumtree_sample_kernel(const double* __restrict__ tree, int capac
         while (true) {
             const int left = 2 * parent + 1;
             if (left >= tree_capacity) break;
-            const double lv = tree[left];
+            const double lv = left < staged ? s_top[left] : tree[left];
             if (v <= lv) parent = left;
             else { v -= lv; parent = left + 1; }
         }
@@ -538,7 +587,7 @@ extern "C" int gymrl_sumtree_sample(const double* d_tree, int capacity, int batc
     GYMRL_REQUIRE(d_tree && d_ring_state && d_beta && d_out_idx && d_out_is_weight && d_scratch_u32 && batch > 0 && capacity > 0, "bad arguments");
     cudaStream_t s = as_stream(stream);
     // d_scratch_u32: 2 words, zero on the first call (the kernel leaves them zero)
-    sumtree_sample_kernel<<<ceil_div(batch, 128), 128, 0, s>>>(d_tree, capacity, batch, d_uniforms, d_ring_state, d_beta, d_out_idx,
+    sumtree_sample_kernel<<<ceil_div(batch, 256), 256, 0, s>>>(d_tree, capacity, batch, d_uniforms, d_ring_state, d_beta, d_out_idx,
                                                               d_out_is_weight, d_out_priority, d_scratch_u32, return_tree_index,
                                                               seed, draw, d_draw_base);
     gymrl_count_launch();

@@ -26,6 +26,33 @@ def capture(fn, warmup: bool = True):
     return g
 
 
+class Branches:
+    """Independent launch sequences as parallel branches: fns[0] on the current stream, the others on side streams, joined
+    before returning.  Inside a CUDA-graph capture the side streams join the capture (event fork / join), so the recorded graph
+    has parallel branches; eagerly they are ordinary concurrent streams.  The off-policy updates are made of kernels of <= 128
+    small CTAs that leave most of the chip idle — the twin critics, or the online / target forwards of a double-Q update, are
+    independent and overlap (every branch must use only preallocated tensors of its own)."""
+
+    def __init__(self, n_side: int = 2):
+        self.side = [torch.cuda.Stream() for _ in range(n_side)]
+
+    def run(self, *fns):
+        if len(fns) - 1 > len(self.side):
+            raise ValueError("more branches than side streams")
+        main = torch.cuda.current_stream()
+        used = self.side[:len(fns) - 1]
+        for s in used:
+            s.wait_stream(main)
+        outs = [None] * len(fns)
+        for k, fn in enumerate(fns[1:]):
+            with torch.cuda.stream(used[k]):
+                outs[k + 1] = fn()
+        outs[0] = fns[0]()
+        for s in used:
+            main.wait_stream(s)
+        return outs
+
+
 class LockstepGraphs:
     """Mixin for the continuous-control off-policy trainers (TD3, DDPG): one captured CUDA graph per *phase* of the
     lockstep (TD3 updates the actor every `policy_freq`-th update, so its lockstep has `policy_freq` phases).
