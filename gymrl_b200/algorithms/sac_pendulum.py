@@ -123,11 +123,14 @@ class SACTrainer:
         self.q2t = Chain.from_names(self.fp_ct, Critic.Q2, B, False)
         self.memory = ReplayBuffer(cfg.memory_capacity, D, A, dev)
         from ..graphs import Branches
-        self.branches = Branches(1)          # the twin critics run as two parallel branches (side stream / graph branch)
+        # update() is recorded as a DAG: an outer three-way fork and two nested two-way forks (the twin critics)
+        self.br_outer, self.branches, self.branches_b = Branches(2), Branches(1), Branches(1)
+        self.pi_nxt = _actor_chain(self.fp_a, A, H, B, False)      # the target branch's own forward scratch
         z = lambda *s, dt=f32: torch.zeros(*s, device=dev, dtype=dt)
         self.idx = z(B, dt=i32)
         self.sa, self.sa2 = z(B, D + A), z(B, D + A)
         self.act_b, self.logp_b, self.pre_b, self.noise_b = z(B, A), z(B), z(B, A), z(B, A)
+        self.act_n, self.logp_n, self.noise_n, self.sa2n = z(B, A), z(B), z(B, A), z(B, D + A)   # the target branch's copies
         self.y = z(B)
         self.acc = z(4)            # [0] alpha*mean(logpi)  [1] sum(logpi)  [2] -mean(minQ)  [3] alpha loss
         self.closs = z(2)
@@ -185,43 +188,62 @@ class SACTrainer:
         if idx is None:
             idx = mem.sample_indices(B, seed=self.seed, draw=1, draw_base=self.ctr_upd, out=self.idx)
         lsmin, lsmax, bound = cfg.log_std_min, cfg.log_std_max, self.action_bound
-        # ---- target (ref :233-237) ----
-        out = self.pi_upd.forward(mem.next_obs, B, row_index=idx)
-        nz = noise_next if noise_next is not None else off.fill_normal(self.noise_b, seed=self.seed, entity0=0, draw=2, draw_base=self.ctr_nz)
-        ops.sample_tanh_gaussian(out[:, :A], out[:, A:], bound, lsmin, lsmax, nz, action=self.act_b, logp=self.logp_b)
-        off.gather_concat(mem.next_obs, idx, self.act_b, None, out=self.sa2, n=B)
-        q1t, q2t = self.branches.run(lambda: self.q1t.forward(self.sa2, B), lambda: self.q2t.forward(self.sa2, B))
-        off.twin_q_target(mem.reward, mem.done, q1t, q2t, cfg.gamma, row_index=idx, logp_next=self.logp_b, log_alpha=self.log_alpha,
-                          out=self.y)
-        # ---- critic (ref :239-246) ----
-        off.gather_concat(mem.obs, idx, mem.action, idx, out=self.sa, n=B)
-        q1, q2 = self.branches.run(lambda: self.q1.forward(self.sa, B), lambda: self.q2.forward(self.sa, B))
+        br, tw_a, tw_b = self.br_outer, self.branches, self.branches_b
+        # The update as a DAG (recorded as parallel branches of the lockstep graph; eagerly: concurrent streams).  Phase 1: the
+        # target y, the critics' forward on (s, a) and the actor's forward on s with its fresh action are mutually independent
+        # (each owns its scratch); inside a branch the twin critics fork again.
+
+        def target_branch():        # ---- target (ref :233-237) ----
+            out = self.pi_nxt.forward(mem.next_obs, B, row_index=idx)
+            nz = noise_next if noise_next is not None else off.fill_normal(self.noise_n, seed=self.seed, entity0=0, draw=2, draw_base=self.ctr_nz)
+            ops.sample_tanh_gaussian(out[:, :A], out[:, A:], bound, lsmin, lsmax, nz, action=self.act_n, logp=self.logp_n)
+            off.gather_concat(mem.next_obs, idx, self.act_n, None, out=self.sa2n, n=B)
+            q1t, q2t = tw_a.run(lambda: self.q1t.forward(self.sa2n, B), lambda: self.q2t.forward(self.sa2n, B))
+            off.twin_q_target(mem.reward, mem.done, q1t, q2t, cfg.gamma, row_index=idx, logp_next=self.logp_n, log_alpha=self.log_alpha,
+                              out=self.y)
+
+        def critic_forward_branch():   # ---- critic forward (ref :239-241) ----
+            off.gather_concat(mem.obs, idx, mem.action, idx, out=self.sa, n=B)
+            return tw_b.run(lambda: self.q1.forward(self.sa, B), lambda: self.q2.forward(self.sa, B))
+
+        def actor_prep_branch():    # ---- new action of the current policy (ref :248-249): does not depend on the critics ----
+            out = self.pi_upd.forward(mem.obs, B, row_index=idx)
+            nz = noise_new if noise_new is not None else off.fill_normal(self.noise_b, seed=self.seed, entity0=0, draw=3, draw_base=self.ctr_nz)
+            ops.sample_tanh_gaussian(out[:, :A], out[:, A:], bound, lsmin, lsmax, nz, action=self.act_b, logp=self.logp_b,
+                                     pre_tanh=self.pre_b)
+            off.gather_concat(mem.obs, idx, self.act_b, None, out=self.sa2, n=B)
+            return out, nz
+
+        (q1, q2), _, (out, nz) = br.run(critic_forward_branch, target_branch, actor_prep_branch)
+        # ---- critic loss / backward / step (ref :242-246) ----
         self.closs.zero_()
         off.twin_q_loss(q1, q2, self.y, self.q1.dout, self.q2.dout, self.closs)
-        self.branches.run(lambda: self.q1.backward(self.sa, B), lambda: self.q2.backward(self.sa, B))   # the twins are independent
+        tw_a.run(lambda: self.q1.backward(self.sa, B), lambda: self.q2.backward(self.sa, B))   # the twins are independent
         self.critic_optimizer.step()
-        # ---- actor (ref :248-255) ----
-        out = self.pi_upd.forward(mem.obs, B, row_index=idx)
-        nz = noise_new if noise_new is not None else off.fill_normal(self.noise_b, seed=self.seed, entity0=0, draw=3, draw_base=self.ctr_nz)
-        ops.sample_tanh_gaussian(out[:, :A], out[:, A:], bound, lsmin, lsmax, nz, action=self.act_b, logp=self.logp_b,
-                                 pre_tanh=self.pre_b)
-        off.gather_concat(mem.obs, idx, self.act_b, None, out=self.sa2, n=B)
-        q1, q2 = self.branches.run(lambda: self.q1.forward(self.sa2, B), lambda: self.q2.forward(self.sa2, B))
-        self.acc.zero_()
-        off.min_q_grad(q1, q2, self.q1.dout, self.q2.dout, acc=self.acc[2:3])
-        dx1, dx2 = self.branches.run(lambda: self.q1.backward(self.sa2, B, param_grads=False, input_grad=True),
-                                     lambda: self.q2.backward(self.sa2, B, param_grads=False, input_grad=True))
-        dx1.add_(dx2)                                       # d(-minQ/B)/d[s, a]   (torch add: tiny [B, D+A] glue)
-        dhead = self.pi_upd.dout
-        off.sac_actor_grad(self.pre_b, nz, out[:, A:], dx1[:, D:], self.log_alpha, bound, lsmin, lsmax, dhead[:, :A], dhead[:, A:],
-                           self.logp_b, self.acc)
-        self.pi_upd.backward(mem.obs, B, row_index=idx)
-        self.actor_optimizer.step()
-        # ---- alpha (ref :257-263) and target sync (ref :265) ----
-        off.sac_alpha_step(self.log_alpha, self.alpha_state, self.acc, B, self.target_entropy, cfg.lr_alpha, loss_out=self.acc[3:4])
-        self.soft_update()
-        ops.counter_add(self.ctr_upd, 1)
-        ops.counter_add(self.ctr_nz, 2)
+
+        # ---- actor (ref :250-255) through the UPDATED critics; the target sync (ref :265) only reads them: a side branch ----
+        def actor_branch():
+            q1n, q2n = tw_a.run(lambda: self.q1.forward(self.sa2, B), lambda: self.q2.forward(self.sa2, B))
+            self.acc.zero_()
+            off.min_q_grad(q1n, q2n, self.q1.dout, self.q2.dout, acc=self.acc[2:3])
+            dx1, dx2 = tw_a.run(lambda: self.q1.backward(self.sa2, B, param_grads=False, input_grad=True),
+                                lambda: self.q2.backward(self.sa2, B, param_grads=False, input_grad=True))
+            dx1.add_(dx2)                                       # d(-minQ/B)/d[s, a]   (torch add: tiny [B, D+A] glue)
+            dhead = self.pi_upd.dout
+            off.sac_actor_grad(self.pre_b, nz, out[:, A:], dx1[:, D:], self.log_alpha, bound, lsmin, lsmax, dhead[:, :A], dhead[:, A:],
+                               self.logp_b, self.acc)
+
+            def actor_step():
+                self.pi_upd.backward(mem.obs, B, row_index=idx)
+                self.actor_optimizer.step()
+
+            def alpha_and_counters():   # ---- alpha (ref :257-263): needs only the log-prob sums of sac_actor_grad ----
+                off.sac_alpha_step(self.log_alpha, self.alpha_state, self.acc, B, self.target_entropy, cfg.lr_alpha, loss_out=self.acc[3:4])
+                ops.counter_add(self.ctr_upd, 1)
+                ops.counter_add(self.ctr_nz, 2)
+            tw_b.run(actor_step, alpha_and_counters)
+
+        br.run(actor_branch, self.soft_update)
         return self.acc, self.closs
 
     # ---------------------------------------------------------------- one lockstep (ref train() loop body :278-294)
