@@ -321,7 +321,7 @@ class PPOTrainer(base.PPOTrainer):
 
     def _sample_step(self, acts, t: int):
         buf, N, A = self.buffer, self.N, self.env.n_actions
-        ops.sample_categorical(acts.lv[:, :A], seed=self.seed, first_id=self.rank * N, draw_base=self.ctr_action,
+        ops.sample_categorical(acts.lv[:, :A], seed=self.seed, first_id=self.rank * N, draw=t, draw_base=self.ctr_action,
                                action=buf.action[t], logp=buf.log_prob[t], entropy=buf.entropy[t], value_in=acts.lv[:, A:A + 1],
                                value_out=buf.value[t])
 

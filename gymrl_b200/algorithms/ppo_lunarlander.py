@@ -325,7 +325,7 @@ class PPOTrainer:
 
     def _sample_step(self, acts, t: int):
         buf, N, A = self.buffer, self.N, self.env.n_actions
-        ops.sample_categorical(acts.lv[:, :A], seed=self.seed, first_id=self.rank * N, draw_base=self.ctr_action,
+        ops.sample_categorical(acts.lv[:, :A], seed=self.seed, first_id=self.rank * N, draw=t, draw_base=self.ctr_action,
                                action=buf.action[t], logp=buf.log_prob[t], value_in=acts.lv[:, A:A + 1],
                                value_out=buf.value[t])
 
@@ -341,10 +341,10 @@ class PPOTrainer:
         N, A = self.N, self.env.n_actions
         for t in range(self.T):
             net.forward(buf.obs[t], acts, N)
-            self._sample_step(acts, t)
-            ops.counter_add(self.ctr_action, 1)
+            self._sample_step(acts, t)     # draw index = device counter + t: the counter advances once per rollout, not per step
             env.step(buf.action[t], obs=buf.obs[t + 1], reward=buf.reward[t], terminated=self.term, truncated=self.trunc,
                      want_next_obs=False, done=buf.done[t])
+        ops.counter_add(self.ctr_action, self.T)
         net.forward(buf.obs[self.T], acts, N)
         buf.v_last.copy_(acts.lv[:, A])
 

@@ -965,10 +965,8 @@ __global__ void __launch_bounds__(ws::THREADS, 1) gemm3x_ws_kernel(const TcGemmP
             };
             const bool do_pf = !(dbg_flags & 8);
             if (do_pf) {
-                // the first slabs are fetched by the producers themselves at kernel start: begin one slab past them
+                // the first slabs are fetched by the producers themselves at kernel start: begin past them
                 for (int i = 0; i < 2 && pf_tile < n_tiles; ++i) { if (++pf_kb == nslab) { pf_kb = 0; pf_tile += n_clusters; } }
-#pragma unroll 1
-                for (int i = 0; i < PF; ++i) pf_issue();
             }
             uint32_t it = 0;
             for (int tile = cluster_id; tile < n_tiles; tile += n_clusters) {
@@ -986,7 +984,13 @@ __global__ void __launch_bounds__(ws::THREADS, 1) gemm3x_ws_kernel(const TcGemmP
                         if ((int)it == nslab - 1) WS_STAMP(17);
                     }
                     __syncwarp();
-                    if (do_pf) pf_issue();
+                    if (do_pf) {
+                        if (it == 0) {   // the look-ahead is opened AFTER the first weight box is in flight (it delayed that box by 0.6 us)
+#pragma unroll 1
+                            for (int i = 0; i < PF; ++i) pf_issue();
+                        }
+                        pf_issue();
+                    }
                 }
             }
         }
