@@ -96,7 +96,7 @@ SIGNATURES = {
     "gymrl_reward_scaling": (c_int, [_P, _P, _P, _P, c_double, _P, c_int, _P]),
     "gymrl_mhc_workspace_bytes": (c_size_t, [c_int, c_int, c_int]),
     "gymrl_mhc_stage_forward": (c_int, [_P, c_int, c_int, _P, _P, _P, _P, _P, _P, _P, _P, _P, _P, _P, c_int, c_int, c_int, c_float, _P]),
-    "gymrl_mhc_stage_backward_a": (c_int, [_P, c_int, c_int, _P, _P, _P, _P, _P, _P, _P, _P, _P, c_int, c_int, c_int, _P]),
+    "gymrl_mhc_stage_backward_a": (c_int, [_P, c_int, c_int, _P, _P, _P, _P, _P, c_int, c_int, _P]),
     "gymrl_mhc_stage_backward_b": (c_int, [_P, c_int, c_int, _P, _P, _P, _P, _P, _P, _P, _P, _P, _P, _P, _P, _P, c_size_t, c_int,
                                            c_int, c_int, _P]),
     "gymrl_rmsnorm_forward": (c_int, [_P, c_int, c_int, c_int, _P, _P, c_int, c_int, c_int, c_int, c_float, _P]),

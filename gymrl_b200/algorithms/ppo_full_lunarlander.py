@@ -171,7 +171,7 @@ class _Acts:
         self.M = M
         self.x0 = e(M, D)                                   # input_proj output = both branches of the stage-0 input
         self.h = [None] + [e(M, 2 * D) for _ in range(S)]   # h[s] = input of stage s (s >= 1), h[S] = backbone output
-        self.coef = [e(M, 8) for _ in range(S)]
+        self.coef = [e(M, 24) for _ in range(S)]     # per stage: pre/post | P | r_ s dpost | dP | H (forward writes, backward completes)
         self.hpre = [e(M, D) for _ in range(S)]
         self.z = [e(M, D) for _ in range(S)]
         self.feat = e(M, D)
@@ -184,7 +184,6 @@ class _Acts:
             self.dfeat = e(M, D)
             self.dh_a, self.dh_b = e(M, 2 * D), e(M, 2 * D)  # ping-pong: dL/dh[s+1] and the partial / full dL/dh[s]
             self.dz, self.dhpre = e(M, D), e(M, D)
-            self.scratch = e(M, 24)
             self.dx0 = e(M, D)
 
 
@@ -265,12 +264,12 @@ class ActorCriticEngine:
         ops.rmsnorm_backward(acts.h[S], self.gf, acts.dfeat, acts.dh_a, self.ggf, M=M, W=D, groups=1, sum2=True, workspace=wr)
         for s in range(S - 1, -1, -1):
             src, rs, bs = (acts.x0, D, 0) if s == 0 else (acts.h[s], 2 * D, D)
-            ops.mhc_stage_backward_a(src, acts.z[s], acts.dh_a, self.stage[s], D=D, row_stride=rs, branch_stride=bs, M=M, dz=acts.dz,
-                                     dh_partial=acts.dh_b, scratch=acts.scratch, sk_iters=self.sk)
+            ops.mhc_stage_backward_a(src, acts.z[s], acts.dh_a, D=D, row_stride=rs, branch_stride=bs, M=M, dz=acts.dz,
+                                     dh_partial=acts.dh_b, coef=acts.coef[s])
             W, _ = self.lin[s]
             gW, gb = self.glin[s]
             ops.linear_backward(acts.dz, acts.hpre[s], W, gW, gb, dx=acts.dhpre, act_in=N_, workspace=ws, M=M)
-            ops.mhc_stage_backward_b(src, acts.dhpre, acts.scratch, acts.dh_b, self.stage[s], self.gstage[s], D=D, row_stride=rs,
+            ops.mhc_stage_backward_b(src, acts.dhpre, acts.coef[s], acts.dh_b, self.stage[s], self.gstage[s], D=D, row_stride=rs,
                                      branch_stride=bs, M=M, workspace=wr, dh=None if s == 0 else acts.dh_a,
                                      dx0=acts.dx0 if s == 0 else None)
         ops.linear_backward(acts.dx0, x, self.Win, self.gWin, self.gbin, row_index=row_index, workspace=ws, M=M)

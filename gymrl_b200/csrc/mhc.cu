@@ -145,7 +145,7 @@ mhc_stage_fwd_kernel(const float* __restrict__ h_prev, int prev_row_stride, int 
             for (int j = 0; j < NCH; ++j) h[i][j] = ld4(hp + (size_t)i * prev_branch_stride + 128 * j + 4 * lane);
         if (z_prev) {
             // depth_connection of the previous stage (ref :190-194): h'_i = post_i silu(z) + sum_j P_ij h_j
-            const float4 c0 = ld4(coef_prev + (size_t)row * 8), c1 = ld4(coef_prev + (size_t)row * 8 + 4);
+            const float4 c0 = ld4(coef_prev + (size_t)row * 24), c1 = ld4(coef_prev + (size_t)row * 24 + 4);
             float4 hn[2][NCH];
 #pragma unroll
             for (int j = 0; j < NCH; ++j) {
@@ -166,8 +166,15 @@ mhc_stage_fwd_kernel(const float* __restrict__ h_prev, int prev_row_stride, int 
             Coef c;
             stage_coefficients<NCH>(h, sp, sk_iters, c);
             if (lane == 0) {
-                st4(coef_cur + (size_t)row * 8, make_float4(c.pre[0], c.pre[1], c.post[0], c.post[1]));
-                st4(coef_cur + (size_t)row * 8 + 4, make_float4(c.P[0][0], c.P[0][1], c.P[1][0], c.P[1][1]));
+                // the whole mapping of the row is kept (24 floats, the layout the backward kernels use): the backward pass reads it
+                // back instead of re-running the 8 projections and the Sinkhorn chain on every row
+                float* sc = coef_cur + (size_t)row * 24;
+                st4(sc, make_float4(c.pre[0], c.pre[1], c.post[0], c.post[1]));
+                st4(sc + 4, make_float4(c.P[0][0], c.P[0][1], c.P[1][0], c.P[1][1]));
+                st4(sc + 8, make_float4(c.r_, c.s, 0.f, 0.f));
+                st4(sc + 12, make_float4(0.f, 0.f, 0.f, 0.f));
+                st4(sc + 16, make_float4(c.H[0], c.H[1], c.H[2], c.H[3]));
+                st4(sc + 20, make_float4(c.H[4], c.H[5], c.H[6], c.H[7]));
             }
 #pragma unroll
             for (int j = 0; j < NCH; ++j)
@@ -193,22 +200,24 @@ mhc_stage_fwd_kernel(const float* __restrict__ h_prev, int prev_row_stride, int 
 // ---------------------------------------------------------------------------------------------------------------
 // backward, part A (before the stage's GEMM backward): from dh' = dL/dh_{s+1}
 //     dz = (sum_i post_i dh'_i) silu'(z);  dh_partial_j = sum_i P_ij dh'_i;  dpost_i = <dh'_i, silu(z)>;  dP_ij = <dh'_i, h_j>
-// scratch row [24] = pre0 pre1 post0 post1 | P00 P01 P10 P11 | r_ s dpost0 dpost1 | dP00 dP01 dP10 dP11 | H0..H7
+// coef row [24] = pre0 pre1 post0 post1 | P00 P01 P10 P11 | r_ s dpost0 dpost1 | dP00 dP01 dP10 dP11 | H0..H7
+// The forward pass left the row's mapping there (pre / post / P / r_ / s / H); this kernel adds the six inner products.  (Round 1
+// re-ran the mapping here: 8 projections, 9 warp reductions and the 40-reciprocal Sinkhorn chain per row, with the stage
+// parameters in 64+ registers per lane — 149 registers, one block per SM.  Now it is a streaming pass.)
 // ---------------------------------------------------------------------------------------------------------------
 template <int NCH>
 __global__ void __launch_bounds__(kWarpsPerBlock * 32)
 mhc_stage_bwd_a_kernel(const float* __restrict__ h_in, int row_stride, int branch_stride, const float* __restrict__ z,
-                       const float* __restrict__ dh_next, const float* __restrict__ g, const float* __restrict__ w,
-                       const float* __restrict__ alpha, const float* __restrict__ beta, float* __restrict__ dz,
-                       float* __restrict__ dh_partial, float* __restrict__ scratch, int M, int sk_iters) {
+                       const float* __restrict__ dh_next, float* __restrict__ dz, float* __restrict__ dh_partial,
+                       float* __restrict__ coef, int M) {
     constexpr int D = 128 * NCH;
     const int lane = threadIdx.x & 31;
     const int warp = blockIdx.x * kWarpsPerBlock + (threadIdx.x >> 5), nwarps = gridDim.x * kWarpsPerBlock;
-    StageParams<NCH> sp;
-    sp.load(g, w, alpha, beta, lane);
     for (int row = warp; row < M; row += nwarps) {
         float4 h[2][NCH], d[2][NCH];
         const float* hp = h_in + (size_t)row * row_stride;
+        float* sc = coef + (size_t)row * 24;
+        const float4 s0 = ld4(sc), s1 = ld4(sc + 4), s2 = ld4(sc + 8);
 #pragma unroll
         for (int i = 0; i < 2; ++i)
 #pragma unroll
@@ -216,8 +225,7 @@ mhc_stage_bwd_a_kernel(const float* __restrict__ h_in, int row_stride, int branc
                 h[i][j] = ld4(hp + (size_t)i * branch_stride + 128 * j + 4 * lane);
                 d[i][j] = ld4(dh_next + (size_t)row * 2 * D + (size_t)i * D + 128 * j + 4 * lane);
             }
-        Coef c;
-        stage_coefficients<NCH>(h, sp, sk_iters, c);
+        const float post0 = s0.z, post1 = s0.w, P00 = s1.x, P01 = s1.y, P10 = s1.z, P11 = s1.w;
         float red[6];
 #pragma unroll
         for (int k = 0; k < 6; ++k) red[k] = 0.f;
@@ -226,24 +234,19 @@ mhc_stage_bwd_a_kernel(const float* __restrict__ h_in, int row_stride, int branc
             const float4 zz = ld4(z + (size_t)row * D + 128 * j + 4 * lane);
             const float4 ho = make_float4(siluf_(zz.x), siluf_(zz.y), siluf_(zz.z), siluf_(zz.w));
             const float4 sg = make_float4(silu_gradf_(zz.x), silu_gradf_(zz.y), silu_gradf_(zz.z), silu_gradf_(zz.w));
-            const float4 dho = axpy4(c.post[0], d[0][j], scale4(c.post[1], d[1][j]));
+            const float4 dho = axpy4(post0, d[0][j], scale4(post1, d[1][j]));
             st4(dz + (size_t)row * D + 128 * j + 4 * lane, mul4(dho, sg));
             red[0] += dot4(d[0][j], ho); red[1] += dot4(d[1][j], ho);
             red[2] += dot4(d[0][j], h[0][j]); red[3] += dot4(d[0][j], h[1][j]);
             red[4] += dot4(d[1][j], h[0][j]); red[5] += dot4(d[1][j], h[1][j]);
-            st4(dh_partial + (size_t)row * 2 * D + 128 * j + 4 * lane, axpy4(c.P[0][0], d[0][j], scale4(c.P[1][0], d[1][j])));
-            st4(dh_partial + (size_t)row * 2 * D + D + 128 * j + 4 * lane, axpy4(c.P[0][1], d[0][j], scale4(c.P[1][1], d[1][j])));
+            st4(dh_partial + (size_t)row * 2 * D + 128 * j + 4 * lane, axpy4(P00, d[0][j], scale4(P10, d[1][j])));
+            st4(dh_partial + (size_t)row * 2 * D + D + 128 * j + 4 * lane, axpy4(P01, d[0][j], scale4(P11, d[1][j])));
         }
 #pragma unroll
         for (int k = 0; k < 6; ++k) red[k] = warp_sum(red[k]);
         if (lane == 0) {
-            float* sc = scratch + (size_t)row * 24;
-            st4(sc, make_float4(c.pre[0], c.pre[1], c.post[0], c.post[1]));
-            st4(sc + 4, make_float4(c.P[0][0], c.P[0][1], c.P[1][0], c.P[1][1]));
-            st4(sc + 8, make_float4(c.r_, c.s, red[0], red[1]));
+            st4(sc + 8, make_float4(s2.x, s2.y, red[0], red[1]));
             st4(sc + 12, make_float4(red[2], red[3], red[4], red[5]));
-            st4(sc + 16, make_float4(c.H[0], c.H[1], c.H[2], c.H[3]));
-            st4(sc + 20, make_float4(c.H[4], c.H[5], c.H[6], c.H[7]));
         }
     }
 }
@@ -534,19 +537,14 @@ extern "C" int gymrl_mhc_stage_forward(const float* h_prev, int prev_row_stride,
 }
 
 extern "C" int gymrl_mhc_stage_backward_a(const float* h, int row_stride, int branch_stride, const float* z, const float* dh_next,
-                                          const float* g, const float* w, const float* alpha, const float* beta, float* dz,
-                                          float* dh_partial, float* scratch, int M, int D, int sk_iters, void* stream) {
-    GYMRL_REQUIRE(h && z && dh_next && g && w && alpha && beta && dz && dh_partial && scratch, "NULL argument");
+                                          float* dz, float* dh_partial, float* coef, int M, int D, void* stream) {
+    GYMRL_REQUIRE(h && z && dh_next && dz && dh_partial && coef, "NULL argument");
     GYMRL_REQUIRE(D == 128 || D == 256, "mHC kernels are built for mhc_dim 128 or 256 (got %d)", D);
     if (M == 0) return GYMRL_OK;
     cudaStream_t s = as_stream(stream);
     const int grid = grid_for_rows(M);
-    if (D == 128)
-        mhc_stage_bwd_a_kernel<1><<<grid, kWarpsPerBlock * 32, 0, s>>>(h, row_stride, branch_stride, z, dh_next, g, w, alpha, beta, dz,
-                                                                       dh_partial, scratch, M, sk_iters);
-    else
-        mhc_stage_bwd_a_kernel<2><<<grid, kWarpsPerBlock * 32, 0, s>>>(h, row_stride, branch_stride, z, dh_next, g, w, alpha, beta, dz,
-                                                                       dh_partial, scratch, M, sk_iters);
+    if (D == 128) mhc_stage_bwd_a_kernel<1><<<grid, kWarpsPerBlock * 32, 0, s>>>(h, row_stride, branch_stride, z, dh_next, dz, dh_partial, coef, M);
+    else mhc_stage_bwd_a_kernel<2><<<grid, kWarpsPerBlock * 32, 0, s>>>(h, row_stride, branch_stride, z, dh_next, dz, dh_partial, coef, M);
     gymrl_count_launch();
     GYMRL_LAUNCH_CHECK("mhc_stage_backward_a");
     return GYMRL_OK;

@@ -422,11 +422,10 @@ def mhc_stage_forward(h_prev, *, D, row_stride, branch_stride, M, z_prev=None, c
                                          float(eps), stream_ptr()))
 
 
-def mhc_stage_backward_a(h, z, dh_next, params, *, D, row_stride, branch_stride, M, dz, dh_partial, scratch, sk_iters=10):
-    g, w, al, be = params
+def mhc_stage_backward_a(h, z, dh_next, *, D, row_stride, branch_stride, M, dz, dh_partial, coef):
+    """coef: the stage's [M, 24] coefficient rows written by mhc_stage_forward (in/out: gains dpost / dP)."""
     check(load().gymrl_mhc_stage_backward_a(ptr(h, f32), int(row_stride), int(branch_stride), ptr(z, f32), ptr(dh_next, f32),
-                                            ptr(g, f32), ptr(w, f32), ptr(al, f32), ptr(be, f32), ptr(dz, f32), ptr(dh_partial, f32),
-                                            ptr(scratch, f32), int(M), int(D), int(sk_iters), stream_ptr()))
+                                            ptr(dz, f32), ptr(dh_partial, f32), ptr(coef, f32), int(M), int(D), stream_ptr()))
 
 
 def mhc_stage_backward_b(h, dh_pre, scratch, dh_partial, params, grads, *, D, row_stride, branch_stride, M, workspace, dh=None,

@@ -514,19 +514,20 @@ size_t gymrl_mhc_workspace_bytes(int D, int head_width, int head_groups);
 /* One fused row-wise pass between two GEMMs of the backbone forward:
  *   (z_prev != NULL)  h_cur = depth_connection(prev stage) = post_i silu(z_prev) + sum_j P_ij h_prev_j, stored [M][2][D];
  *                     otherwise the row is h_prev itself (not stored);
- *   (g != NULL)       mapping() of the next stage on that row: coef_cur [M][8] = {pre0 pre1 post0 post1 P00 P01 P10 P11},
+ *   (g != NULL)       mapping() of the next stage on that row: coef_cur [M][24] = {pre0 pre1 post0 post1 | P00 P01 P10 P11 |
+ *                     r_ s 0 0 | 0 0 0 0 | H0..H7} (the mapping is kept whole for the backward pass; coef_prev has the same layout),
  *                     h_pre [M][D] = sum_i pre_i h_i (the next GEMM's input);
  *   (final_weight)    feat [M][D] = RMSNorm(h_0 + h_1) * final_weight  (MHCBackbone.forward :263-267). */
 int gymrl_mhc_stage_forward(const float* d_h_prev, int prev_row_stride, int prev_branch_stride, const float* d_z_prev,
                             const float* d_coef_prev, float* d_h_cur, const float* d_g, const float* d_w, const float* d_alpha,
                             const float* d_beta, float* d_coef_cur, float* d_h_pre, const float* d_final_weight, float* d_feat,
                             int M, int D, int sk_iters, float eps, void* stream);
-/* Backward of one stage, split around its GEMM backward.  A: from d_dh_next = dL/d(stage output) [M][2][D] and the saved
- * stage input h and GEMM output z: dz [M][D] (the GEMM's upstream gradient), dh_partial [M][2][D], scratch [M][24]. */
+/* Backward of one stage, split around its GEMM backward.  A: from d_dh_next = dL/d(stage output) [M][2][D], the saved stage
+ * input h, the GEMM output z and the stage's coefficient rows d_coef [M][24] as the forward pass left them: dz [M][D] (the
+ * GEMM's upstream gradient), dh_partial [M][2][D], and the six inner products dpost_i, dP_ij into d_coef[:, 10:16]. */
 int gymrl_mhc_stage_backward_a(const float* d_h, int row_stride, int branch_stride, const float* d_z, const float* d_dh_next,
-                               const float* d_g, const float* d_w, const float* d_alpha, const float* d_beta, float* d_dz,
-                               float* d_dh_partial, float* d_scratch, int M, int D, int sk_iters, void* stream);
-/* B: with d_dh_pre = dz @ W [M][D]: the full input gradient (d_dh [M][2][D], or its branch sum d_dx0 [M][D] when that is
+                               float* d_dz, float* d_dh_partial, float* d_coef, int M, int D, void* stream);
+/* B (d_scratch = the d_coef rows after A): with d_dh_pre = dz @ W [M][D]: the full input gradient (d_dh [M][2][D], or its branch sum d_dx0 [M][D] when that is
  * non-NULL) and the parameter gradients of mhc.norm.weight (dg [2D]), mhc.w (dw [2D][8]), alpha [3], beta [8]. */
 int gymrl_mhc_stage_backward_b(const float* d_h, int row_stride, int branch_stride, const float* d_dh_pre, const float* d_scratch,
                                const float* d_dh_partial, float* d_dh, float* d_dx0, const float* d_g, const float* d_w,
