@@ -217,6 +217,13 @@ class ActorCriticEngine:
         self.ggh = fp.span("actor.mlp.2.weight", "critic.mlp.2.weight", 1, 2 * HW, grad=True).view(2 * HW)
         self.Wa, self.ba, self.gWa, self.gba = P("actor.mlp.3.weight"), P("actor.mlp.3.bias"), G("actor.mlp.3.weight"), G("actor.mlp.3.bias")
         self.Wc, self.bc, self.gWc, self.gbc = P("critic.mlp.3.weight"), P("critic.mlp.3.bias"), G("critic.mlp.3.weight"), G("critic.mlp.3.bias")
+        # the D x D layers and the head trunk are TMA-fed from pre-split tf32 weight images (csrc/wimages.cu): at the update's
+        # 131072-row minibatches they run on the persistent warp-specialised GEMM (128-wide pair tiles for the D = 128 layers)
+        if D % 128 == 0 and (2 * HW) % 128 == 0:
+            mats = [(f"shared.layers.{l}.linear{k}.weight", f"shared.layers.{l}.linear{k}.weight", D, D)
+                    for l in range(model.n_layers) for k in (1, 2)]
+            mats.append(("actor.mlp.0.weight", "critic.mlp.0.weight", 2 * HW, D))
+            fp.enable_weight_images(mats)
         self.workspace = None
         self.ws_rows = None
 

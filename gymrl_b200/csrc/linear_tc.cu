@@ -732,22 +732,23 @@ static int launch_tc_ts(const TcGemmParams& p, int splits, cudaStream_t s) {
 #include <cuda.h>   // CUtensorMap (types only: the encoder is fetched through cudaGetDriverEntryPoint, no libcuda link)
 
 namespace ws {
-constexpr int BM = 128, BN = 256;
+constexpr int BM = 128;     // rows per CTA; the tile width BN (256 or 128 output columns) is a template parameter
 constexpr int PROD_WARPS = 4, EPI_WARPS = 8;
 constexpr int TMA_WARP = 4, MMA_WARP = 5, RELAY_WARP = 6, EPI_WARP0 = 7;
 constexpr int THREADS = (EPI_WARP0 + EPI_WARPS) * 32;   // 448
 constexpr int PROD_THREADS = PROD_WARPS * 32;           // 128
 constexpr int A_PASSES = BM * 8 / PROD_THREADS;         // float4 per producer thread per slab (8)
 
-template <int NCTA>
+template <int NCTA, int BN>
 struct Cfg {
     static constexpr int B_ROWS = BN / NCTA;                           // B rows (output columns) this CTA stages
     static constexpr uint32_t A_BYTES = BM * 128;                      // one image of one 32-k slab
     static constexpr uint32_t B_BYTES = B_ROWS * 128;
-    static constexpr uint32_t STAGE_BYTES = 2 * A_BYTES + 2 * B_BYTES;   // 64 KB (pair) / 96 KB (single CTA)
-    static constexpr int NST = NCTA == 2 ? 3 : 2;
+    static constexpr uint32_t STAGE_BYTES = 2 * A_BYTES + 2 * B_BYTES;   // BN = 256: 64 KB (pair) / 96 KB (single CTA); BN = 128: 48 / 64 KB
+    static constexpr int NST = (int)((227u * 1024u - 33u * 1024u) / STAGE_BYTES) > 4 ? 4 : (int)((227u * 1024u - 33u * 1024u) / STAGE_BYTES);
     static constexpr uint32_t EPI_SCRATCH = EPI_WARPS * 4096;
     static constexpr size_t SMEM = (size_t)NST * STAGE_BYTES + EPI_SCRATCH + 1024;
+    static constexpr int TMEM_COLS = 2 * BN;                           // two accumulators
 };
 
 __device__ __forceinline__ uint32_t cluster_ctarank() {
@@ -819,13 +820,13 @@ __device__ __forceinline__ void tma_load_b(uint32_t smem_dst, const CUtensorMap*
 }
 }  // namespace ws
 
-template <int NCTA>
+template <int NCTA, int BN>
 __global__ void __launch_bounds__(ws::THREADS, 1) gemm3x_ws_kernel(const TcGemmParams p, const __grid_constant__ CUtensorMap tmap_b,
                                                                    int tiles_m, int tiles_n) {
     const int dbg_flags = p.bn_max;   // developer probe (GYMRL_TC_WS_DBG): 1 = producers skip their st.shared, 2 = only the hi*hi MMA, 4 = no TMA
-    using C = ws::Cfg<NCTA>;
+    using C = ws::Cfg<NCTA, BN>;
     constexpr int NST = C::NST;
-    constexpr int BM = ws::BM, BN = ws::BN;
+    constexpr int BM = ws::BM;
     extern __shared__ __align__(1024) uint8_t smem_raw[];
     uint8_t* smem = reinterpret_cast<uint8_t*>((reinterpret_cast<uintptr_t>(smem_raw) + 1023) & ~(uintptr_t)1023);
     __shared__ __align__(8) uint64_t bar_full[NST];
@@ -861,10 +862,10 @@ __global__ void __launch_bounds__(ws::THREADS, 1) gemm3x_ws_kernel(const TcGemmP
     }
     if (warp == ws::MMA_WARP) {   // the same warp of both CTAs allocates (and later frees) all 512 TMEM columns: two accumulators
         if (NCTA == 2) {
-            asm volatile("tcgen05.alloc.cta_group::2.sync.aligned.shared::cta.b32 [%0], %1;" ::"r"(smem_u32(&tmem_base_s)), "n"(512) : "memory");
+            asm volatile("tcgen05.alloc.cta_group::2.sync.aligned.shared::cta.b32 [%0], %1;" ::"r"(smem_u32(&tmem_base_s)), "n"(C::TMEM_COLS) : "memory");
             asm volatile("tcgen05.relinquish_alloc_permit.cta_group::2.sync.aligned;" ::: "memory");
         } else {
-            asm volatile("tcgen05.alloc.cta_group::1.sync.aligned.shared::cta.b32 [%0], %1;" ::"r"(smem_u32(&tmem_base_s)), "n"(512) : "memory");
+            asm volatile("tcgen05.alloc.cta_group::1.sync.aligned.shared::cta.b32 [%0], %1;" ::"r"(smem_u32(&tmem_base_s)), "n"(C::TMEM_COLS) : "memory");
             asm volatile("tcgen05.relinquish_alloc_permit.cta_group::1.sync.aligned;" ::: "memory");
         }
     }
@@ -1085,8 +1086,8 @@ __global__ void __launch_bounds__(ws::THREADS, 1) gemm3x_ws_kernel(const TcGemmP
     if (NCTA == 2) ws::cluster_sync_all(); else __syncthreads();
     if (t == 0) WS_STAMP(2);
     if (warp == ws::MMA_WARP) {
-        if (NCTA == 2) asm volatile("tcgen05.dealloc.cta_group::2.sync.aligned.b32 %0, %1;" ::"r"(tmem_d), "n"(512) : "memory");
-        else asm volatile("tcgen05.dealloc.cta_group::1.sync.aligned.b32 %0, %1;" ::"r"(tmem_d), "n"(512) : "memory");
+        if (NCTA == 2) asm volatile("tcgen05.dealloc.cta_group::2.sync.aligned.b32 %0, %1;" ::"r"(tmem_d), "n"(C::TMEM_COLS) : "memory");
+        else asm volatile("tcgen05.dealloc.cta_group::1.sync.aligned.b32 %0, %1;" ::"r"(tmem_d), "n"(C::TMEM_COLS) : "memory");
     }
 }
 
@@ -1114,9 +1115,9 @@ static int ws_mode() {
 static unsigned long long g_ws_launches = 0;
 extern "C" unsigned long long gymrl_debug_ws_launches(void) { return g_ws_launches; }   // developer probe (tests: the ws path really ran)
 
-template <int NCTA>
+template <int NCTA, int BN>
 static int launch_ws(const TcGemmParams& p, const float* b_hi, long long img_stride, int b_rows_total, cudaStream_t s) {
-    using C = ws::Cfg<NCTA>;
+    using C = ws::Cfg<NCTA, BN>;
     PFN_encodeTiled enc = get_encode_tiled();
     if (!enc) GYMRL_FAIL(GYMRL_ECUDA, "cuTensorMapEncodeTiled is not available from this driver");
     CUtensorMap map;
@@ -1130,11 +1131,11 @@ static int launch_ws(const TcGemmParams& p, const float* b_hi, long long img_str
     if (r != CUDA_SUCCESS) GYMRL_FAIL(GYMRL_ECUDA, "cuTensorMapEncodeTiled failed (%d)", (int)r);
     static bool configured = false;
     if (!configured) {
-        cudaError_t e = cudaFuncSetAttribute(gemm3x_ws_kernel<NCTA>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)C::SMEM);
+        cudaError_t e = cudaFuncSetAttribute(gemm3x_ws_kernel<NCTA, BN>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)C::SMEM);
         if (e != cudaSuccess) GYMRL_FAIL(GYMRL_ECUDA, "cudaFuncSetAttribute(smem=%zu) failed: %s", C::SMEM, cudaGetErrorString(e));
         configured = true;
     }
-    const int tiles_m = ceil_div(p.M, ws::BM * NCTA), tiles_n = p.N / ws::BN;
+    const int tiles_m = ceil_div(p.M, ws::BM * NCTA), tiles_n = p.N / BN;
     const int n_tiles = tiles_m * tiles_n;
     cudaLaunchConfig_t cfg;
     memset(&cfg, 0, sizeof(cfg));
@@ -1153,10 +1154,10 @@ static int launch_ws(const TcGemmParams& p, const float* b_hi, long long img_str
         cfg.gridDim = dim3(GYMRL_NUM_SMS / NCTA * NCTA);
         cfg.attrs = attr; cfg.numAttrs = na;
         int n = 0;
-        if (NCTA == 2 && cudaOccupancyMaxActiveClusters(&n, gemm3x_ws_kernel<NCTA>, &cfg) == cudaSuccess && n > 0) max_clusters = n;
+        if (NCTA == 2 && cudaOccupancyMaxActiveClusters(&n, gemm3x_ws_kernel<NCTA, BN>, &cfg) == cudaSuccess && n > 0) max_clusters = n;
         else max_clusters = GYMRL_NUM_SMS / NCTA;
         (void)cudaGetLastError();
-        if (getenv("GYMRL_TC_VERBOSE")) fprintf(stderr, "[gymrl] gemm3x_ws_kernel<%d>: %d co-resident clusters\n", NCTA, max_clusters);
+        if (getenv("GYMRL_TC_VERBOSE")) fprintf(stderr, "[gymrl] gemm3x_ws_kernel<%d, %d>: %d co-resident clusters\n", NCTA, BN, max_clusters);
     }
     int clusters = max_clusters < n_tiles ? max_clusters : n_tiles;
     cfg.gridDim = dim3(clusters * NCTA);
@@ -1169,8 +1170,8 @@ static int launch_ws(const TcGemmParams& p, const float* b_hi, long long img_str
     TcGemmParams pk = p;
     static const int dbg = [] { const char* e = getenv("GYMRL_TC_WS_DBG"); return e ? atoi(e) : 0; }();
     pk.bn_max = dbg;
-    cudaError_t e = cudaLaunchKernelEx(&cfg, gemm3x_ws_kernel<NCTA>, pk, map, tiles_m, tiles_n);
-    if (e != cudaSuccess) GYMRL_FAIL(GYMRL_ECUDA, "launch of gemm3x_ws_kernel<%d> failed: %s", NCTA, cudaGetErrorString(e));
+    cudaError_t e = cudaLaunchKernelEx(&cfg, gemm3x_ws_kernel<NCTA, BN>, pk, map, tiles_m, tiles_n);
+    if (e != cudaSuccess) GYMRL_FAIL(GYMRL_ECUDA, "launch of gemm3x_ws_kernel<%d, %d> failed: %s", NCTA, BN, cudaGetErrorString(e));
     gymrl_count_launch();
     ++g_ws_launches;
     return GYMRL_OK;
@@ -1180,22 +1181,30 @@ static int launch_ws(const TcGemmParams& p, const float* b_hi, long long img_str
 // ungathered, the output is at least 256 columns wide in whole tiles and there are enough tiles to occupy the chip.
 static bool ws_try_launch(const TcGemmParams& p, bool a_kmajor, bool b_kmajor, int splits, cudaStream_t s, int* rc) {
     const int mode = ws_mode();
-    if (mode == 0 || !a_kmajor || splits != 1 || p.a_rows || p.b_rows || p.N % ws::BN != 0 || p.K % 32 != 0 || p.K < 64) return false;
+    if (mode == 0 || !a_kmajor || splits != 1 || p.a_rows || p.b_rows || p.N % 128 != 0 || p.K % 32 != 0 || p.K < 64) return false;
     if (p.ldb != (b_kmajor ? p.K : p.N)) return false;
     const int ncta = mode == 1 ? 1 : 2;
-    const long long tiles = (long long)ceil_div(p.M, ws::BM * ncta) * (p.N / ws::BN);
     // Measured (tools/ws_gemm_bench.py, M = 16384, in a CUDA graph): with >= 2 tiles per CTA pair the overlapped epilogue wins
     // (N = 512 forward: 32.3 us vs 35.9 us); with a single tile per pair nothing overlaps and the one-tile-per-CTA kernel's
     // shorter set-up wins (N = 256: 20.9 vs 19.6 us).  GYMRL_TC_WS_MIN_TILES overrides the threshold (A/B runs).
+    // 128-wide pair tiles (BN = 128) serve the narrow layers of long batches (PPO-full: 131072 x 128 x 128 = 512 tiles, where the
+    // one-tile-per-CTA kernel spends most of a CTA's life in set-up and epilogue): GYMRL_TC_WS_BN128_MIN_TILES, default 200.
     const char* mt_env = getenv("GYMRL_TC_WS_MIN_TILES");     // read per call: the test-suite flips it inside one process
     const long long min_tiles = mt_env ? atoll(mt_env) : 0ll;
     const long long need = min_tiles > 0 ? min_tiles : (ncta == 2 ? 100 : 200);
-    if (tiles < need) return false;
+    const char* mt128_env = getenv("GYMRL_TC_WS_BN128_MIN_TILES");
+    const long long need128 = mt128_env ? atoll(mt128_env) : 200ll;
+    const long long rows_t = (long long)ceil_div(p.M, ws::BM * ncta);
+    int bn = 0;
+    if (p.N % 256 == 0 && rows_t * (p.N / 256) >= need) bn = 256;
+    else if (ncta == 2 && need128 > 0 && rows_t * (p.N / 128) >= need128) bn = 128;
+    if (bn == 0) return false;
     const float* hi = nullptr;
     long long stride = 0;
     // forward: B = W [N][K];  backward-input: B = W [K][N] read as W^T [N][K] from the transposed images
     if (!(b_kmajor ? wimg_lookup(p.B, p.N, p.K, false, &hi, &stride) : wimg_lookup(p.B, p.K, p.N, true, &hi, &stride))) return false;
-    *rc = ncta == 2 ? launch_ws<2>(p, hi, stride, p.N, s) : launch_ws<1>(p, hi, stride, p.N, s);
+    if (bn == 128) *rc = launch_ws<2, 128>(p, hi, stride, p.N, s);
+    else *rc = ncta == 2 ? launch_ws<2, 256>(p, hi, stride, p.N, s) : launch_ws<1, 256>(p, hi, stride, p.N, s);
     return true;
 }
 

@@ -220,13 +220,14 @@ ppo_heads_fused_kernel(const float* __restrict__ h, int ldh, const float* __rest
                        float* __restrict__ metrics, int M, gymrl_ppo_cfg cfg) {
     constexpr int H = 128 * NCH;
     constexpr int P = A * H + A + H + 1;     // [dWa | dba | dWc | dbc]
-    extern __shared__ float s_acc[];
+    constexpr int PS = (P + 3) & ~3;
+    static_assert(A % 4 == 0, "slice offsets must stay 16-byte aligned");
+    extern __shared__ __align__(16) float s_acc[];
     __shared__ float s_met[kHeadsWarps][6];
     const int lane = threadIdx.x & 31, wid = threadIdx.x >> 5;
     const int warp = blockIdx.x * kHeadsWarps + wid, nwarps = gridDim.x * kHeadsWarps;
     pdl_wait();
     pdl_launch_dependents();
-    for (int i = threadIdx.x; i < P; i += blockDim.x) s_acc[i] = 0.f;
     float4 wa[A][NCH], wc[NCH], gwa[A][NCH], gwc[NCH];
     float bav[A];
     // every lane evaluates the same loss, so the scalar sums (A + 1 bias gradients, 6 metrics) are spread over lanes 0..A+6:
@@ -308,27 +309,28 @@ ppo_heads_fused_kernel(const float* __restrict__ h, int ldh, const float* __rest
             st4(dp + H + 128 * j + 4 * lane, dc);
         }
     }
-    __syncthreads();
-    for (int wsel = 0; wsel < kHeadsWarps; ++wsel) {
-        if (wid == wsel) {
+    // every warp writes its register sums into its own [P] slice; then all threads fold the slices in warp order (the same
+    // order of additions as the old one-warp-at-a-time accumulation, which cost eight barrier rounds at the end of the kernel)
+    {
+        float* mine = s_acc + (size_t)wid * PS;                   // slice stride PS: P rounded up to 16 bytes
 #pragma unroll
-            for (int j = 0; j < NCH; ++j) {
+        for (int j = 0; j < NCH; ++j) {
 #pragma unroll
-                for (int a = 0; a < A; ++a) {
-                    float* q = s_acc + (size_t)a * H + 128 * j + 4 * lane;
-                    q[0] += gwa[a][j].x; q[1] += gwa[a][j].y; q[2] += gwa[a][j].z; q[3] += gwa[a][j].w;
-                }
-                float* q = s_acc + A * H + A + 128 * j + 4 * lane;
-                q[0] += gwc[j].x; q[1] += gwc[j].y; q[2] += gwc[j].z; q[3] += gwc[j].w;
-            }
-            if (lane < A) s_acc[A * H + lane] += lane_acc;
-            else if (lane == A) s_acc[A * H + A + H] += lane_acc;
-            else if (lane < A + 7) s_met[wid][lane - A - 1] = lane_acc;
+            for (int a = 0; a < A; ++a) st4(mine + (size_t)a * H + 128 * j + 4 * lane, gwa[a][j]);
+            st4(mine + A * H + A + 128 * j + 4 * lane, gwc[j]);   // A * H + A is a multiple of 4 floats
         }
-        __syncthreads();
+        if (lane < A) mine[A * H + lane] = lane_acc;
+        else if (lane == A) mine[A * H + A + H] = lane_acc;
+        else if (lane < A + 7) s_met[wid][lane - A - 1] = lane_acc;
     }
+    __syncthreads();
     float* out = partials + (size_t)blockIdx.x * P;
-    for (int i = threadIdx.x; i < P; i += blockDim.x) out[i] = s_acc[i];
+    for (int i = threadIdx.x; i < P; i += blockDim.x) {
+        float sum = 0.f;
+#pragma unroll
+        for (int w = 0; w < kHeadsWarps; ++w) sum += s_acc[(size_t)w * PS + i];
+        out[i] = sum;
+    }
     if (metrics) {
         __shared__ double dscratch[32];
         float m[6] = {0.f, 0.f, 0.f, 0.f, 0.f, 0.f};
@@ -369,7 +371,7 @@ extern "C" int gymrl_ppo_heads_fused(const float* d_h, int ldh, const float* d_W
     if (grid < 1) grid = 1;
     GYMRL_REQUIRE(workspace_bytes >= (size_t)grid * P * sizeof(float), "workspace too small: need %zu bytes", (size_t)grid * P * sizeof(float));
     cudaStream_t s = as_stream(stream);
-    const size_t smem = (size_t)P * sizeof(float);
+    const size_t smem = (size_t)kHeadsWarps * ((P + 3) & ~3) * sizeof(float);   // one [P] slice per warp (41 KB at H = 256)
     float* partials = (float*)d_workspace;
     if (H == 256)
         gymrl_launch_pdl(ppo_heads_fused_kernel<2, 4>, dim3(grid), dim3(kHeadsWarps * 32), smem, s, d_h, ldh, d_Wa, d_ba, d_Wc, d_bc, d_row_index, d_action, d_logp_old, d_adv,

@@ -97,8 +97,10 @@ def _ws_everywhere():
     """The dispatcher only sends multi-tile-per-pair shapes to the ws kernel; the tests exercise it at every shape it supports."""
     import os
     os.environ["GYMRL_TC_WS_MIN_TILES"] = "1"
+    os.environ["GYMRL_TC_WS_BN128_MIN_TILES"] = "1"     # widths that are multiples of 128 but not of 256: the BN = 128 pair tiles
     yield
     os.environ.pop("GYMRL_TC_WS_MIN_TILES", None)
+    os.environ.pop("GYMRL_TC_WS_BN128_MIN_TILES", None)
 
 
 def _ws_launches():
@@ -120,7 +122,7 @@ def _flat_with_matrix(w, pad_front=8):
 
 
 @pytest.mark.parametrize("M,N,K,act", [(16384, 512, 256, 1), (16384, 256, 256, 1), (16384 + 128, 256, 256, 0), (20000, 512, 512, 2),
-                                       (16384, 256, 64, 0)])
+                                       (16384, 256, 64, 0), (131072, 128, 128, 0), (4096 + 128, 384, 64, 1), (1000, 128, 256, 2)])
 def test_ws_forward_matches_register_split_kernel_bitwise(modes, M, N, K, act):
     """Same 12 MMAs per 32-k slab on the same hi / lo operand bits, so the TMA-fed persistent kernel must reproduce the
     one-tile-per-CTA kernel BIT FOR BIT — and both are fp32-grade against float64."""
@@ -144,7 +146,8 @@ def test_ws_forward_matches_register_split_kernel_bitwise(modes, M, N, K, act):
     assert torch.equal(y_new, y_old)
 
 
-@pytest.mark.parametrize("M,N,K,act", [(16384, 512, 256, 1), (16384, 256, 256, 2), (16384, 256, 512, 1), (12800, 256, 256, 0)])
+@pytest.mark.parametrize("M,N,K,act", [(16384, 512, 256, 1), (16384, 256, 256, 2), (16384, 256, 512, 1), (12800, 256, 256, 0),
+                                       (131072, 128, 128, 0), (8192, 256, 384, 1)])
 def test_ws_backward_input_matches_register_split_kernel_bitwise(modes, M, N, K, act):
     """dX = (dY W) * act'(h): the ws kernel reads W^T from the transposed weight images as a K-major operand; the old kernel
     stages W MN-major.  The per-slab products are the same numbers, the results must agree to fp32 rounding of the
