@@ -258,31 +258,30 @@ mhc_stage_bwd_a_kernel(const float* __restrict__ h_in, int row_stride, int branc
 // partial row layout: [2D*8 dw | 2D dg | 3 dalpha | 8 dbeta]
 // ---------------------------------------------------------------------------------------------------------------
 template <int NCH>
-__global__ void __launch_bounds__(kWarpsPerBlock * 32)
+__global__ void __launch_bounds__(kWarpsPerBlock * 32, NCH == 1 ? 2 : 1)
 mhc_stage_bwd_b_kernel(const float* __restrict__ h_in, int row_stride, int branch_stride, const float* __restrict__ dh_pre,
                        const float* __restrict__ scratch, const float* __restrict__ dh_partial, float* __restrict__ dh_out,
                        float* __restrict__ dx0, const float* __restrict__ g, const float* __restrict__ w,
                        const float* __restrict__ alpha, float* __restrict__ partials, int M) {
     constexpr int D = 128 * NCH;
     constexpr int P = 2 * D * 8 + 2 * D + 11;
+    constexpr int PS = (P + 3) & ~3;
     const int lane = threadIdx.x & 31, wid = threadIdx.x >> 5;
     const int warp = blockIdx.x * kWarpsPerBlock + wid, nwarps = gridDim.x * kWarpsPerBlock;
-    extern __shared__ float s_acc[];   // [P] block accumulator
+    extern __shared__ __align__(16) float s_acc[];   // [PS] block accumulator | [8][2D] the stage's w, k-major (lane-contiguous float4 reads)
+    float* s_w = s_acc + PS;
     for (int i = threadIdx.x; i < P; i += blockDim.x) s_acc[i] = 0.f;
+    for (int i = threadIdx.x; i < 2 * D * 8; i += blockDim.x) s_w[(i & 7) * 2 * D + (i >> 3)] = w[i];
     __syncthreads();
-    float4 gp[2][NCH], wp[2][NCH][8];
+    // The weights are read from shared memory inside the row loop (16 LDS.128 per row at D = 128) instead of living in 64 registers
+    // per lane: with the 64 accumulator registers the kernel sat at 211 registers = one block per SM, i.e. 8 warps to hide a
+    // row's HBM round trip; at <= 128 registers two blocks are resident.
+    float4 gp[2][NCH];
     float al[3];
 #pragma unroll
     for (int i = 0; i < 2; ++i)
 #pragma unroll
-        for (int j = 0; j < NCH; ++j) {
-            const int c = i * D + 128 * j + 4 * lane;
-            gp[i][j] = ld4(g + c);
-#pragma unroll
-            for (int k = 0; k < 8; ++k)
-                wp[i][j][k] = make_float4(w[(size_t)(c + 0) * 8 + k], w[(size_t)(c + 1) * 8 + k], w[(size_t)(c + 2) * 8 + k],
-                                          w[(size_t)(c + 3) * 8 + k]);
-        }
+        for (int j = 0; j < NCH; ++j) gp[i][j] = ld4(g + i * D + 128 * j + 4 * lane);
 #pragma unroll
     for (int k = 0; k < 3; ++k) al[k] = alpha[k];
     float4 a_w[2][NCH][8], a_g[2][NCH];
@@ -344,7 +343,7 @@ mhc_stage_bwd_b_kernel(const float* __restrict__ h_in, int row_stride, int branc
                 const float4 gh = mul4(gp[i][j], h[i][j]);
 #pragma unroll
                 for (int k = 0; k < 8; ++k) {
-                    wd = axpy4(dH[k], wp[i][j][k], wd);
+                    wd = axpy4(dH[k], *reinterpret_cast<const float4*>(s_w + k * 2 * D + i * D + 128 * j + 4 * lane), wd);
                     a_w[i][j][k] = axpy4(dH[k], gh, a_w[i][j][k]);
                 }
                 a_g[i][j] = add4(a_g[i][j], mul4(h[i][j], wd));
@@ -562,7 +561,7 @@ extern "C" int gymrl_mhc_stage_backward_b(const float* h, int row_stride, int br
     GYMRL_REQUIRE(workspace_bytes >= (size_t)grid * P * sizeof(float), "workspace too small: need %zu bytes",
                   (size_t)grid * P * sizeof(float));
     cudaStream_t s = as_stream(stream);
-    const size_t smem = (size_t)P * sizeof(float);
+    const size_t smem = ((size_t)((P + 3) & ~3) + (size_t)2 * D * 8) * sizeof(float);   // accumulator + the stage's w (k-major)
     if (D == 128) {
         mhc_stage_bwd_b_kernel<1><<<grid, kWarpsPerBlock * 32, smem, s>>>(h, row_stride, branch_stride, dh_pre, scratch, dh_partial, dh, dx0,
                                                                           g, w, alpha, (float*)workspace, M);
