@@ -189,7 +189,7 @@ def gemm_roofline(torch, ops, peaks, peaks_src):
             traffic = None
     from gymrl_b200 import _ffi
     tc = _ffi.load().gymrl_get_gemm_mode() == 1
-    kernel = ("gemm3x_ws_kernel<2> (tcgen05.mma.cta_group::2 kind::tf32, 3 MMAs per fp32 product; B = weights by TMA from pre-split images, "
+    kernel = ("gemm3x_ws_kernel<2, 256> (tcgen05.mma.cta_group::2 kind::tf32, 3 MMAs per fp32 product; B = weights by TMA from pre-split images, "
               "A register-split; persistent, 2 TMEM accumulators, overlapped epilogue; M=16384 N=512 K=256, +bias+tanh)"
               if tc else "gemm_kernel<128,128,8,8,kmajor,kmajor> (fp32 FFMA, M=16384 N=512 K=256, +bias+tanh)")
     return {"bound": "tensor", "kernel": kernel,
@@ -325,7 +325,7 @@ def _make_config_runner(which, torch):
             return {"bound": "hbm", "kernel": "whole lockstep (sumtree_sample / sumtree_update / nstep_push / replay gather + the Q-net GEMMs)",
                     "achieved": ach, "peak": peaks["hbm_gbs"], "unit": "GB/s", "frac": ach / peaks["hbm_gbs"], "traffic": None,
                     "algorithmic_bytes_per_env_step": 925, "peak_source": src,
-                    "note": "pointer-chasing tree walks over a 32 MB float64 tree and ~64 kernels of <= 8192 threads per lockstep: "
+                    "note": "pointer-chasing tree walks over a 32 MB float64 tree and 42 kernels of <= 8192 threads per lockstep (parallel graph branches): "
                             "L2-latency / launch bound, nowhere near the HBM roofline (stated, not hidden)"}
         return tr, step, cfg.num_envs * K, step, roof
     if which == "c4":
@@ -348,7 +348,7 @@ def _make_config_runner(which, torch):
                     "achieved": ach, "peak": peak, "unit": "TFLOP/s", "frac": ach / peak, "traffic": None,
                     "algorithmic_flops_per_env_step": 2.5e6, "peak_source": src + ": dense bf16 cuBLAS, sustained",
                     "path_hbm": {"algorithmic_bytes_per_env_step": 72, "achieved_GBps": 72.0 * value / 1e9, "peak_GBps": peaks["hbm_gbs"]},
-                    "note": "~86 kernels of M = 4096 per lockstep: launch-latency bound (0.4 ms per lockstep), far from either roofline"}
+                    "note": "~84 kernels of M = 4096 per lockstep recorded as a DAG of parallel graph branches: launch-latency bound (0.31 ms per lockstep), far from either roofline"}
         return tr, step, cfg.num_envs * K, step, roof
     if which == "c5":
         from gymrl_b200.algorithms import ppo_full_lunarlander as F
