@@ -143,6 +143,7 @@ class ActorCriticEngine:
         self.deferred_reduce = True   # forward_trunk/backward may run inside an ops.reduce_defer_begin() scope
         # heads + loss + heads backward as one sweep (gymrl_ppo_heads_fused) where the kernel is built for the shape
         self.can_fuse_heads = self.A == 4 and self.H in (128, 256)
+        self.can_fuse_rollout_tail = self.A <= 7 and self.H % 4 == 0     # gymrl_policy_heads_sample (PPO rollout tail)
         # GYMRL_PPO_BRANCHES=1: dW kernels of the trunk backward on a side stream / graph branch (see backward_trunk)
         self.branches = None
         if os.environ.get("GYMRL_PPO_BRANCHES", "0") == "1":
@@ -339,9 +340,17 @@ class PPOTrainer:
     def _rollout_body(self):
         buf, env, net, acts = self.buffer, self.env, self.net, self.acts_roll
         N, A = self.N, self.env.n_actions
+        fused_tail = getattr(net, "can_fuse_rollout_tail", False) and getattr(self.cfg, "fused_rollout_tail", True)
         for t in range(self.T):
-            net.forward(buf.obs[t], acts, N)
-            self._sample_step(acts, t)     # draw index = device counter + t: the counter advances once per rollout, not per step
+            # draw index = device counter + t: the counter advances once per rollout, not per step
+            if fused_tail:
+                # both heads + the categorical sample in one launch (bit-identical to the three it replaces)
+                net.forward_trunk(buf.obs[t], acts, N)
+                ops.policy_heads_sample(acts.ac, net.Wa2, net.ba2, net.Wc2, net.bc2, n=N, seed=self.seed, first_id=self.rank * N, draw=t,
+                                        draw_base=self.ctr_action, action=buf.action[t], logp=buf.log_prob[t], value=buf.value[t])
+            else:
+                net.forward(buf.obs[t], acts, N)
+                self._sample_step(acts, t)
             env.step(buf.action[t], obs=buf.obs[t + 1], reward=buf.reward[t], terminated=self.term, truncated=self.trunc,
                      want_next_obs=False, done=buf.done[t])
         ops.counter_add(self.ctr_action, self.T)

@@ -84,6 +84,99 @@ extern "C" int gymrl_sample_categorical(const float* d_logits, int ld_logits, co
     return GYMRL_OK;
 }
 
+// ---- rollout tail in one launch: actor head + critic head + Categorical sample ----------------------------------------------
+// h [n][2H] = (actor | critic) head-trunk activations; logits = Wa h_a + ba (Wa [A][H]), V = Wc h_c + bc; then exactly what
+// sample_categorical_kernel does on those logits.  One warp per row; the dot products repeat skinny_fwd_kernel's arithmetic
+// (lane-strided float4 FMAs in the same order, the same butterfly), so logits, actions and log-probs are bit-identical to the
+// three separate launches (gymrl_linear_forward x 2 + gymrl_sample_categorical) this replaces in the PPO rollout graph.
+#define PHS_MAX_A 8
+__global__ void __launch_bounds__(256) policy_heads_sample_kernel(const float* __restrict__ h, int ldh, const float* __restrict__ Wa,
+                                                                  const float* __restrict__ ba, const float* __restrict__ Wc,
+                                                                  const float* __restrict__ bc, int H, int A, int32_t* __restrict__ action,
+                                                                  float* __restrict__ logp, float* __restrict__ entropy,
+                                                                  float* __restrict__ value, float* __restrict__ lv_out, int n,
+                                                                  uint64_t seed, uint64_t first_id, uint32_t draw,
+                                                                  const uint32_t* __restrict__ draw_base, int deterministic) {
+    extern __shared__ __align__(16) float sw[];   // [A + 1][H]: Wa rows, then Wc
+    for (int i = threadIdx.x; i < A * H; i += blockDim.x) sw[i] = Wa[i];
+    for (int i = threadIdx.x; i < H; i += blockDim.x) sw[A * H + i] = Wc[i];
+    __syncthreads();
+    if (draw_base) draw += *draw_base;
+    const int lane = threadIdx.x & 31, warp = threadIdx.x >> 5, wpb = blockDim.x >> 5;
+    for (int m = blockIdx.x * wpb + warp; m < n; m += gridDim.x * wpb) {
+        const float* hp = h + (size_t)m * ldh;
+        float acc[PHS_MAX_A + 1];
+#pragma unroll
+        for (int a = 0; a <= PHS_MAX_A; ++a) acc[a] = 0.f;
+        for (int k = lane * 4; k < H; k += 128) {
+            const float4 va = *reinterpret_cast<const float4*>(hp + k);
+            const float4 vc = *reinterpret_cast<const float4*>(hp + H + k);
+#pragma unroll
+            for (int a = 0; a < PHS_MAX_A; ++a) {
+                if (a < A) {
+                    const float4 ww = *reinterpret_cast<const float4*>(&sw[a * H + k]);
+                    acc[a] = fmaf(va.x, ww.x, fmaf(va.y, ww.y, fmaf(va.z, ww.z, fmaf(va.w, ww.w, acc[a]))));
+                }
+            }
+            const float4 wc = *reinterpret_cast<const float4*>(&sw[A * H + k]);
+            acc[PHS_MAX_A] = fmaf(vc.x, wc.x, fmaf(vc.y, wc.y, fmaf(vc.z, wc.z, fmaf(vc.w, wc.w, acc[PHS_MAX_A]))));
+        }
+        float z[PHS_MAX_A], ln[PHS_MAX_A], p[PHS_MAX_A];
+#pragma unroll
+        for (int a = 0; a < PHS_MAX_A; ++a) {
+            if (a < A) z[a] = warp_sum(acc[a]) + ba[a];
+        }
+        const float V = warp_sum(acc[PHS_MAX_A]) + bc[0];
+        normalized_logits(z, A, ln, p);
+        int best = 0;
+        if (deterministic) {
+            float bv = z[0];
+            for (int j = 1; j < A; ++j) if (z[j] > bv) { bv = z[j]; best = j; }
+        } else {
+            float bv = -INFINITY;
+            for (int j = 0; j < A; ++j) {
+                const u32x4 r = philox_draw(seed, first_id + m, draw, PHILOX_ACTION | ((uint32_t)(j >> 2) << 8));
+                const uint32_t w = (j & 3) == 0 ? r.x : ((j & 3) == 1 ? r.y : ((j & 3) == 2 ? r.z : r.w));
+                const float q = -logf(u01_open0_f32(w));
+                const float val = p[j] / q;
+                if (val > bv) { bv = val; best = j; }
+            }
+        }
+        if (lane == 0) {
+            action[m] = best;
+            if (logp) logp[m] = ln[best];
+            if (value) value[m] = V;
+            if (entropy) {
+                float e = 0.f;
+                for (int j = 0; j < A; ++j) e += fmaxf(ln[j], -3.402823466e+38f) * p[j];
+                entropy[m] = -e;
+            }
+            if (lv_out) {
+                for (int j = 0; j < A; ++j) lv_out[(size_t)m * 8 + j] = z[j];
+                lv_out[(size_t)m * 8 + A] = V;
+            }
+        }
+    }
+}
+
+extern "C" int gymrl_policy_heads_sample(const float* d_h, int ldh, const float* d_Wa, const float* d_ba, const float* d_Wc,
+                                         const float* d_bc, int H, int n_actions, int32_t* d_action, float* d_logp, float* d_entropy,
+                                         float* d_value, float* d_lv_out, int n, uint64_t seed, uint64_t first_id, uint32_t draw,
+                                         const uint32_t* d_draw_base, int deterministic, void* stream) {
+    GYMRL_REQUIRE(d_h && d_Wa && d_ba && d_Wc && d_bc && d_action, "NULL pointer");
+    GYMRL_REQUIRE(n > 0 && n_actions > 0 && n_actions <= 7, "bad n=%d or n_actions=%d (max 7)", n, n_actions);
+    GYMRL_REQUIRE(H > 0 && H % 4 == 0 && H <= 2048 && ldh >= 2 * H && ldh % 4 == 0 && ((reinterpret_cast<uintptr_t>(d_h) & 15) == 0),
+                  "h must be a 16-byte aligned [n][>= 2H] matrix with H a multiple of 4");
+    int blocks = ceil_div(n, 8);
+    if (blocks > GYMRL_NUM_SMS * 8) blocks = GYMRL_NUM_SMS * 8;
+    policy_heads_sample_kernel<<<blocks, 256, (size_t)(n_actions + 1) * H * sizeof(float), as_stream(stream)>>>(
+        d_h, ldh, d_Wa, d_ba, d_Wc, d_bc, H, n_actions, d_action, d_logp, d_entropy, d_value, d_lv_out, n, seed, first_id, draw,
+        d_draw_base, deterministic);
+    gymrl_count_launch();
+    GYMRL_LAUNCH_CHECK("policy_heads_sample");
+    return GYMRL_OK;
+}
+
 __global__ void eps_greedy_kernel(const float* __restrict__ q, int ld, int32_t* __restrict__ action, int n, int A,
                                   float eps, uint64_t seed, uint64_t first_id, uint32_t draw, const uint32_t* __restrict__ draw_base,
                                   const float* __restrict__ eps_dev) {

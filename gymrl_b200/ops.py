@@ -128,6 +128,18 @@ def sample_categorical(logits, noise=None, *, seed=0, first_id=0, draw=0, draw_b
     return action, logp, entropy
 
 
+def policy_heads_sample(h, Wa, ba, Wc, bc, *, n=None, seed=0, first_id=0, draw=0, draw_base=None, deterministic=False, action=None,
+                        logp=None, entropy=None, value=None, lv_out=None):
+    """Actor head + critic head + Categorical sample over h [n, 2H] = (actor | critic) in one launch (the PPO rollout tail)."""
+    n = h.shape[0] if n is None else n
+    A, H = Wa.shape
+    action = torch.empty(n, device=h.device, dtype=i32) if action is None else action
+    check(load().gymrl_policy_heads_sample(ptr(h, f32), _ld(h), ptr(Wa, f32), ptr(ba, f32), ptr(Wc, f32), ptr(bc, f32), int(H), int(A),
+                                           ptr(action, i32), ptr(logp, f32), ptr(entropy, f32), ptr(value, f32), ptr(lv_out, f32), int(n),
+                                           seed, first_id, draw, ptr(draw_base, i32), int(deterministic), stream_ptr()))
+    return action
+
+
 def select_eps_greedy(q, eps, *, seed=0, first_id=0, draw=0, draw_base=None, action=None):
     """eps: a Python float, or a device float32 tensor of one element (read by the kernel: capture-safe schedules)."""
     n, a = q.shape

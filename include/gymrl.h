@@ -106,6 +106,14 @@ int gymrl_sample_categorical(const float* d_logits, int ld_logits, const float* 
                              const float* d_value_in, int ld_value_in, float* d_value_out, int n, int n_actions,
                              uint64_t seed, uint64_t first_id, uint32_t draw, const uint32_t* d_draw_base,
                              int deterministic, void* stream);
+/* The tail of a PPO rollout step in one launch (ActorCritic.get_action, algorithms/ppo_lunarlander.py:92-104, on the engine's
+ * fused head-trunk activations d_h [n][2H] = (actor | critic)): logits = Wa h_a + ba (Wa [A][H]), V = Wc h_c + bc, then
+ * gymrl_sample_categorical on those logits — bit-identical to gymrl_linear_forward x 2 + gymrl_sample_categorical (same
+ * summation order, same Philox keys).  d_logp / d_entropy / d_value / d_lv_out ([n][8] = logits | V) are nullable. */
+int gymrl_policy_heads_sample(const float* d_h, int ldh, const float* d_Wa, const float* d_ba, const float* d_Wc,
+                              const float* d_bc, int H, int n_actions, int32_t* d_action, float* d_logp, float* d_entropy,
+                              float* d_value, float* d_lv_out, int n, uint64_t seed, uint64_t first_id, uint32_t draw,
+                              const uint32_t* d_draw_base, int deterministic, void* stream);
 /* epsilon-greedy over Q-values (DQNTrainer.select_action, algorithms/dqn_cartpole.py:124-133).
  * Per env: u ~ U[0,1); if u < eps: uniform random action else argmax (first max). */
 int gymrl_select_eps_greedy(const float* d_q, int ld_q, int32_t* d_action, int n, int n_actions,

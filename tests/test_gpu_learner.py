@@ -598,3 +598,29 @@ def test_sum_sumsq_and_grad_sumsq_fixed_order(ops):
     s = outs[0][0].clone()
     ops.sum_sumsq(x, s)
     np.testing.assert_allclose(s.cpu().numpy(), 2 * outs[0][0].cpu().numpy(), rtol=1e-15)
+
+
+def test_policy_heads_sample_equals_separate_launches(ops):
+    """The fused rollout tail (actor head + critic head + Categorical sample) must be BIT-identical to
+    gymrl_linear_forward x 2 + gymrl_sample_categorical: same summation order, same Philox keys."""
+    g = torch.Generator().manual_seed(11)
+    for (N, H, A) in [(4096 + 3, 256, 4), (77, 128, 2), (1000, 64, 7)]:
+        h = torch.tanh(torch.randn(N, 2 * H, generator=g)).cuda()
+        Wa, ba = (torch.randn(A, H, generator=g) / H ** 0.5).cuda(), torch.randn(A, generator=g).cuda()
+        Wc, bc = (torch.randn(1, H, generator=g) / H ** 0.5).cuda(), torch.randn(1, generator=g).cuda()
+        lv = torch.zeros(N, 8, device="cuda")
+        ops.linear_forward(h[:, :H], Wa, ba, 0, out=lv[:, :A])
+        ops.linear_forward(h[:, H:], Wc, bc, 0, out=lv[:, A:A + 1])
+        ctr = torch.tensor([5], device="cuda", dtype=torch.int32)
+        v0 = torch.zeros(N, device="cuda")
+        a0, lp0, e0 = ops.sample_categorical(lv[:, :A], seed=3, first_id=17, draw=2, draw_base=ctr, want_entropy=True,
+                                             value_in=lv[:, A:A + 1], value_out=v0)
+        lp1, e1, v1 = (torch.zeros(N, device="cuda") for _ in range(3))
+        lv1 = torch.zeros(N, 8, device="cuda")
+        a1 = ops.policy_heads_sample(h, Wa, ba, Wc, bc, seed=3, first_id=17, draw=2, draw_base=ctr, logp=lp1, entropy=e1, value=v1,
+                                     lv_out=lv1)
+        assert torch.equal(lv1[:, :A + 1], lv[:, :A + 1])
+        assert torch.equal(a1, a0) and torch.equal(lp1, lp0) and torch.equal(e1, e0) and torch.equal(v1, v0)
+        d0 = ops.sample_categorical(lv[:, :A], deterministic=True)[0]
+        d1 = ops.policy_heads_sample(h, Wa, ba, Wc, bc, deterministic=True)
+        assert torch.equal(d1, d0)
