@@ -99,6 +99,8 @@ class DuelingEngine:
             self.dout = z(M, A + 1)
             self.dW, self.db = z(A + 1, H), z(A + 1)
             self.ws = torch.empty(ops.backward_weight_workspace(M, A + 1, H), device=dev, dtype=torch.uint8)
+            from ..graphs import Branches
+            self._br = Branches(1)
 
     def _layers(self):
         fp, A = self.fp, self.A
@@ -134,17 +136,23 @@ class DuelingEngine:
         return ops.linear_forward(h, self.W, self.b, NONE, out=self.out, M=M)
 
     def backward(self, x, M, row_index=None):
-        """Given self.dout = dL/d[adv | value]."""
+        """Given self.dout = dL/d[adv | value].  The head's parameter gradients do not feed the trunk's backward pass: two branches."""
         fp, A = self.fp, self.A
-        ops.linear_backward_weight(self.dout, self.trunk.out, self.dW, self.db, workspace=self.ws, M=M)
-        off.noisy_backward2(dict(dw=self.dW[:A], db=self.db[:A], eps_in=self.eps_in_a, eps_out=self.eps_out_a,
-                                 dw_mu=fp.g("advantage.weight_mu"), dw_sigma=fp.g("advantage.weight_sigma"),
-                                 db_mu=fp.g("advantage.bias_mu"), db_sigma=fp.g("advantage.bias_sigma")),
-                            dict(dw=self.dW[A:], db=self.db[A:], eps_in=self.eps_in_v, eps_out=self.eps_out_v,
-                                 dw_mu=fp.g("value.weight_mu"), dw_sigma=fp.g("value.weight_sigma"),
-                                 db_mu=fp.g("value.bias_mu"), db_sigma=fp.g("value.bias_sigma")), self.H)
-        ops.linear_backward_input(self.dout[:M], self.W, self.trunk.out, RELU, out=self.trunk.dout)
-        self.trunk.backward(x, M, row_index=row_index)
+
+        def head_grads():
+            ops.linear_backward_weight(self.dout, self.trunk.out, self.dW, self.db, workspace=self.ws, M=M)
+            off.noisy_backward2(dict(dw=self.dW[:A], db=self.db[:A], eps_in=self.eps_in_a, eps_out=self.eps_out_a,
+                                     dw_mu=fp.g("advantage.weight_mu"), dw_sigma=fp.g("advantage.weight_sigma"),
+                                     db_mu=fp.g("advantage.bias_mu"), db_sigma=fp.g("advantage.bias_sigma")),
+                                dict(dw=self.dW[A:], db=self.db[A:], eps_in=self.eps_in_v, eps_out=self.eps_out_v,
+                                     dw_mu=fp.g("value.weight_mu"), dw_sigma=fp.g("value.weight_sigma"),
+                                     db_mu=fp.g("value.bias_mu"), db_sigma=fp.g("value.bias_sigma")), self.H)
+
+        def trunk():
+            ops.linear_backward_input(self.dout[:M], self.W, self.trunk.out, RELU, out=self.trunk.dout)
+            self.trunk.backward(x, M, row_index=row_index)
+
+        self._br.run(trunk, head_grads)
 
 
 class SumTree(off.DeviceSumTree):
