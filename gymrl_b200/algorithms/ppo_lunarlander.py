@@ -475,7 +475,10 @@ class PPOTrainer:
         torch.cuda.synchronize()
         g = torch.cuda.CUDAGraph()
         c0 = _ffi.launch_count()
-        with torch.cuda.graph(g, capture_error_mode=error_mode):
+        # with side branches (GYMRL_PPO_BRANCHES=1) the main chain is captured on a high-priority stream, so the dX kernels of the
+        # critical path win the SMs over the dW kernels of the side branch
+        cap_stream = torch.cuda.Stream(priority=-1) if getattr(self.net, "branches", None) is not None else None
+        with torch.cuda.graph(g, stream=cap_stream, capture_error_mode=error_mode):
             fn()
         g.n_kernels = _ffi.launch_count() - c0   # our kernels recorded in this graph (one launch call each)
         return g

@@ -39,6 +39,9 @@ class Chain:
             self.ws_l = [torch.empty(ops.backward_weight_workspace(self.M, W.shape[0], W.shape[1]), device=dev, dtype=torch.uint8)
                          for (W, _, _, _, _) in self.layers]
             self.dx = torch.zeros(self.M, self.layers[0][0].shape[1], device=dev, dtype=f32)
+            if len(self.layers) > 1 and self.M <= self.BRANCH_MAX_ROWS:
+                from .graphs import Branches
+                self._br = Branches(len(self.layers))      # created here, never inside a graph capture
 
     @staticmethod
     def from_names(fp: FlatParams, specs: Sequence[Tuple[str, str, int]], max_batch: int, backward: bool = True) -> "Chain":
@@ -84,13 +87,10 @@ class Chain:
             elif input_grad:
                 ops.linear_backward_input(self.d[0][:M], W, None, _ffi.ACT_NONE, out=self.dx)
 
-        if param_grads and L > 1 and M <= self.BRANCH_MAX_ROWS:
+        if param_grads and self._br is not None and M <= self.BRANCH_MAX_ROWS:
             # small batches (off-policy updates): a layer's weight gradient does not feed the chain of input gradients, so every
             # layer's dW launches (GEMM / sweep + fold) run as a side branch of their own next to the dX chain.  At PPO's minibatch sizes the
             # GEMMs fill the chip and nothing overlaps (measured slower there), hence the row limit.
-            if self._br is None:
-                from .graphs import Branches
-                self._br = Branches(L)
             main = torch.cuda.current_stream()
             for l in range(L - 1, -1, -1):
                 side = self._br.side[l]
