@@ -402,3 +402,67 @@ def test_graph_lockstep_equals_eager_lockstep(algo):
     assert torch.equal(ca, cb) and torch.equal(oa, ob) and torch.equal(ra, rb)
     for a, b in zip(pa, pb):
         torch.testing.assert_close(a, b, rtol=1e-6, atol=1e-7)
+
+
+@pytest.mark.parametrize("cap", [37, 4096, 20000, 1 << 21])
+def test_sumtree_invariant_and_determinism_full_size(cap):
+    """Properties of the batched tree writes that hold at any size (C3's capacity 2^21 included): after every batch each internal
+    node is EXACTLY fl(left + right) (so the root is the tree-order pairwise sum of the leaves), duplicates resolve last-writer-
+    wins in batch order, the scratch is left clean, and the same batches give bitwise the same tree."""
+    from gymrl_b200 import ops_offpolicy as off
+    g = torch.Generator().manual_seed(cap)
+    n = min(8192, 4 * cap)
+
+    def run():
+        t = off.DeviceSumTree(cap, torch.device("cuda"))
+        ring = torch.tensor([0, 0], device="cuda", dtype=i32)
+        leaves = np.zeros(cap)
+        gg = torch.Generator().manual_seed(cap + 1)
+        for b in range(4):
+            idx = torch.randint(0, cap, (n,), generator=gg, dtype=torch.int32)
+            idx[1::7] = idx[0]                                     # heavy duplication of one leaf
+            pr = torch.rand(n, generator=gg, dtype=torch.float64) + 0.01
+            t.update(idx.cuda(), pr.cuda())
+            for i, p in zip(idx.tolist(), pr.tolist()):           # the reference's loop: last writer wins
+                leaves[i] = p
+        m = min(cap, 8192)
+        ring[0] = cap - m // 2                                     # a wrapped store range, priority = max(leaves)
+        ring[1] = cap
+        t.store_new(m, ring)
+        pos = (np.arange(m) + cap - m // 2) % cap
+        leaves[pos] = leaves.max()
+        return t, leaves
+
+    t, leaves = run()
+    tree = t.tree.cpu().numpy()
+    assert np.array_equal(tree[cap - 1:], leaves)
+    internal = np.arange(cap - 1)
+    assert np.array_equal(tree[internal], tree[2 * internal + 1] + tree[2 * internal + 2])       # exact, every node
+    np.testing.assert_allclose(tree[0], leaves.sum(), rtol=1e-12)
+    w = t.winner.cpu().numpy()
+    assert (w[:cap] == -1).all() and (w[cap:] == 0).all()                                        # scratch restored
+    assert float(t.max_scratch.item()) == 0.0 and t.u32_scratch.tolist() == [0, 0]
+    t2, _ = run()
+    assert torch.equal(t.tree, t2.tree)                                                          # bitwise reproducible
+
+
+def test_replay_store_all_wraps_like_a_deque():
+    """gymrl_replay_store_all: five fields + the ring advance in one launch, wrapping at the capacity (deque(maxlen) semantics)."""
+    from gymrl_b200 import ops_offpolicy as off
+    cap, D, A = 1000, 3, 2
+    ring = off.ReplayRing(cap, D, A, False, torch.device("cuda"))
+    ref = {k: np.zeros(s, np.float32) for k, s in (("obs", (cap, D)), ("nobs", (cap, D)), ("act", (cap, A)), ("rew", (cap,)), ("done", (cap,)))}
+    rng = np.random.default_rng(0)
+    cursor = size = 0
+    for n in (400, 400, 400, 7, 1000):
+        o, o2 = rng.standard_normal((n, D)).astype(np.float32), rng.standard_normal((n, D)).astype(np.float32)
+        a, r = rng.standard_normal((n, A)).astype(np.float32), rng.standard_normal(n).astype(np.float32)
+        d = (rng.random(n) < 0.3).astype(np.uint8)
+        ring.store(cu(o), cu(a), cu(r), cu(o2), cu(d))
+        pos = (cursor + np.arange(n)) % cap
+        ref["obs"][pos], ref["nobs"][pos], ref["act"][pos], ref["rew"][pos], ref["done"][pos] = o, o2, a, r, d.astype(np.float32)
+        cursor, size = (cursor + n) % cap, min(cap, size + n)
+        assert ring.state.tolist() == [cursor, size] and len(ring) == size
+    assert np.array_equal(ring.obs.cpu().numpy(), ref["obs"]) and np.array_equal(ring.next_obs.cpu().numpy(), ref["nobs"])
+    assert np.array_equal(ring.action.cpu().numpy(), ref["act"]) and np.array_equal(ring.reward.cpu().numpy(), ref["rew"])
+    assert np.array_equal(ring.done.cpu().numpy(), ref["done"]) and int(ring._done_ctr.item()) == 0
