@@ -49,6 +49,8 @@ SIGNATURES = {
     "gymrl_env_set_state": (c_int, [_P, _P, _P]),
     "gymrl_env_set_profile": (c_int, [_P, _P]),
     "gymrl_env_overflow_count": (c_int, [_P, _P, _P]),
+    "gymrl_env_set_solver": (c_int, [_P, c_int]),
+    "gymrl_env_get_solver": (c_int, [_P, _P]),
     "gymrl_env_episode_stats": (c_int, [_P, c_int, _P, _P, _P, _P]),
     "gymrl_policy_heads_sample": (c_int, [_P, c_int, _P, _P, _P, _P, c_int, c_int, _P, _P, _P, _P, _P, c_int, c_u64, c_u64, c_u32, _P, c_int, _P]),
     "gymrl_sample_categorical": (c_int, [_P, c_int, _P, _P, _P, _P, _P, c_int, _P, c_int, c_int, c_u64, c_u64, c_u32, _P, c_int, _P]),

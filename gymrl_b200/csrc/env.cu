@@ -357,6 +357,19 @@ extern "C" int gymrl_env_set_profile(gymrl_env* e, long long* d_prof) {
     return GYMRL_OK;
 }
 
+extern "C" int gymrl_env_set_solver(gymrl_env* e, int variant) {
+    GYMRL_REQUIRE(e != nullptr, "env is NULL");
+    GYMRL_REQUIRE(variant == 0 || variant == 1, "unknown solver variant %d (0 or 1)", variant);
+    GYMRL_REQUIRE(e->kind == GYMRL_ENV_LUNARLANDER || variant == 0, "solver variants exist for LunarLander only");
+    e->solver = variant;
+    return GYMRL_OK;
+}
+extern "C" int gymrl_env_get_solver(gymrl_env* e, int* variant) {
+    GYMRL_REQUIRE(e != nullptr && variant != nullptr, "NULL argument");
+    *variant = e->solver;
+    return GYMRL_OK;
+}
+
 extern "C" int gymrl_env_overflow_count(gymrl_env* e, uint64_t* count, void* stream) {
     GYMRL_REQUIRE(e != nullptr && count != nullptr, "NULL argument");
     unsigned long long c = 0;

@@ -32,6 +32,7 @@ struct gymrl_env {
     int32_t* order;          // [N] env ids, heavy first
     int32_t* order_cnt;      // [2] = {heavy count, heavy envs per warp}
     long long* prof;         // nullable diagnostic buffer [N][8], see gymrl_env_set_profile
+    int solver;              // LunarLander solver loop variant (gymrl_env_set_solver; same results bit for bit)
     // shared bookkeeping, all [N]
     int32_t* elapsed;     // TimeLimit counter
     uint32_t* episode;    // episodes started so far (keys the reset draws)
@@ -69,5 +70,6 @@ int lunar_step(gymrl_env* e, const int32_t* actions, float* obs, float* next_obs
                uint8_t* terminated, uint8_t* truncated, uint8_t* done, cudaStream_t s);
 int lunar_get_state(gymrl_env* e, double* state, cudaStream_t s);
 int lunar_set_state(gymrl_env* e, const double* state, cudaStream_t s);
+int lunar_default_solver();
 
 void gymrl_count_launch(int n = 1);

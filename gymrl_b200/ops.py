@@ -98,6 +98,15 @@ class VecEnv:
         self._prof = buf
         check(load().gymrl_env_set_profile(self._h, ptr(buf, torch.int64) if buf is not None else None))
 
+    def set_solver(self, variant: int) -> None:
+        """LunarLander: arrangement of the solver loops in the step kernel (0 / 1, bit-identical results; see gymrl.h)."""
+        check(load().gymrl_env_set_solver(self._h, int(variant)))
+
+    def get_solver(self) -> int:
+        v = C.c_int()
+        check(load().gymrl_env_get_solver(self._h, C.byref(v)))
+        return int(v.value)
+
     def overflow_count(self) -> int:
         """LunarLander: touching manifolds dropped because all 8 contact slots of an env copy were taken (see gymrl.h)."""
         c = C.c_uint64()

@@ -80,6 +80,12 @@ int gymrl_env_set_state(gymrl_env* env, const double* d_state, void* stream);
  * subsequent step with {step cycles, collide, constraint setup, velocity iterations, position iterations (cycles),
  * touching manifolds, position iterations run, work slot}.  NULL switches it off (the default). */
 int gymrl_env_set_profile(gymrl_env* env, long long* d_prof);
+/* LunarLander only (no reference counterpart): which arrangement of the constraint-solver loops the step kernel runs.
+ * 0 = rows in the oracle's order; 1 = a joint row beside a contact row of the other leg (shorter dependency chain).  Both give
+ * the same results bit for bit (tests/test_gpu_envs.py, tests/test_hostsim_lunar.py); the setter exists for A/B timing and for
+ * those tests.  A new env starts with the library default (environment variable GYMRL_LL_SOLVER overrides it). */
+int gymrl_env_set_solver(gymrl_env* env, int variant);
+int gymrl_env_get_solver(gymrl_env* env, int* variant);
 /* LunarLander keeps at most 8 touching manifolds per env copy (the device solver's contact slots; Box2D's contact list is
  * unbounded).  A ninth is dropped — in the CUDA env and in the CPU oracle alike — and counted here: the number of such events
  * since the env was created (synchronises the stream; 0 for the other envs).  Convergence runs report it (observed: 0). */

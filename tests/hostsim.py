@@ -43,8 +43,10 @@ def build(variant=0, force=False):
     if cc is None:
         raise RuntimeError("nvcc not found: the host build of env_lunar.cu needs the CUDA toolkit (no GPU)")
     _BUILD.mkdir(exist_ok=True)
+    # variant 2 = variant 1 with the "division operand out of range" flag forced on about half of the steps (repeat path)
+    solver, extra = (1, ["-DLL_HOSTSIM_FORCE_BAD=1"]) if variant == 2 else (variant, [])
     cmd = [cc, "-O3", "-std=c++17", "-Xcompiler", "-fPIC", "-Xcompiler", "-fno-strict-aliasing", "-Xcompiler", "-ffp-contract=off",
-           "-Xcompiler", "-mfma", "--expt-relaxed-constexpr", "-fmad=false", "-DGYMRL_HOSTSIM", f"-DLL_SOLVER_VARIANT={variant}",
+           "-Xcompiler", "-mfma", "--expt-relaxed-constexpr", "-fmad=false", "-DGYMRL_HOSTSIM", f"-DLL_SOLVER_VARIANT={solver}", *extra,
            "-gencode", "arch=compute_100a,code=sm_100a", "-shared", "-o", str(out), str(_SRC)]
     r = subprocess.run(cmd, capture_output=True, text=True)
     if r.returncode != 0:
@@ -61,7 +63,7 @@ def lib(variant=0):
         L.gymrl_hostsim_lunar_reset.restype = None
         L.gymrl_hostsim_lunar_step.argtypes = [C.c_void_p, C.c_int, C.c_uint64, C.c_uint64] + [C.c_void_p] * 6
         L.gymrl_hostsim_lunar_step.restype = None
-        assert L.gymrl_hostsim_solver_variant() == variant
+        assert L.gymrl_hostsim_solver_variant() == (1 if variant == 2 else variant)
         _libs[variant] = L
     return _libs[variant]
 
