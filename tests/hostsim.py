@@ -20,6 +20,10 @@ _ROOT = Path(__file__).resolve().parent.parent
 _SRC = _ROOT / "gymrl_b200" / "csrc" / "env_lunar.cu"
 _BUILD = Path(__file__).resolve().parent / "_build"
 _libs = {}
+# host build -> (solver variant of env_lunar.cu, force the "division operand out of its window" flag on about half of the steps so
+# that the repeat path runs).  Solver 0 = the oracle's row order; 1 = joint rows beside the other leg's contact rows + div_chain;
+# 2 = the oracle's order with div_chain in the position iterations; 3 = 2 + the velocity loop specialised on the joints' limit states.
+BUILDS = {0: (0, False), 1: (1, False), 2: (1, True), 3: (2, False), 4: (2, True), 5: (3, False)}
 
 
 def nvcc():
@@ -43,8 +47,8 @@ def build(variant=0, force=False):
     if cc is None:
         raise RuntimeError("nvcc not found: the host build of env_lunar.cu needs the CUDA toolkit (no GPU)")
     _BUILD.mkdir(exist_ok=True)
-    # variant 2 = variant 1 with the "division operand out of range" flag forced on about half of the steps (repeat path)
-    solver, extra = (1, ["-DLL_HOSTSIM_FORCE_BAD=1"]) if variant == 2 else (variant, [])
+    solver, force_bad = BUILDS[variant]
+    extra = ["-DLL_HOSTSIM_FORCE_BAD=1"] if force_bad else []
     cmd = [cc, "-O3", "-std=c++17", "-Xcompiler", "-fPIC", "-Xcompiler", "-fno-strict-aliasing", "-Xcompiler", "-ffp-contract=off",
            "-Xcompiler", "-mfma", "--expt-relaxed-constexpr", "-fmad=false", "-DGYMRL_HOSTSIM", f"-DLL_SOLVER_VARIANT={solver}", *extra,
            "-gencode", "arch=compute_100a,code=sm_100a", "-shared", "-o", str(out), str(_SRC)]
@@ -63,7 +67,7 @@ def lib(variant=0):
         L.gymrl_hostsim_lunar_reset.restype = None
         L.gymrl_hostsim_lunar_step.argtypes = [C.c_void_p, C.c_int, C.c_uint64, C.c_uint64] + [C.c_void_p] * 6
         L.gymrl_hostsim_lunar_step.restype = None
-        assert L.gymrl_hostsim_solver_variant() == (1 if variant == 2 else variant)
+        assert L.gymrl_hostsim_solver_variant() == BUILDS[variant][0]
         _libs[variant] = L
     return _libs[variant]
 
