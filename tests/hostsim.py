@@ -23,7 +23,7 @@ _libs = {}
 # host build -> (solver variant of env_lunar.cu, force the "division operand out of its window" flag on about half of the steps so
 # that the repeat path runs).  Solver 0 = the oracle's row order; 1 = joint rows beside the other leg's contact rows + div_chain;
 # 2 = the oracle's order with div_chain in the position iterations; 3 = 2 + the velocity loop specialised on the joints' limit states.
-BUILDS = {0: (0, False), 1: (1, False), 2: (1, True), 3: (2, False), 4: (2, True), 5: (3, False)}
+BUILDS = {0: (0, False), 1: (1, False), 2: (1, True), 3: (2, False), 4: (2, True), 5: (3, False), 6: (4, False), 7: (4, True)}
 
 
 def nvcc():
