@@ -359,7 +359,7 @@ extern "C" int gymrl_env_set_profile(gymrl_env* e, long long* d_prof) {
 
 extern "C" int gymrl_env_set_solver(gymrl_env* e, int variant) {
     GYMRL_REQUIRE(e != nullptr, "env is NULL");
-    GYMRL_REQUIRE(variant >= 0 && variant <= 4, "unknown solver variant %d (0 .. 4)", variant);
+    GYMRL_REQUIRE(variant == 0 || variant == 2 || variant == 3, "unknown solver variant %d (0, 2 or 3)", variant);
     GYMRL_REQUIRE(e->kind == GYMRL_ENV_LUNARLANDER || variant == 0, "solver variants exist for LunarLander only");
     e->solver = variant;
     return GYMRL_OK;

@@ -99,7 +99,7 @@ class VecEnv:
         check(load().gymrl_env_set_profile(self._h, ptr(buf, torch.int64) if buf is not None else None))
 
     def set_solver(self, variant: int) -> None:
-        """LunarLander: arrangement of the solver loops in the step kernel (0 .. 3, bit-identical results; see gymrl.h)."""
+        """LunarLander: arrangement of the solver loops in the step kernel (0, 2 or 3: bit-identical results; see gymrl.h)."""
         check(load().gymrl_env_set_solver(self._h, int(variant)))
 
     def get_solver(self) -> int:

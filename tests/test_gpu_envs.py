@@ -106,7 +106,7 @@ def _heuristic(s):
     return a
 
 
-@pytest.mark.parametrize("solver", [0, 1, 2, 3, 4])
+@pytest.mark.parametrize("solver", [0, 2, 3])
 def test_lunarlander_bit_exact(solver):
     from oracle.lunar import LunarLanderVec
     ops = _ops()
@@ -128,7 +128,7 @@ def test_lunarlander_bit_exact(solver):
     assert total >= N  # every env finished at least once (crash, landing or timeout paths all exercised)
 
 
-@pytest.mark.parametrize("solver", [0, 1, 2, 3, 4])
+@pytest.mark.parametrize("solver", [0, 2, 3])
 def test_lunarlander_teacher_forced_single_steps(solver):
     """set_state from the oracle, one step, compare: isolates single-step arithmetic from trajectory divergence."""
     from oracle.lunar import LunarLanderVec
@@ -151,12 +151,13 @@ def test_lunarlander_teacher_forced_single_steps(solver):
 def test_lunarlander_solver_variants_agree_at_size():
     """The arrangements of the solver loops (gymrl_env_set_solver) give the same bits: 2048 copies x 400 steps of a heuristic /
     random / no-op mix (landings, crashes, sleeping copies, time-outs), every output of every step and the final state snapshot.
-    Variants 1 - 4 replace div.rn by its fast sequence inside the position iterations and repeat the phase with the plain
+    Variants 2 and 3 replace div.rn by its fast sequence inside the position iterations and repeat the phase with the plain
     operator when an operand leaves the sequence's exponent window - this is the test of that claim at size."""
     ops = _ops()
     N = 2048
-    envs = [ops.VecEnv("LunarLander-v3", N, seed=21) for _ in range(5)]
-    for v, env in enumerate(envs):
+    variants = (0, 2, 3)
+    envs = [ops.VecEnv("LunarLander-v3", N, seed=21) for _ in variants]
+    for v, env in zip(variants, envs):
         env.set_solver(v)
     o = [env.reset().clone() for env in envs]
     assert all(torch.equal(o[0], x) for x in o[1:])
@@ -168,14 +169,16 @@ def test_lunarlander_solver_variants_agree_at_size():
         act = np.where(idx % 3 == 0, _heuristic(ob), np.where(idx % 3 == 1, rng.integers(0, 4, N), 0)).astype(np.int32)
         a = torch.as_tensor(act, device="cuda")
         r = [env.step(a) for env in envs]
-        for v in (1, 2, 3, 4):
-            for x, y in zip(r[0], r[v]):
-                assert torch.equal(x, y), f"step {t}, solver {v}"
+        for k in range(1, len(envs)):
+            for x, y in zip(r[0], r[k]):
+                assert torch.equal(x, y), f"step {t}, solver {variants[k]}"
         obs = r[0][0].clone()
     s0 = envs[0].get_state()
     assert all(torch.equal(s0, env.get_state()) for env in envs[1:])
     totals = [env.episode_stats(100)[2] for env in envs]
     assert totals[0] >= N // 2 and all(t == totals[0] for t in totals)
+    with pytest.raises(RuntimeError, match="unknown solver variant"):
+        envs[0].set_solver(1)
 
 
 def test_shard_independence():
