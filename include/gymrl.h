@@ -81,8 +81,9 @@ int gymrl_env_set_state(gymrl_env* env, const double* d_state, void* stream);
  * touching manifolds, position iterations run, work slot}.  NULL switches it off (the default). */
 int gymrl_env_set_profile(gymrl_env* env, long long* d_prof);
 /* LunarLander only (no reference counterpart): which arrangement of the constraint-solver loops the step kernel runs.
- * 0 = the oracle's arrangement with the plain division; 2 = the position rows' divisions evaluated branch-free; 3 = 2 + the
- * velocity loop specialised on the joints' limit states (the default: the fastest measured).  All give the same results bit for
+ * 0 = the oracle's arrangement with the plain division; 2 = the position rows' divisions evaluated branch-free (the default:
+ * never slower than 0); 3 = 2 + the velocity loop specialised on the joints' limit states (fastest under a fresh policy, slower
+ * once the copies of a warp stop sharing their limit states - see env_lunar.cu).  All give the same results bit for
  * bit (tests/test_gpu_envs.py, tests/test_hostsim_lunar.py); the setter exists for A/B timing and for those tests.  A new env
  * starts with the library default (environment variable GYMRL_LL_SOLVER overrides it). */
 int gymrl_env_set_solver(gymrl_env* env, int variant);
