@@ -21,8 +21,8 @@ _SRC = _ROOT / "gymrl_b200" / "csrc" / "env_lunar.cu"
 _BUILD = Path(__file__).resolve().parent / "_build"
 _libs = {}
 # host build -> (solver variant of env_lunar.cu, force the "division operand out of its window" flag on about half of the steps so
-# that the repeat path runs).  Solver 0 = the oracle's arrangement, plain division; 2 = div_chain in the position iterations;
-# 3 = 2 + the velocity loop specialised on the joints' limit states (the shipping default).
+# that the repeat path runs).  Solver 0 = the oracle's arrangement, plain division; 2 = div_chain in the position iterations (the
+# shipping default); 3 = 2 + the velocity loop specialised on the joints' limit states.
 BUILDS = {0: (0, False), 1: (2, False), 2: (2, True), 3: (3, False), 4: (3, True)}
 
 
